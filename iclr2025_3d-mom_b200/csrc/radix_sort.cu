@@ -1,0 +1,187 @@
+// Onesweep LSD radix sort, see radix_sort.cuh.
+#include "radix_sort.cuh"
+
+namespace b200gs {
+
+namespace {
+
+constexpr u32 LB_AGG = 1u << 30;     // tile aggregate published
+constexpr u32 LB_INCL = 1u << 31;    // inclusive prefix published
+constexpr u32 LB_VALUE = (1u << 30) - 1;
+
+struct DigitSpec { int shift[RS_MAX_PASSES]; u32 mask[RS_MAX_PASSES]; };
+
+// One read of the keys builds the digit histogram of every pass.
+__global__ void __launch_bounds__(256)
+rs_histogram(const u32* __restrict__ keys, u32 n, int passes, DigitSpec spec, u32* __restrict__ g_hist)
+{
+    __shared__ u32 s_hist[RS_MAX_PASSES * RS_RADIX];
+    for (int i = threadIdx.x; i < passes * RS_RADIX; i += 256) s_hist[i] = 0;
+    __syncthreads();
+    const u32 stride = gridDim.x * 256;
+    const u32 gtid = blockIdx.x * 256 + threadIdx.x;
+    const u32 n4 = n >> 2;
+    const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+    auto add = [&](u32 k) {
+#pragma unroll
+        for (int p = 0; p < RS_MAX_PASSES; ++p)
+            if (p < passes) atomicAdd(&s_hist[p * RS_RADIX + ((k >> spec.shift[p]) & spec.mask[p])], 1u);
+    };
+    for (u32 i = gtid; i < n4; i += stride) {
+        uint4 k = __ldg(k4 + i);
+        add(k.x); add(k.y); add(k.z); add(k.w);
+    }
+    for (u32 i = (n4 << 2) + gtid; i < n; i += stride) add(keys[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * RS_RADIX; i += 256) {
+        u32 c = s_hist[i];
+        if (c) atomicAdd(&g_hist[i], c);
+    }
+}
+
+// Turns each pass's histogram into exclusive digit bases.
+__global__ void __launch_bounds__(256) rs_scan_hist(u32* __restrict__ g_hist)
+{
+    __shared__ u32 s_warp[8];
+    u32* h = g_hist + blockIdx.x * RS_RADIX;
+    u32 v = h[threadIdx.x];
+    h[threadIdx.x] = block_exclusive_scan_256(v, s_warp);
+}
+
+template <bool HAS_VALS>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_onesweep_pass(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in,
+                 u32* __restrict__ keys_out, u32* __restrict__ vals_out, u32 n, int shift, u32 mask,
+                 const u32* __restrict__ g_base, u32* lookback, u32* ticket)
+{
+    __shared__ u32 s_warp_hist[RS_WARPS][RS_RADIX];
+    __shared__ u32 s_keys[RS_TILE];
+    __shared__ u32 s_vals[HAS_VALS ? RS_TILE : 1];
+    __shared__ u32 s_digit_off[RS_RADIX];
+    __shared__ u32 s_scan[8];
+    __shared__ u32 s_tile;
+
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) s_warp_hist[w][tid] = 0;
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u32 base = tile * RS_TILE;
+    const u32 wbase = base + warp * (32 * RS_IPT);
+
+    u32 key[RS_IPT];
+    unsigned short rank[RS_IPT];
+#pragma unroll
+    for (int i = 0; i < RS_IPT; ++i) {
+        u32 idx = wbase + i * 32 + lane;
+        key[i] = idx < n ? __ldg(keys_in + idx) : 0xFFFFFFFFu;
+    }
+    // Stable in-warp ranking: items are visited in index order (i-major, then lane).
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int i = 0; i < RS_IPT; ++i) {
+        u32 d = (key[i] >> shift) & mask;
+        u32 peers = __match_any_sync(0xffffffffu, d);
+        u32 before = s_warp_hist[warp][d];
+        rank[i] = (unsigned short)(before + __popc(peers & lt));
+        __syncwarp();
+        if ((peers & lt) == 0) s_warp_hist[warp][d] = before + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // Thread d owns digit d: exclusive scan over warps, then chain with earlier tiles.
+    u32 count = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+        u32 t = s_warp_hist[w][tid];
+        s_warp_hist[w][tid] = count;
+        count += t;
+    }
+    u32 prefix = 0;
+    u32* lb = lookback + (size_t)tile * RS_RADIX + tid;
+    if (tile == 0) {
+        st_volatile_u32(lb, count | LB_INCL);
+    } else {
+        st_volatile_u32(lb, count | LB_AGG);
+        for (u32 t = tile; t-- > 0;) {
+            const u32* p = lookback + (size_t)t * RS_RADIX + tid;
+            u32 v;
+            do { v = ld_volatile_u32(p); } while ((v & (LB_AGG | LB_INCL)) == 0);
+            prefix += v & LB_VALUE;
+            if (v & LB_INCL) break;
+        }
+        st_volatile_u32(lb, ((prefix + count) & LB_VALUE) | LB_INCL);
+    }
+    const u32 local_start = block_exclusive_scan_256(count, s_scan);
+    s_digit_off[tid] = g_base[tid] + prefix - local_start;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) s_warp_hist[w][tid] += local_start;
+    __syncthreads();
+
+#pragma unroll
+    for (int i = 0; i < RS_IPT; ++i) {
+        u32 d = (key[i] >> shift) & mask;
+        u32 pos = s_warp_hist[warp][d] + rank[i];
+        s_keys[pos] = key[i];
+        if (HAS_VALS) {
+            u32 idx = wbase + i * 32 + lane;
+            s_vals[pos] = idx < n ? __ldg(vals_in + idx) : 0u;
+        }
+    }
+    __syncthreads();
+    const u32 valid = min((u32)RS_TILE, n - base);
+    for (u32 j = tid; j < valid; j += RS_THREADS) {
+        u32 k = s_keys[j];
+        u32 out = s_digit_off[(k >> shift) & mask] + j;
+        keys_out[out] = k;
+        if (HAS_VALS) vals_out[out] = s_vals[j];
+    }
+}
+
+}  // namespace
+
+int radix_sort_pairs(u32* keys_a, u32* vals_a, u32* keys_b, u32* vals_b, size_t n,
+                     int begin_bit, int end_bit, void* temp, size_t temp_bytes,
+                     cudaStream_t stream)
+{
+    if (n == 0) return 0;
+    if (n >= (size_t)LB_VALUE) { set_error("radix_sort_pairs: n=%zu exceeds 2^30-1", n); return -1; }
+    RadixPlan plan = radix_plan(n, begin_bit, end_bit);
+    if (plan.passes > RS_MAX_PASSES) { set_error("radix_sort_pairs: more than %d passes", RS_MAX_PASSES); return -1; }
+    if (temp_bytes < plan.temp_bytes) { set_error("radix_sort_pairs: temp too small"); return -1; }
+    u32* g_hist = (u32*)temp;
+    u32* tickets = g_hist + (size_t)plan.passes * RS_RADIX;
+    u32* lookback = tickets + 256;
+    cudaMemsetAsync(temp, 0, plan.temp_bytes, stream);
+
+    DigitSpec spec;
+    for (int p = 0; p < RS_MAX_PASSES; ++p) {
+        int lo = begin_bit + p * RS_RADIX_BITS;
+        int nb = end_bit - lo; if (nb > RS_RADIX_BITS) nb = RS_RADIX_BITS; if (nb < 1) nb = 1;
+        spec.shift[p] = lo < 32 ? lo : 31;
+        spec.mask[p] = (1u << nb) - 1;
+    }
+    int hgrid = (int)((n / 4 + 255) / 256); if (hgrid < 1) hgrid = 1;
+    if (hgrid > NUM_SMS * 8) hgrid = NUM_SMS * 8;
+    rs_histogram<<<hgrid, 256, 0, stream>>>(keys_a, (u32)n, plan.passes, spec, g_hist);
+    rs_scan_hist<<<plan.passes, 256, 0, stream>>>(g_hist);
+
+    u32 *kin = keys_a, *kout = keys_b, *vin = vals_a, *vout = vals_b;
+    for (int p = 0; p < plan.passes; ++p) {
+        u32* lb = lookback + (size_t)p * plan.tiles * RS_RADIX;
+        if (vals_a)
+            rs_onesweep_pass<true><<<(unsigned)plan.tiles, RS_THREADS, 0, stream>>>(
+                kin, vin, kout, vout, (u32)n, spec.shift[p], spec.mask[p], g_hist + p * RS_RADIX, lb, tickets + p);
+        else
+            rs_onesweep_pass<false><<<(unsigned)plan.tiles, RS_THREADS, 0, stream>>>(
+                kin, nullptr, kout, nullptr, (u32)n, spec.shift[p], spec.mask[p], g_hist + p * RS_RADIX, lb, tickets + p);
+        u32* t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+    }
+    if (check_launch("radix_sort_pairs")) return -1;
+    return (plan.passes & 1) ? 1 : 0;
+}
+
+}  // namespace b200gs

@@ -1,0 +1,110 @@
+/* b200gs — C ABI of the B200-native 4D Gaussian-splatting hot path.
+ *
+ * This is the drop-in boundary: every entry point replaces one pybind11 / torch::Tensor
+ * entry point (or one PyTorch-operator chain) of cvsp-lab/ICLR2025_3D-MOM and is what the
+ * reference-side Python binding (ctypes) loads from libb200gs.so.
+ *
+ * Conventions
+ *  - Plain C: raw DEVICE pointers (unless a parameter says "host"), explicit sizes, and the
+ *    CUDA stream to launch on (pass PyTorch's current stream). No torch types.
+ *  - Every function returns 0 on success and non-zero on error; b200gs_last_error() returns
+ *    the message of the last error raised on the calling thread.
+ *  - Ownership: the caller owns every buffer, scratch included. The library never allocates
+ *    or frees device memory and keeps no global state besides the per-thread error string.
+ *  - No implicit device synchronisation except where stated (b200gs_rast_forward_stage1).
+ *  - "null" for an optional tensor has the meaning of the reference's empty tensor.
+ *  Citations: RAST = submodules/depth-diff-gaussian-rasterization, KNN = submodules/simple-knn.
+ */
+#ifndef B200GS_H_INCLUDED
+#define B200GS_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200gs_stream_t; /* cudaStream_t */
+
+const char* b200gs_last_error(void);
+int b200gs_version(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Rasterizer — replaces _C.rasterize_gaussians / rasterize_gaussians_backward / mark_visible
+ * (RAST/ext.cpp:15-19; RAST/rasterize_points.cu:35-117, :119-202, :204-223) and underneath
+ * them CudaRasterizer::Rasterizer::{forward,backward,markVisible}
+ * (RAST/cuda_rasterizer/rasterizer.h:24-87).
+ * ------------------------------------------------------------------------------------- */
+
+/* Sizes in bytes of the geometry / binning / image scratch buffers for P Gaussians, R
+ * (tile, Gaussian) instances and a W x H image. Replaces required<GeometryState>() etc.
+ * (RAST/cuda_rasterizer/rasterizer_impl.h:65-72). */
+int b200gs_rast_buffer_sizes(int P, long long R, int W, int H, size_t out_bytes[3]);
+
+/* Stage 1 of the forward pass: per-Gaussian projection, covariance, SH colour, tile
+ * rectangle (RAST/cuda_rasterizer/forward.cu:155-256). Writes radii[P] (int32) and fills
+ * geom_buf. host_counters (HOST memory, 2 x uint64) receives {num_rendered, num_visible};
+ * this is the forward pass's single device->host read and synchronises `stream`, like the
+ * reference's cudaMemcpy at rasterizer_impl.cu:282. The caller then sizes the binning
+ * buffer with b200gs_rast_buffer_sizes(P, num_rendered, ...). */
+int b200gs_rast_forward_stage1(int P, int D, int M, int W, int H,
+                               const float* means3D, const float* shs, const float* colors_precomp,
+                               const float* opacities, const float* scales, float scale_modifier,
+                               const float* rotations, const float* cov3D_precomp,
+                               const float* viewmatrix, const float* projmatrix, const float* campos,
+                               float tan_fovx, float tan_fovy, int prefiltered,
+                               int* radii, void* geom_buf, size_t geom_bytes,
+                               unsigned long long* host_counters, b200gs_stream_t stream);
+
+/* Stage 2: depth sort, instance emission, tile sort, tile ranges, compositing
+ * (rasterizer_impl.cu:284-336; forward.cu:261-379). Writes out_color[3,H,W] and
+ * out_depth[1,H,W]; keeps final transmittance / contributor counts in img_buf. */
+int b200gs_rast_forward_stage2(int P, long long num_rendered, long long num_visible, int W, int H,
+                               const float* background, void* geom_buf, void* bin_buf, size_t bin_bytes,
+                               void* img_buf, size_t img_bytes, float* out_color, float* out_depth,
+                               b200gs_stream_t stream);
+
+/* Backward pass (rasterizer_impl.cu:343-444; backward.cu). grad_arena is scratch of
+ * 12*P floats. All eight outputs are fully written (zeros for culled Gaussians), so they
+ * may be uninitialised on entry: dL_dmean2D[P,3], dL_dcolor[P,3], dL_dopacity[P],
+ * dL_dmean3D[P,3], dL_dcov3D[P,6], dL_dsh[P,M,3] (may be null), dL_dscale[P,3], dL_drot[P,4]. */
+int b200gs_rast_backward(int P, int D, int M, long long num_rendered, int W, int H,
+                         const float* background, const float* means3D, const float* shs,
+                         const float* colors_precomp, const float* scales, float scale_modifier,
+                         const float* rotations, const float* cov3D_precomp,
+                         const float* viewmatrix, const float* projmatrix, const float* campos,
+                         float tan_fovx, float tan_fovy, const int* radii,
+                         void* geom_buf, void* bin_buf, void* img_buf,
+                         const float* dL_dpix, const float* dL_dpix_depth, float* grad_arena,
+                         float* dL_dmean2D, float* dL_dcolor, float* dL_dopacity, float* dL_dmean3D,
+                         float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                         b200gs_stream_t stream);
+
+/* present[P] (uint8/bool) = view-space z > 0.2 (rasterizer_impl.cu:54-66, :141-153). */
+int b200gs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                        unsigned char* present, b200gs_stream_t stream);
+
+/* Parity/debug: re-expresses one field of the internal state of the last forward call in the
+ * REFERENCE's layout (rasterizer_impl.h:21-73) into a device buffer `dst` of dst_bytes.
+ * Fields: "depths" f32[P], "means2D" f32[P,2], "conic_opacity" f32[P,4], "rgb" f32[P,3],
+ * "clamped" u8[P,3], "cov3D" f32[P,6], "tiles_touched" u32[P], "point_list" u32[R],
+ * "keys" u64[R] (tile<<32 | depth bits, sorted), "ranges" u32[tiles,2], "n_contrib" u32[H*W],
+ * "accum_alpha" f32[H*W]. Returns the number of bytes written, or -1. */
+long long b200gs_rast_export(const char* field, int P, long long num_rendered, int W, int H,
+                             void* geom_buf, void* bin_buf, void* img_buf, void* dst, long long dst_bytes,
+                             b200gs_stream_t stream);
+
+/* Stand-alone stable radix sort of (u32 key, u32 value) pairs on key bits [begin_bit, end_bit);
+ * replaces cub::DeviceRadixSort::SortPairs (rasterizer_impl.cu:304-309; KNN/simple_knn.cu:208-213).
+ * keys_a/vals_a hold the input, *_b are ping-pong buffers; returns 0 or 1 = which side holds the
+ * result, or -1. temp_bytes from b200gs_sort_temp_bytes. */
+size_t b200gs_sort_temp_bytes(size_t n, int begin_bit, int end_bit);
+int b200gs_sort_pairs_u32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b,
+                          size_t n, int begin_bit, int end_bit, void* temp, size_t temp_bytes,
+                          b200gs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GS_H_INCLUDED */
