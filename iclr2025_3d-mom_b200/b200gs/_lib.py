@@ -55,6 +55,10 @@ def _declare(L):
     L.b200gs_sort_temp_bytes.argtypes = [c_size_t, c_int, c_int]
     L.b200gs_sort_pairs_u32.restype = c_int
     L.b200gs_sort_pairs_u32.argtypes = [P, P, P, P, c_size_t, c_int, c_int, P, c_size_t, P]
+    L.b200gs_dist2_scratch_bytes.restype = c_size_t
+    L.b200gs_dist2_scratch_bytes.argtypes = [c_size_t]
+    L.b200gs_dist2.restype = c_int
+    L.b200gs_dist2.argtypes = [c_int, P, P, P, c_size_t, P]
     for name, (res, args) in _OPTIONAL.items():
         if hasattr(L, name):
             fn = getattr(L, name)

@@ -47,6 +47,9 @@ int rast_backward(int P, int D, int M, long long R, int W, int H, const float* b
 int mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                  unsigned char* present, cudaStream_t stream);
 
+size_t dist2_scratch_bytes(size_t P);
+int dist2(int P, const float* points, float* mean_dists, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+
 // ---- export of internal state in the reference's layout (parity tests only) -------------
 enum ExportField { F_DEPTHS, F_MEANS2D, F_CONIC_OPACITY, F_RGB, F_CLAMPED, F_KEYS };
 
@@ -195,6 +198,13 @@ int b200gs_sort_pairs_u32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, 
 {
     return radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, n, begin_bit, end_bit, temp, temp_bytes,
                             (cudaStream_t)stream);
+}
+
+size_t b200gs_dist2_scratch_bytes(size_t P) { return dist2_scratch_bytes(P); }
+int b200gs_dist2(int P, const float* points, float* mean_dists, void* scratch, size_t scratch_bytes,
+                 b200gs_stream_t stream)
+{
+    return dist2(P, points, mean_dists, scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

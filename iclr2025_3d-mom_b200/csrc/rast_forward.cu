@@ -27,89 +27,96 @@ __constant__ float SH3c[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45704
 constexpr int PRE_THREADS = 128;
 constexpr int PRE_WARPS = PRE_THREADS / 32;
 
-// Column-major 3x3 with the product rule of the matrix library the reference uses
-// (out[c][r] = a[0][r]*b[c][0] + a[1][r]*b[c][1] + a[2][r]*b[c][2], evaluated left to
-// right) so FMA contraction, and therefore every rounding, is the same.
-struct M3 { float m[3][3]; };
-__device__ __forceinline__ M3 m3mul(const M3& a, const M3& b) {
-    M3 o;
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-            o.m[c][r] = a.m[0][r] * b.m[c][0] + a.m[1][r] * b.m[c][1] + a.m[2][r] * b.m[c][2];
-    return o;
+// The bit-exact part of the projection (radii, tile rectangles and depth keys must equal the
+// reference's to the last bit) is written with explicit round-to-nearest intrinsics, so no
+// compiler contraction choice can change a rounding.  The operation order restates what the
+// reference's expressions compile to under nvcc's default -fmad=true (verified against its
+// SASS): a*b + c*d + e*f  ->  fma(e, f, fma(a, b, c*d)).
+__device__ __forceinline__ float dot3(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return __fmaf_rn(a2, b2, __fmaf_rn(a0, b0, __fmul_rn(a1, b1)));
 }
-__device__ __forceinline__ M3 m3t(const M3& a) {
-    M3 o;
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int r = 0; r < 3; ++r) o.m[c][r] = a.m[r][c];
-    return o;
+// matrix[0]*x + matrix[4]*y + matrix[8]*z + matrix[12]  (auxiliary.h:58-76)
+__device__ __forceinline__ float affine3(float x, float y, float z, float m0, float m1, float m2, float m3) {
+    return __fadd_rn(dot3(x, m0, y, m1, z, m2), m3);
 }
-
 __device__ __forceinline__ float3 xform43(const float3 p, const float* m) {
-    return make_float3(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
-                       m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
-                       m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]);
+    return make_float3(affine3(p.x, p.y, p.z, m[0], m[4], m[8], m[12]),
+                       affine3(p.x, p.y, p.z, m[1], m[5], m[9], m[13]),
+                       affine3(p.x, p.y, p.z, m[2], m[6], m[10], m[14]));
 }
 __device__ __forceinline__ float4 xform44(const float3 p, const float* m) {
-    return make_float4(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
-                       m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
-                       m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14],
-                       m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15]);
+    return make_float4(affine3(p.x, p.y, p.z, m[0], m[4], m[8], m[12]),
+                       affine3(p.x, p.y, p.z, m[1], m[5], m[9], m[13]),
+                       affine3(p.x, p.y, p.z, m[2], m[6], m[10], m[14]),
+                       affine3(p.x, p.y, p.z, m[3], m[7], m[11], m[15]));
 }
 
 // NDC -> pixel; evaluated in double exactly like the reference (auxiliary.h:41-44).
-__device__ __forceinline__ float ndc_to_pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
+__device__ __forceinline__ float ndc_to_pix(float v, int S) {
+    return (float)__dmul_rn(__fma_rn(__dadd_rn((double)v, 1.0), (double)S, -1.0), 0.5);
+}
 
 // World-space covariance from scale and (already normalised) quaternion, forward.cu:118-152.
+// M = S*R has exactly one non-zero term per entry, so M[c][r] = s_r * R[c][r]; Sigma = M^T M.
 __device__ __forceinline__ void cov3d_from_scale_rot(const float3 scale, float mod, const float4 q, float* cov)
 {
-    M3 S;
+    const float s[3] = {__fmul_rn(mod, scale.x), __fmul_rn(mod, scale.y), __fmul_rn(mod, scale.z)};
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    const float xz = __fmul_rn(x, z), rx = __fmul_rn(r, x), rz = __fmul_rn(r, z);
+    const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+    auto dbl = [](float v) { return __fadd_rn(v, v); };
+    float R[3][3];   // R[c][r], column-major like the reference's matrix type
+    R[0][0] = __fsub_rn(1.f, dbl(__fadd_rn(yy, zz)));
+    R[0][1] = dbl(__fmaf_rn(x, y, -rz));
+    R[0][2] = dbl(__fmaf_rn(r, y, xz));
+    R[1][0] = dbl(__fmaf_rn(x, y, rz));
+    R[1][1] = __fsub_rn(1.f, dbl(__fmaf_rn(x, x, zz)));
+    R[1][2] = dbl(__fmaf_rn(y, z, -rx));
+    R[2][0] = dbl(__fmaf_rn(-r, y, xz));
+    R[2][1] = dbl(__fmaf_rn(y, z, rx));
+    R[2][2] = __fsub_rn(1.f, dbl(__fmaf_rn(x, x, yy)));
+    float M[3][3];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int r = 0; r < 3; ++r) S.m[c][r] = 0.f;
-    S.m[0][0] = mod * scale.x; S.m[1][1] = mod * scale.y; S.m[2][2] = mod * scale.z;
-    const float r = q.x, x = q.y, y = q.z, z = q.w;
-    M3 R;
-    R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
-    R.m[1][0] = 2.f * (x * y + r * z); R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
-    R.m[2][0] = 2.f * (x * z - r * y); R.m[2][1] = 2.f * (y * z + r * x); R.m[2][2] = 1.f - 2.f * (x * x + y * y);
-    M3 M = m3mul(S, R);
-    M3 Sg = m3mul(m3t(M), M);
-    cov[0] = Sg.m[0][0]; cov[1] = Sg.m[0][1]; cov[2] = Sg.m[0][2];
-    cov[3] = Sg.m[1][1]; cov[4] = Sg.m[1][2]; cov[5] = Sg.m[2][2];
+        for (int rr = 0; rr < 3; ++rr) M[c][rr] = __fmul_rn(s[rr], R[c][rr]);
+    auto sig = [&](int c, int rr) { return dot3(M[rr][0], M[c][0], M[rr][1], M[c][1], M[rr][2], M[c][2]); };
+    cov[0] = sig(0, 0); cov[1] = sig(0, 1); cov[2] = sig(0, 2);
+    cov[3] = sig(1, 1); cov[4] = sig(1, 2); cov[5] = sig(2, 2);
 }
 
-// EWA projection of the 3D covariance, forward.cu:74-113.
+// EWA projection of the 3D covariance, forward.cu:74-113: cov2D = T^T Vrk^T T with T = W J,
+// the third column of J being zero.
 __device__ __forceinline__ float3 cov2d_project(const float3 mean, float fx, float fy, float tanx, float tany,
-                                                const float* cov, const float* vm)
+                                                const float* c, const float* vm)
 {
-    float3 t = xform43(mean, vm);
-    const float limx = 1.3f * tanx, limy = 1.3f * tany;
-    const float txtz = t.x / t.z, tytz = t.y / t.z;
-    t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
-    t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
-    M3 J;
-    J.m[0][0] = fx / t.z; J.m[0][1] = 0.f; J.m[0][2] = -(fx * t.x) / (t.z * t.z);
-    J.m[1][0] = 0.f; J.m[1][1] = fy / t.z; J.m[1][2] = -(fy * t.y) / (t.z * t.z);
-    J.m[2][0] = 0.f; J.m[2][1] = 0.f; J.m[2][2] = 0.f;
-    M3 Wm;
-    Wm.m[0][0] = vm[0]; Wm.m[0][1] = vm[4]; Wm.m[0][2] = vm[8];
-    Wm.m[1][0] = vm[1]; Wm.m[1][1] = vm[5]; Wm.m[1][2] = vm[9];
-    Wm.m[2][0] = vm[2]; Wm.m[2][1] = vm[6]; Wm.m[2][2] = vm[10];
-    M3 T = m3mul(Wm, J);
-    M3 V;
-    V.m[0][0] = cov[0]; V.m[0][1] = cov[1]; V.m[0][2] = cov[2];
-    V.m[1][0] = cov[1]; V.m[1][1] = cov[3]; V.m[1][2] = cov[4];
-    V.m[2][0] = cov[2]; V.m[2][1] = cov[4]; V.m[2][2] = cov[5];
-    M3 C = m3mul(m3mul(m3t(T), m3t(V)), T);
-    C.m[0][0] += 0.3f;
-    C.m[1][1] += 0.3f;
-    return make_float3(C.m[0][0], C.m[0][1], C.m[1][1]);
+    const float3 t0 = xform43(mean, vm);
+    const float tz = t0.z;
+    const float limx = __fmul_rn(1.3f, tanx), limy = __fmul_rn(1.3f, tany);
+    const float txtz = __fdiv_rn(t0.x, tz), tytz = __fdiv_rn(t0.y, tz);
+    const float tx = __fmul_rn(fminf(limx, fmaxf(-limx, txtz)), tz);
+    const float ty = __fmul_rn(fminf(limy, fmaxf(-limy, tytz)), tz);
+    const float tz2 = __fmul_rn(tz, tz);
+    const float J00 = __fdiv_rn(fx, tz), J02 = __fdiv_rn(-__fmul_rn(fx, tx), tz2);
+    const float J11 = __fdiv_rn(fy, tz), J12 = __fdiv_rn(-__fmul_rn(fy, ty), tz2);
+    // T[0][r] = W[0][r]*J00 + W[2][r]*J02 ; T[1][r] = W[1][r]*J11 + W[2][r]*J12 ; W[k][r] = vm[4r + k]
+    float T0[3], T1[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        T0[r] = __fmaf_rn(vm[4 * r + 2], J02, __fmul_rn(vm[4 * r + 0], J00));
+        T1[r] = __fmaf_rn(vm[4 * r + 2], J12, __fmul_rn(vm[4 * r + 1], J11));
+    }
+    // A[k][0] = T0 . Vrk column k, A[k][1] = T1 . Vrk column k (Vrk symmetric: c0 c1 c2 / c1 c3 c4 / c2 c4 c5)
+    const float A00 = dot3(T0[0], c[0], T0[1], c[1], T0[2], c[2]);
+    const float A10 = dot3(T0[0], c[1], T0[1], c[3], T0[2], c[4]);
+    const float A20 = dot3(T0[0], c[2], T0[1], c[4], T0[2], c[5]);
+    const float A01 = dot3(T1[0], c[0], T1[1], c[1], T1[2], c[2]);
+    const float A11 = dot3(T1[0], c[1], T1[1], c[3], T1[2], c[4]);
+    const float A21 = dot3(T1[0], c[2], T1[1], c[4], T1[2], c[5]);
+    const float c00 = __fadd_rn(dot3(A00, T0[0], A10, T0[1], A20, T0[2]), 0.3f);
+    const float c01 = dot3(A01, T0[0], A11, T0[1], A21, T0[2]);
+    const float c11 = __fadd_rn(dot3(A01, T1[0], A11, T1[1], A21, T1[2]), 0.3f);
+    return make_float3(c00, c01, c11);
 }
 
 struct PreArgs {
@@ -159,8 +166,8 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
     u32 xmin = 0, xmax = 0, ymin = 0, ymax = 0;
     if (alive) {
         float4 ph = xform44(p, pm);
-        float pw = 1.0f / (ph.w + 0.0000001f);
-        float3 pp = make_float3(ph.x * pw, ph.y * pw, ph.z * pw);
+        const float pw = __fdiv_rn(1.0f, __fadd_rn(ph.w, 0.0000001f));
+        const float3 pp = make_float3(__fmul_rn(ph.x, pw), __fmul_rn(ph.y, pw), __fmul_rn(ph.z, pw));
         float cov_local[6];
         const float* cov3 = cov_local;
         if (a.cov3d_pre) {
@@ -174,22 +181,23 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
             for (int k = 0; k < 6; ++k) a.g.cov3D[6 * (size_t)idx + k] = cov_local[k];
         }
         float3 cov = cov2d_project(p, a.fx, a.fy, a.tanx, a.tany, cov3, vm);
-        float det = cov.x * cov.z - cov.y * cov.y;
+        const float det = __fmaf_rn(cov.x, cov.z, -__fmul_rn(cov.y, cov.y));
         if (det == 0.0f) alive = false;
         else {
-            float det_inv = 1.f / det;
-            conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
-            float mid = 0.5f * (cov.x + cov.z);
-            float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
-            float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
-            radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+            const float det_inv = __fdiv_rn(1.f, det);
+            conic = make_float3(__fmul_rn(cov.z, det_inv), -__fmul_rn(cov.y, det_inv), __fmul_rn(cov.x, det_inv));
+            const float mid = __fmul_rn(0.5f, __fadd_rn(cov.x, cov.z));
+            const float disc = __fsqrt_rn(fmaxf(0.1f, __fmaf_rn(mid, mid, -det)));
+            const float lambda1 = __fadd_rn(mid, disc), lambda2 = __fsub_rn(mid, disc);
+            radius = ceilf(__fmul_rn(3.f, __fsqrt_rn(fmaxf(lambda1, lambda2))));
             pix = make_float2(ndc_to_pix(pp.x, a.W), ndc_to_pix(pp.y, a.H));
             // tile rectangle, auxiliary.h:46-56
             const int ri = (int)radius;
-            xmin = min((u32)a.grid_x, (u32)max(0, (int)((pix.x - ri) / TILE_X)));
-            ymin = min((u32)a.grid_y, (u32)max(0, (int)((pix.y - ri) / TILE_Y)));
-            xmax = min((u32)a.grid_x, (u32)max(0, (int)((pix.x + ri + TILE_X - 1) / TILE_X)));
-            ymax = min((u32)a.grid_y, (u32)max(0, (int)((pix.y + ri + TILE_Y - 1) / TILE_Y)));
+            const float rf = (float)ri, tw = (float)TILE_X, th = (float)TILE_Y;
+            xmin = min((u32)a.grid_x, (u32)max(0, (int)__fdiv_rn(__fsub_rn(pix.x, rf), tw)));
+            ymin = min((u32)a.grid_y, (u32)max(0, (int)__fdiv_rn(__fsub_rn(pix.y, rf), th)));
+            xmax = min((u32)a.grid_x, (u32)max(0, (int)__fdiv_rn(__fsub_rn(__fadd_rn(__fadd_rn(pix.x, rf), tw), 1.f), tw)));
+            ymax = min((u32)a.grid_y, (u32)max(0, (int)__fdiv_rn(__fsub_rn(__fadd_rn(__fadd_rn(pix.y, rf), th), 1.f), th)));
             if ((xmax - xmin) * (ymax - ymin) == 0) alive = false;
         }
     }

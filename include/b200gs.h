@@ -104,6 +104,15 @@ int b200gs_sort_pairs_u32(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, 
                           size_t n, int begin_bit, int end_bit, void* temp, size_t temp_bytes,
                           b200gs_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * simple-knn — replaces simple_knn._C.distCUDA2 (KNN/spatial.cu:15-26, KNN/ext.cpp) and
+ * SimpleKNN::knn (KNN/simple_knn.cu:185-220): mean_dists[i] = mean of the three smallest
+ * squared distances from point i to the other points. points[P,3] float32.
+ * ------------------------------------------------------------------------------------- */
+size_t b200gs_dist2_scratch_bytes(size_t P);
+int b200gs_dist2(int P, const float* points, float* mean_dists, void* scratch, size_t scratch_bytes,
+                 b200gs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,7 @@ def test_forward_bit_exact_and_image(P, W, H, mu):
     # per-Gaussian projected state (visible ones; the reference leaves culled slots stale)
     np.testing.assert_array_equal(get("depths", np.float32)[vis], rh.ref_get("depths")[vis])
     np.testing.assert_array_equal(get("means2D", np.float32).reshape(-1, 2)[vis], rh.ref_get("means2D").reshape(-1, 2)[vis])
+    np.testing.assert_array_equal(get("cov3D", np.float32).reshape(-1, 6)[vis], rh.ref_get("cov3D").reshape(-1, 6)[vis])
     np.testing.assert_array_equal(get("conic_opacity", np.float32).reshape(-1, 4)[vis],
                                   rh.ref_get("conic_opacity").reshape(-1, 4)[vis])
     np.testing.assert_allclose(get("rgb", np.float32).reshape(-1, 3)[vis], rh.ref_get("rgb").reshape(-1, 3)[vis],
