@@ -452,7 +452,7 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ l
 
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
-    u32 contributor = 0, last = 0;
+    u32 last = 0;
 
     if (rounds > 0) stage_fill(stage[0], list, range.x, range.y, 0, false, recA, recB, recC);
     cp_async_commit();
@@ -464,25 +464,31 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ l
         if (__syncthreads_count(done) == TILE_PIXELS) break;
         const Stage& st = stage[r & 1];
         const int cnt = (int)min((u32)CB, n - (u32)r * CB);
-        if (!done) {
-            for (int j = 0; j < cnt; ++j) {
-                ++contributor;
-                const float4 A = st.A[j];
-                const float4 B = st.B[j];
-                const float dx = A.x - fxp, dy = A.y - fyp;
-                const float power = -0.5f * (A.z * dx * dx + B.x * dy * dy) - A.w * dx * dy;
-                if (power > 0.0f || power < B.w) continue;
+        // Every lane walks the batch in lock-step (finished pixels are predicated off): the
+        // warp vote both ends the batch early and keeps the 32 lanes converged, which the
+        // data-dependent `continue`s of the reference loop (forward.cu:328-366) do not.
+        for (int j = 0; j < cnt; ++j) {
+            if (__all_sync(0xffffffffu, done)) break;
+            const float4 A = st.A[j];
+            const float4 B = st.B[j];
+            const float dx = A.x - fxp, dy = A.y - fyp;
+            const float power = -0.5f * (A.z * dx * dx + B.x * dy * dy) - A.w * dx * dy;
+            if (!done && !(power > 0.0f) && !(power < B.w)) {
                 const float alpha = fminf(0.99f, B.y * expf(power));
-                if (alpha < 1.0f / 255.0f) continue;
-                const float test_T = T * (1 - alpha);
-                if (test_T < 0.0001f) { done = true; break; }
-                const float4 Cc = st.C[j];
-                C0 += Cc.x * alpha * T;
-                C1 += Cc.y * alpha * T;
-                C2 += Cc.z * alpha * T;
-                Dp += B.z * alpha * T;
-                T = test_T;
-                last = contributor;
+                if (!(alpha < 1.0f / 255.0f)) {
+                    const float test_T = T * (1 - alpha);
+                    if (test_T < 0.0001f) {
+                        done = true;
+                    } else {
+                        const float4 Cc = st.C[j];
+                        C0 += Cc.x * alpha * T;
+                        C1 += Cc.y * alpha * T;
+                        C2 += Cc.z * alpha * T;
+                        Dp += B.z * alpha * T;
+                        T = test_T;
+                        last = (u32)r * CB + (u32)j + 1u;
+                    }
+                }
             }
         }
         __syncthreads();   // batch r fully consumed before its buffer is refilled

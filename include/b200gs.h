@@ -113,6 +113,35 @@ size_t b200gs_dist2_scratch_bytes(size_t P);
 int b200gs_dist2(int P, const float* points, float* mean_dists, void* scratch, size_t scratch_bytes,
                  b200gs_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Optimiser — replaces the ~8 foreach launches of torch.optim.Adam.step() that the reference
+ * runs every iteration (scene/gaussian_model.py:197-209; train_4DGS.py:295-297) with one
+ * launch over all parameter tensors. Arithmetic = torch/optim/adam.py::_multi_tensor_adam
+ * (no weight decay, no amsgrad, not capturable): the caller computes, per tensor and in
+ * double precision like torch does, neg_step_size = -(lr / (1 - beta1^step)) and
+ * bias_correction2_sqrt = sqrt(1 - beta2^step) after incrementing that tensor's step.
+ * The table is HOST memory (copied into kernel arguments). Tensors whose grad is None are
+ * simply not listed, which is how torch skips them.
+ * ------------------------------------------------------------------------------------- */
+#define B200GS_ADAM_MAX_TENSORS 56
+typedef struct {
+    float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+    long long numel;
+    float neg_step_size;
+    float bias_correction2_sqrt;
+} b200gs_adam_tensor;
+int b200gs_adam_multi(int n_tensors, const b200gs_adam_tensor* tensors /* host */, double beta1, double beta2,
+                      double eps, b200gs_stream_t stream);
+
+/* Densify / prune bookkeeping — replaces the per-tensor boolean-mask indexing and torch.cat
+ * chains of scene/gaussian_model.py:424-482 (_prune_optimizer, cat_tensors_to_optimizer):
+ * for every listed tensor, dst[i, :] = src[index[i], :], i < n_out, rows of row_floats floats.
+ * index = int64 row ids on the device (null = identity, i.e. a plain multi-tensor copy). */
+#define B200GS_GATHER_MAX_TENSORS 64
+typedef struct { const float* src; float* dst; int row_floats; int reserved; } b200gs_gather_tensor;
+int b200gs_gather_rows_multi(int n_tensors, const b200gs_gather_tensor* tensors /* host */,
+                             const long long* index, long long n_out, b200gs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
