@@ -1,0 +1,453 @@
+"""Drop-in HexPlane deformation field: `HexPlaneField`, `Deformation`, `deform_network`.
+
+Mirrors scene/hexplane.py:109-183 and scene/deformation.py:16-242 — same constructor
+arguments, attribute paths, parameter names / shapes (so `state_dict()` keys such as
+`deformation_net.grid.grids.{level}.{plane}`, `deformation_net.grid.aabb`,
+`deformation_net.feature_out.0.weight`, `timenet.*`, `*_poc` match), same call signatures and
+return values — while forward and backward run the hand-written sm_100a kernels of
+libb200gs (csrc/hexplane.cu, csrc/deform_mlp.cu) through `torch.autograd.Function`s.
+
+Differences that do not change results:
+  * plane parameters keep their [1, 32, H, W] shape but use torch.channels_last strides (one
+    coalesced 128-byte line per texel in the kernels);
+  * the sin/cos positional encodings the reference computes and then slices away
+    (deformation.py:205-207 vs :107-135) are not computed.
+Configurations the reference can express but does not train with are rejected loudly
+(NotImplementedError) instead of silently falling back to PyTorch operators.
+"""
+import ctypes
+import itertools
+
+import torch
+import torch.nn as nn
+import torch.nn.init as init
+
+from . import _lib
+from ._lib import check, current_stream
+
+MAX_LEVELS = 4
+
+
+class _HexDesc(ctypes.Structure):
+    _fields_ = [("levels", ctypes.c_int), ("channels", ctypes.c_int), ("res", (ctypes.c_int * 4) * MAX_LEVELS),
+                ("plane", (ctypes.c_void_p * 6) * MAX_LEVELS), ("grad_plane", (ctypes.c_void_p * 6) * MAX_LEVELS),
+                ("aabb", ctypes.c_void_p)]
+
+
+class _MlpWeights(ctypes.Structure):
+    _fields_ = [("feat_dim", ctypes.c_int), ("width", ctypes.c_int), ("w1", ctypes.c_void_p), ("b1", ctypes.c_void_p),
+                ("w2", ctypes.c_void_p * 3), ("b2", ctypes.c_void_p * 3), ("w3", ctypes.c_void_p * 3),
+                ("b3", ctypes.c_void_p * 3)]
+
+
+class _MlpGrads(ctypes.Structure):
+    _fields_ = [("w1", ctypes.c_void_p), ("b1", ctypes.c_void_p), ("w2", ctypes.c_void_p * 3),
+                ("b2", ctypes.c_void_p * 3), ("w3", ctypes.c_void_p * 3), ("b3", ctypes.c_void_p * 3)]
+
+
+_P = ctypes.c_void_p
+_lib.register("b200gs_hexplane_forward", ctypes.c_int,
+              [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, ctypes.c_float, _P, _P])
+_lib.register("b200gs_hexplane_backward", ctypes.c_int,
+              [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, ctypes.c_float, _P, _P, _P])
+_lib.register("b200gs_deform_mlp_saved_floats", ctypes.c_size_t, [ctypes.c_longlong])
+_lib.register("b200gs_deform_mlp_forward", ctypes.c_int,
+              [ctypes.POINTER(_MlpWeights), ctypes.c_longlong, _P, _P, _P, _P, _P, ctypes.c_float, _P, ctypes.c_float,
+               _P, _P, _P, _P, _P])
+_lib.register("b200gs_deform_mlp_backward", ctypes.c_int,
+              [ctypes.POINTER(_MlpWeights), ctypes.POINTER(_MlpGrads), ctypes.c_longlong, _P, _P, _P, _P, _P, _P, _P])
+
+
+def _cl(t):
+    """[1,C,H,W] tensor in channels_last memory (values unchanged)."""
+    return t if t.is_contiguous(memory_format=torch.channels_last) and t.stride(1) == 1 \
+        else t.contiguous(memory_format=torch.channels_last)
+
+
+def _hex_desc(aabb, planes, levels, res, grads=None):
+    d = _HexDesc()
+    d.levels = levels
+    d.channels = int(planes[0].shape[1])
+    for l in range(levels):
+        for a in range(4):
+            d.res[l][a] = int(res[l][a])
+        for k in range(6):
+            p = planes[l * 6 + k]
+            if p.stride(1) != 1:
+                raise RuntimeError("HexPlane planes must be channels_last")
+            d.plane[l][k] = p.data_ptr()
+            d.grad_plane[l][k] = grads[l * 6 + k].data_ptr() if grads is not None and grads[l * 6 + k] is not None else None
+    d.aabb = aabb.data_ptr()
+    return d
+
+
+def _check_cuda_f32(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("the B200 deformation field runs on CUDA tensors only (no CPU path)")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"expected float32, got {t.dtype}")
+
+
+def _times_arg(times, P):
+    """times_sel is a [P,1] tensor in the reference (gaussian_renderer/__init__.py:56)."""
+    if torch.is_tensor(times):
+        t = times.reshape(-1)
+        if t.numel() == 1 and P != 1:
+            t = t.expand(P)
+        if t.numel() != P:
+            raise RuntimeError("timestamps must have one entry per point")
+        return t.to(torch.float32).contiguous(), 0.0
+    return None, float(times)
+
+
+class _HexPlaneFn(torch.autograd.Function):
+    """features = HexPlaneField(pts, t); inputs (pts, times, aabb, levels, res, *planes)."""
+
+    @staticmethod
+    def forward(ctx, pts, times, aabb, levels, res, *planes):
+        pts = pts.contiguous()
+        _check_cuda_f32(pts, aabb, *planes)
+        P = int(pts.shape[0])
+        tt, ts = _times_arg(times, P)
+        feat = torch.empty((P, 32 * levels), dtype=torch.float32, device=pts.device)
+        d = _hex_desc(aabb, planes, levels, res)
+        check(_lib.lib().b200gs_hexplane_forward(ctypes.byref(d), P, pts.data_ptr(), tt.data_ptr() if tt is not None else None,
+                                                 ts, feat.data_ptr(), current_stream()), "hexplane_forward")
+        ctx.save_for_backward(pts, tt if tt is not None else torch.empty(0), aabb, *planes)
+        ctx.meta = (levels, res, ts, tt is not None)
+        return feat
+
+    @staticmethod
+    def backward(ctx, d_feat):
+        pts, tt, aabb, *planes = ctx.saved_tensors
+        levels, res, ts, has_t = ctx.meta
+        P = int(pts.shape[0])
+        need_planes = [ctx.needs_input_grad[5 + i] for i in range(len(planes))]
+        grads = [torch.zeros_like(p, memory_format=torch.preserve_format) if n else None for p, n in zip(planes, need_planes)]
+        d_pts = torch.empty_like(pts) if ctx.needs_input_grad[0] else None
+        d = _hex_desc(aabb, planes, levels, res, grads)
+        check(_lib.lib().b200gs_hexplane_backward(ctypes.byref(d), P, pts.data_ptr(), tt.data_ptr() if has_t else None, ts,
+                                                  d_feat.contiguous().data_ptr(),
+                                                  d_pts.data_ptr() if d_pts is not None else None, current_stream()),
+              "hexplane_backward")
+        return (d_pts, None, None, None, None, *grads)
+
+
+class _DeformFn(torch.autograd.Function):
+    """(pts, scales, rot) = field(xyz, scales, rot, t, scene_flow, frame_num, delta_scale).
+
+    inputs: xyz, scales, rot, times, scene_flow, frame_num, delta_scale, aabb, levels, res, heads,
+            w1, b1, (w2,b2,w3,b3) x 3 heads, *planes
+    """
+    N_FIXED = 11
+    N_W = 14
+
+    @staticmethod
+    def forward(ctx, xyz, scales, rot, times, scene_flow, frame_num, delta_scale, aabb, levels, res, heads, *rest):
+        weights, planes = rest[:_DeformFn.N_W], rest[_DeformFn.N_W:]
+        xyz = xyz.contiguous(); scales = scales.contiguous(); rot = rot.contiguous(); scene_flow = scene_flow.contiguous()
+        _check_cuda_f32(xyz, scales, rot, scene_flow, aabb, *planes, *[w for w in weights if w is not None])
+        L = _lib.lib()
+        P = int(xyz.shape[0])
+        dev = xyz.device
+        stream = current_stream()
+        tt, ts = _times_arg(times, P)
+        feat = torch.empty((P, 32 * levels), dtype=torch.float32, device=dev)
+        d = _hex_desc(aabb, planes, levels, res)
+        check(L.b200gs_hexplane_forward(ctypes.byref(d), P, xyz.data_ptr(), tt.data_ptr() if tt is not None else None, ts,
+                                        feat.data_ptr(), stream), "hexplane_forward")
+        mw = _DeformFn._weights_struct(weights, heads, 32 * levels)
+        saved = torch.empty((L.b200gs_deform_mlp_saved_floats(P),), dtype=torch.float32, device=dev)
+        pts_o = torch.empty_like(xyz); scales_o = torch.empty_like(scales); rot_o = torch.empty_like(rot)
+        if torch.is_tensor(frame_num):
+            fn_dev = frame_num.to(device=dev, dtype=torch.float32).reshape(-1)[:1].contiguous()
+            fn_val, fn_ptr = 0.0, fn_dev.data_ptr()
+        else:
+            fn_dev, fn_val, fn_ptr = None, float(frame_num), None
+        check(L.b200gs_deform_mlp_forward(ctypes.byref(mw), P, feat.data_ptr(), xyz.data_ptr(), scales.data_ptr(),
+                                          rot.data_ptr(), scene_flow.data_ptr(), fn_val, fn_ptr, float(delta_scale),
+                                          pts_o.data_ptr(), scales_o.data_ptr(), rot_o.data_ptr(), saved.data_ptr(), stream),
+              "deform_mlp_forward")
+        ctx.save_for_backward(xyz, tt if tt is not None else torch.empty(0), aabb, feat, saved,
+                              *[w if w is not None else torch.empty(0) for w in weights], *planes)
+        ctx.meta = (levels, res, heads, ts, tt is not None)
+        return pts_o, scales_o, rot_o
+
+    @staticmethod
+    def _weights_struct(weights, heads, feat_dim):
+        mw = _MlpWeights()
+        mw.feat_dim = feat_dim
+        mw.width = int(weights[0].shape[0])
+        mw.w1 = weights[0].data_ptr(); mw.b1 = weights[1].data_ptr()
+        for h in range(3):
+            w2, b2, w3, b3 = weights[2 + 4 * h: 6 + 4 * h]
+            on = heads[h] and w2 is not None and w2.numel() > 0
+            mw.w2[h] = w2.data_ptr() if on else None
+            mw.b2[h] = b2.data_ptr() if on else None
+            mw.w3[h] = w3.data_ptr() if on else None
+            mw.b3[h] = b3.data_ptr() if on else None
+        return mw
+
+    @staticmethod
+    def backward(ctx, d_pts, d_scales, d_rot):
+        xyz, tt, aabb, feat, saved, *rest = ctx.saved_tensors
+        weights, planes = rest[:_DeformFn.N_W], rest[_DeformFn.N_W:]
+        levels, res, heads, ts, has_t = ctx.meta
+        L = _lib.lib()
+        P = int(xyz.shape[0])
+        stream = current_stream()
+        mw = _DeformFn._weights_struct(weights, heads, 32 * levels)
+        gws = [torch.zeros_like(w) if w.numel() else None for w in weights]
+        mg = _MlpGrads()
+        mg.w1 = gws[0].data_ptr(); mg.b1 = gws[1].data_ptr()
+        for h in range(3):
+            for name, i in (("w2", 2), ("b2", 3), ("w3", 4), ("b3", 5)):
+                g = gws[i + 4 * h]
+                getattr(mg, name)[h] = g.data_ptr() if (g is not None and heads[h]) else None
+        d_feat = torch.empty_like(feat)
+        cp = lambda t: t.contiguous().data_ptr() if t is not None else None
+        check(L.b200gs_deform_mlp_backward(ctypes.byref(mw), ctypes.byref(mg), P, feat.data_ptr(), saved.data_ptr(),
+                                           cp(d_pts) if heads[0] else None, cp(d_scales) if heads[1] else None,
+                                           cp(d_rot) if heads[2] else None, d_feat.data_ptr(), stream), "deform_mlp_backward")
+        gplanes = [torch.zeros_like(p, memory_format=torch.preserve_format) for p in planes]
+        d_xyz_grid = torch.empty_like(xyz)
+        d = _hex_desc(aabb, planes, levels, res, gplanes)
+        check(L.b200gs_hexplane_backward(ctypes.byref(d), P, xyz.data_ptr(), tt.data_ptr() if has_t else None, ts,
+                                         d_feat.data_ptr(), d_xyz_grid.data_ptr(), stream), "hexplane_backward")
+        # pts = xyz*1 + ..., scales = scales*1 + ds, rot = rot + dr: identity paths
+        d_xyz = d_xyz_grid + d_pts if d_pts is not None else d_xyz_grid
+        gw_out = [g if (g is not None) else None for g in gws]
+        for h in range(3):
+            if not heads[h]:
+                for i in range(2 + 4 * h, 6 + 4 * h):
+                    gw_out[i] = None
+        return (d_xyz, d_scales, d_rot, None, None, None, None, None, None, None, None, *gw_out, *gplanes)
+
+
+# ---------------------------------------------------------------------------------------------
+# modules (same structure as the reference so state_dicts and the optimiser groups line up)
+# ---------------------------------------------------------------------------------------------
+def init_grid_param(grid_nd, in_dim, out_dim, reso, a=0.1, b=0.5):
+    """scene/hexplane.py:48-70; returns channels_last parameters."""
+    assert in_dim == len(reso), "Resolution must have same number of elements as input-dimension"
+    has_time_planes = in_dim == 4
+    assert grid_nd <= in_dim
+    grid_coefs = nn.ParameterList()
+    for coo_comb in itertools.combinations(range(in_dim), grid_nd):
+        t = torch.empty([1, out_dim] + [reso[cc] for cc in coo_comb[::-1]])
+        if has_time_planes and 3 in coo_comb:
+            nn.init.ones_(t)
+        else:
+            nn.init.uniform_(t, a=a, b=b)
+        grid_coefs.append(nn.Parameter(_cl(t)))
+    return grid_coefs
+
+
+class HexPlaneField(nn.Module):
+    def __init__(self, bounds, planeconfig, multires) -> None:
+        super().__init__()
+        aabb = torch.tensor([[bounds, bounds, bounds], [-bounds, -bounds, -bounds]])
+        self.aabb = nn.Parameter(aabb, requires_grad=False)
+        self.grid_config = [planeconfig]
+        self.multiscale_res_multipliers = multires
+        self.concat_features = True
+        cfg0 = self.grid_config[0]
+        if cfg0["grid_dimensions"] != 2 or cfg0["input_coordinate_dim"] != 4:
+            raise NotImplementedError("b200gs HexPlaneField supports 2-D planes over (x, y, z, t) only")
+        if cfg0["output_coordinate_dim"] != 32:
+            raise NotImplementedError("b200gs HexPlaneField supports 32 channels per plane")
+        if len(multires) not in (2, 4):
+            raise NotImplementedError("b200gs HexPlaneField is built for 2 or 4 resolution levels")
+        self.grids = nn.ModuleList()
+        self.feat_dim = 0
+        self._res = []
+        for res in self.multiscale_res_multipliers:
+            config = cfg0.copy()
+            config["resolution"] = [r * res for r in config["resolution"][:3]] + config["resolution"][3:]
+            gp = init_grid_param(grid_nd=config["grid_dimensions"], in_dim=config["input_coordinate_dim"],
+                                 out_dim=config["output_coordinate_dim"], reso=config["resolution"])
+            self.feat_dim += gp[-1].shape[1]
+            self.grids.append(gp)
+            self._res.append(tuple(int(r) for r in config["resolution"]))
+        print("feature_dim:", self.feat_dim)
+
+    @property
+    def get_aabb(self):
+        return self.aabb[0], self.aabb[1]
+
+    def set_aabb(self, xyz_max, xyz_min):
+        aabb = torch.tensor([xyz_max, xyz_min], dtype=torch.float32)
+        self.aabb = nn.Parameter(aabb.to(self.aabb.device), requires_grad=False)
+        print("Voxel Plane: set aabb=", self.aabb)
+
+    def _planes(self):
+        out = []
+        for gp in self.grids:
+            for p in gp:
+                if p.stride(1) != 1:           # e.g. after load_state_dict into a re-created parameter
+                    p.data = _cl(p.data)
+                out.append(p)
+        return out
+
+    def get_density(self, pts, timestamps=None):
+        if timestamps is None:
+            raise NotImplementedError("static (time-free) HexPlane queries are not on the reference's path")
+        pts = pts.reshape(-1, pts.shape[-1])
+        return _HexPlaneFn.apply(pts[:, :3], timestamps, self.aabb, len(self.grids), tuple(self._res), *self._planes())
+
+    def forward(self, pts, timestamps=None):
+        return self.get_density(pts, timestamps)
+
+
+def _head(W, k):
+    return nn.Sequential(nn.ReLU(), nn.Linear(W, W), nn.ReLU(), nn.Linear(W, k))
+
+
+class Deformation(nn.Module):
+    def __init__(self, D=8, W=256, input_ch=27, input_ch_time=9, grid_pe=0, skips=[], args=None):
+        super().__init__()
+        self.D = D
+        self.W = W
+        self.input_ch = input_ch
+        self.input_ch_time = input_ch_time
+        self.skips = skips
+        self.grid_pe = grid_pe
+        self.no_grid = args.no_grid
+        self.grid = HexPlaneField(args.bounds, args.kplanes_config, args.multires)
+        self.args = args
+        unsupported = []
+        if args.no_grid: unsupported.append("no_grid")
+        if args.empty_voxel: unsupported.append("empty_voxel")
+        if args.static_mlp: unsupported.append("static_mlp")
+        if grid_pe != 0: unsupported.append("grid_pe")
+        if getattr(args, "apply_rotation", False): unsupported.append("apply_rotation")
+        if not args.no_do: unsupported.append("no_do=False")
+        if not args.no_dshs: unsupported.append("no_dshs=False")
+        if D > 1: unsupported.append("defor_depth>1")
+        if W != 64: unsupported.append("net_width!=64")
+        if unsupported:
+            raise NotImplementedError("b200gs Deformation: configuration outside the fused kernels' scope: " + ", ".join(unsupported))
+        self.ratio = 0
+        self.create_net()
+
+    @property
+    def get_aabb(self):
+        return self.grid.get_aabb
+
+    def set_aabb(self, xyz_max, xyz_min):
+        print("Deformation Net Set aabb", xyz_max, xyz_min)
+        self.grid.set_aabb(xyz_max, xyz_min)
+
+    def create_net(self):
+        feature_out = [nn.Linear(self.grid.feat_dim, self.W)]
+        for _ in range(self.D - 1):
+            feature_out.append(nn.ReLU())
+            feature_out.append(nn.Linear(self.W, self.W))
+        self.feature_out = nn.Sequential(*feature_out)
+        self.pos_deform = _head(self.W, 3)
+        self.scales_deform = _head(self.W, 3)
+        self.rotations_deform = _head(self.W, 4)
+        self.opacity_deform = _head(self.W, 1)
+        self.shs_deform = _head(self.W, 16 * 3)
+
+    @property
+    def get_empty_ratio(self):
+        return self.ratio
+
+    def forward(self, rays_pts_emb, scales_emb=None, rotations_emb=None, opacity=None, shs_emb=None, time_feature=None,
+                time_emb=None, scene_flow=None, frame_num=None, delta_scale=None):
+        if time_emb is None:
+            raise NotImplementedError("forward_static needs static_mlp, which the reference does not enable")
+        return self.forward_dynamic(rays_pts_emb, scales_emb, rotations_emb, opacity, shs_emb, time_feature, time_emb,
+                                    scene_flow, frame_num, delta_scale)
+
+    def forward_dynamic(self, rays_pts_emb, scales_emb, rotations_emb, opacity_emb, shs_emb, time_feature, time_emb,
+                        scene_flow, frame_num, delta_scale):
+        a = self.args
+        heads = (not a.no_dx, not a.no_ds, not a.no_dr)
+        weights = [self.feature_out[0].weight, self.feature_out[0].bias]
+        for m in (self.pos_deform, self.scales_deform, self.rotations_deform):
+            weights += [m[1].weight, m[1].bias, m[3].weight, m[3].bias]
+        xyz = rays_pts_emb[:, :3]
+        if scene_flow is None:
+            scene_flow = torch.zeros_like(xyz)
+        if frame_num is None:
+            frame_num = 0.0
+        if delta_scale is None:
+            delta_scale = 0.0
+        pts, scales, rotations = _DeformFn.apply(xyz, scales_emb[:, :3], rotations_emb[:, :4], time_emb[:, :1], scene_flow,
+                                                 frame_num, delta_scale, self.grid.aabb, len(self.grid.grids),
+                                                 tuple(self.grid._res), heads, *weights, *self.grid._planes())
+        opacity = opacity_emb[:, :1]
+        shs = shs_emb
+        return pts, scales, rotations, opacity, shs
+
+    def get_mlp_parameters(self):
+        return [p for n, p in self.named_parameters() if "grid" not in n]
+
+    def get_grid_parameters(self):
+        return [p for n, p in self.named_parameters() if "grid" in n]
+
+
+class deform_network(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        net_width = args.net_width
+        timebase_pe = args.timebase_pe
+        defor_depth = args.defor_depth
+        posbase_pe = args.posebase_pe
+        scale_rotation_pe = args.scale_rotation_pe
+        opacity_pe = args.opacity_pe
+        timenet_width = args.timenet_width
+        timenet_output = args.timenet_output
+        grid_pe = args.grid_pe
+        times_ch = 2 * timebase_pe + 1
+        self.timenet = nn.Sequential(nn.Linear(times_ch, timenet_width), nn.ReLU(), nn.Linear(timenet_width, timenet_output))
+        self.deformation_net = Deformation(W=net_width, D=defor_depth, input_ch=(3) + (3 * (posbase_pe)) * 2,
+                                           grid_pe=grid_pe, input_ch_time=timenet_output, args=args)
+        self.register_buffer('time_poc', torch.FloatTensor([(2 ** i) for i in range(timebase_pe)]))
+        self.register_buffer('pos_poc', torch.FloatTensor([(2 ** i) for i in range(posbase_pe)]))
+        self.register_buffer('rotation_scaling_poc', torch.FloatTensor([(2 ** i) for i in range(scale_rotation_pe)]))
+        self.register_buffer('opacity_poc', torch.FloatTensor([(2 ** i) for i in range(opacity_pe)]))
+        self.apply(initialize_weights)
+
+    def forward(self, point, scales=None, rotations=None, opacity=None, shs=None, times_sel=None, scene_flow=None,
+                frame_num=None, delta_scale=None):
+        return self.forward_dynamic(point, scales, rotations, opacity, shs, times_sel, scene_flow, frame_num, delta_scale)
+
+    @property
+    def get_aabb(self):
+        return self.deformation_net.get_aabb
+
+    @property
+    def get_empty_ratio(self):
+        return self.deformation_net.get_empty_ratio
+
+    def forward_dynamic(self, point, scales=None, rotations=None, opacity=None, shs=None, times_sel=None, scene_flow=None,
+                        frame_num=None, delta_scale=None):
+        # the reference embeds point/scales/rotations with sin/cos here and then uses only the raw
+        # leading columns (deformation.py:205-207, :107-135); the raw tensors are passed directly
+        return self.deformation_net(point, scales, rotations, opacity, shs, None, times_sel, scene_flow, frame_num,
+                                    delta_scale)
+
+    def get_mlp_parameters(self):
+        return self.deformation_net.get_mlp_parameters() + list(self.timenet.parameters())
+
+    def get_grid_parameters(self):
+        return self.deformation_net.get_grid_parameters()
+
+
+def initialize_weights(m):
+    # scene/deformation.py:229-235 (xavier twice when a bias exists; same RNG consumption)
+    if isinstance(m, nn.Linear):
+        init.xavier_uniform_(m.weight, gain=1)
+        if m.bias is not None:
+            init.xavier_uniform_(m.weight, gain=1)
+
+
+def poc_fre(input_data, poc_buf):
+    input_data_emb = (input_data.unsqueeze(-1) * poc_buf).flatten(-2)
+    return torch.cat([input_data, input_data_emb.sin(), input_data_emb.cos()], -1)

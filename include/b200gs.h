@@ -142,6 +142,57 @@ typedef struct { const float* src; float* dst; int row_floats; int reserved; } b
 int b200gs_gather_rows_multi(int n_tensors, const b200gs_gather_tensor* tensors /* host */,
                              const long long* index, long long n_out, b200gs_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Deformation field — replaces the PyTorch operator chains behind
+ * scene/hexplane.py::HexPlaneField.forward (:177, interpolate_ms_features :73-106: 6*levels
+ * F.grid_sample + products + cat) and scene/deformation.py::Deformation.forward_dynamic
+ * (:97-153: feature_out Linear + three ReLU-Linear-ReLU-Linear heads on cuBLAS), forward and
+ * backward. Planes are CHANNELS-LAST: plane[l][k] points at [res_b][res_a][32] floats for the
+ * coordinate pair k = (a,b) in (0,1)(0,2)(0,3)(1,2)(1,3)(2,3); res[l] = resolution of x,y,z,t.
+ * ------------------------------------------------------------------------------------- */
+#define B200GS_HEXPLANE_MAX_LEVELS 4
+typedef struct {
+    int levels;
+    int channels;                                   /* 32 */
+    int res[B200GS_HEXPLANE_MAX_LEVELS][4];
+    const float* plane[B200GS_HEXPLANE_MAX_LEVELS][6];
+    float* grad_plane[B200GS_HEXPLANE_MAX_LEVELS][6]; /* backward: accumulated into (caller zero-fills); null = skip */
+    const float* aabb;                              /* device, 6 floats: max xyz, then min xyz (hexplane.py:116-120) */
+} b200gs_hexplane_desc;
+
+/* features[P, 32*levels] = HexPlaneField(pts[P,3], t). times[P] may be null -> time_scalar for all. */
+int b200gs_hexplane_forward(const b200gs_hexplane_desc* desc /* host */, long long P, const float* pts,
+                            const float* times, float time_scalar, float* features, b200gs_stream_t stream);
+/* plane gradients are ACCUMULATED into desc->grad_plane; d_pts[P,3] (may be null) is written. */
+int b200gs_hexplane_backward(const b200gs_hexplane_desc* desc /* host */, long long P, const float* pts,
+                             const float* times, float time_scalar, const float* d_features, float* d_pts,
+                             b200gs_stream_t stream);
+
+typedef struct {
+    int feat_dim;                 /* 32 * levels (64 or 128) */
+    int width;                    /* net_width, 64 */
+    const float* w1; const float* b1;           /* feature_out.0  [64, feat_dim], [64] */
+    const float* w2[3]; const float* b2[3];     /* {pos,scales,rotations}_deform.1  [64,64],[64]; null = head off (no_dx/no_ds/no_dr) */
+    const float* w3[3]; const float* b3[3];     /* {pos,scales,rotations}_deform.3  [k,64],[k], k = 3,3,4 */
+} b200gs_mlp_weights;
+typedef struct { float* w1; float* b1; float* w2[3]; float* b2[3]; float* w3[3]; float* b3[3]; } b200gs_mlp_grads;
+
+/* floats of the activation stash the forward leaves for the backward */
+size_t b200gs_deform_mlp_saved_floats(long long P);
+/* pts_out = xyz + pos_head + delta_scale*(frame_num*scene_flow); scales_out = scales + scale_head;
+ * rot_out = rot + rot_head (deformation.py:113-135). frame_num_dev (device float, may be null)
+ * overrides frame_num: the reference hands frame_num over as a 0-d CUDA tensor (scene/dataset.py:39)
+ * and reading it on the host would cost a device sync per view. */
+int b200gs_deform_mlp_forward(const b200gs_mlp_weights* w /* host */, long long P, const float* features,
+                              const float* xyz, const float* scales, const float* rot, const float* scene_flow,
+                              float frame_num, const float* frame_num_dev, float delta_scale, float* pts_out, float* scales_out, float* rot_out,
+                              float* saved, b200gs_stream_t stream);
+/* weight gradients are ACCUMULATED into gw (caller zero-fills); d_features[P, feat_dim] is written.
+ * d_pts / d_scales / d_rot: upstream gradients of the three outputs (null = zero). */
+int b200gs_deform_mlp_backward(const b200gs_mlp_weights* w /* host */, const b200gs_mlp_grads* gw /* host */,
+                               long long P, const float* features, const float* saved, const float* d_pts,
+                               const float* d_scales, const float* d_rot, float* d_features, b200gs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

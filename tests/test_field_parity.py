@@ -1,0 +1,122 @@
+"""GPU parity: fused HexPlane + deformation-MLP kernels (through the drop-in nn.Modules) against
+the plain-PyTorch restatement of the reference modules (oracle/field_torch.py; F.grid_sample +
+F.linear on the same device). Tolerances: forward 2e-5 relative to the tensor's max-abs (FP32
+accumulation order differs from cuBLAS), gradients 1e-3 relative (north_star)."""
+import types
+
+import pytest
+import torch
+
+from oracle import field_torch as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _args(multires, T):
+    return types.SimpleNamespace(
+        net_width=64, timebase_pe=4, defor_depth=0, posebase_pe=10, scale_rotation_pe=2, opacity_pe=2,
+        timenet_width=64, timenet_output=32, bounds=1.6, grid_pe=0,
+        kplanes_config={'grid_dimensions': 2, 'input_coordinate_dim': 4, 'output_coordinate_dim': 32,
+                        'resolution': [64, 64, 64, T]},
+        multires=multires, no_dx=False, no_grid=False, no_ds=False, no_dr=False, no_do=True, no_dshs=True,
+        empty_voxel=False, static_mlp=False, apply_rotation=False)
+
+
+def _model(multires, T, seed=0):
+    from b200gs.field import deform_network
+    torch.manual_seed(seed)
+    net = deform_network(_args(multires, T)).cuda()
+    with torch.no_grad():
+        for p in net.deformation_net.grid.grids.parameters():
+            p.add_(torch.randn_like(p) * 0.01)       # make the time planes non-trivial
+        for n, p in net.named_parameters():
+            if n.endswith("bias"):
+                p.add_(torch.randn_like(p) * 0.05)
+    net.deformation_net.set_aabb([1.4, 1.3, 1.45], [-1.35, -1.4, -1.2])
+    return net
+
+
+def _inputs(P, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    xyz = (torch.rand(P, 3, generator=g) * 3.4 - 1.7).cuda()           # ~15% outside the aabb -> border clamp
+    scales = (torch.randn(P, 3, generator=g) * 0.6 - 5).cuda()
+    rot = torch.randn(P, 4, generator=g).cuda()
+    opacity = torch.randn(P, 1, generator=g).cuda()
+    shs = torch.randn(P, 16, 3, generator=g).cuda()
+    flow = (torch.randn(P, 3, generator=g) * 1e-3).cuda()
+    return xyz, scales, rot, opacity, shs, flow
+
+
+def _rel(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+@pytest.mark.parametrize("multires,T,P", [([1, 2], 50, 5000), ([1, 2], 50, 64), ([1, 2], 50, 1), ([1, 2, 4, 8], 25, 3001)])
+def test_deform_network_forward_backward(multires, T, P):
+    net = _model(multires, T)
+    levels = len(multires)
+    xyz, scales, rot, opacity, shs, flow = _inputs(P)
+    time = torch.full((P, 1), 0.37, device="cuda")
+    frame_num = torch.tensor(22, device="cuda")
+    sd = {k: v.detach().clone().contiguous().requires_grad_(v.dtype.is_floating_point) for k, v in net.state_dict().items()}
+
+    a = [t.clone().requires_grad_(True) for t in (xyz, scales, rot)]
+    pts, sc, rt, op, sh = net(a[0], a[1], a[2], opacity, shs, time, flow, frame_num, 1)
+    b = [t.clone().requires_grad_(True) for t in (xyz, scales, rot)]
+    rp, rs, rr, ro, rsh = oracle.deform_forward(sd, levels, b[0], b[1], b[2], opacity, shs, time, flow, frame_num, 1)
+    assert _rel(pts, rp) < 2e-5 and _rel(sc, rs) < 2e-5 and _rel(rt, rr) < 2e-5
+    assert torch.equal(op, ro) and sh is shs
+
+    g = torch.Generator().manual_seed(5)
+    wp, ws, wr = (torch.randn(P, 3, generator=g).cuda(), torch.randn(P, 3, generator=g).cuda(),
+                  torch.randn(P, 4, generator=g).cuda())
+    ((pts * wp).sum() + (sc * ws).sum() + (rt * wr).sum()).backward()
+    ((rp * wp).sum() + (rs * ws).sum() + (rr * wr).sum()).backward()
+    for x, y, name in zip(a, b, ("xyz", "scales", "rot")):
+        assert _rel(x.grad, y.grad) < 1e-3, name
+    params = dict(net.named_parameters())
+    checked = 0
+    for k, v in sd.items():
+        if not v.requires_grad or k.endswith("grid.aabb") or k not in params:
+            continue
+        p = params[k]
+        if v.grad is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert p.grad is not None, k
+        assert _rel(p.grad, v.grad) < 1e-3, (k, _rel(p.grad, v.grad))
+        checked += 1
+    assert checked >= 2 + 12 + 6 * levels
+    # never-used sub-networks get no gradient, exactly like the reference (Appendix C iii)
+    assert all(p.grad is None for n, p in net.named_parameters() if n.startswith("timenet") or "opacity_deform" in n or "shs_deform" in n)
+
+
+def test_hexplane_field_standalone_and_state_dict():
+    from b200gs.field import HexPlaneField, deform_network
+    torch.manual_seed(3)
+    cfg = {'grid_dimensions': 2, 'input_coordinate_dim': 4, 'output_coordinate_dim': 32, 'resolution': [64, 64, 64, 50]}
+    f = HexPlaneField(1.6, cfg, [1, 2]).cuda()
+    assert f.feat_dim == 64 and f.grids[1][0].shape == (1, 32, 128, 128) and f.grids[0][2].shape == (1, 32, 50, 64)
+    P = 777
+    g = torch.Generator().manual_seed(4)
+    pts = (torch.rand(P, 3, generator=g) * 4 - 2).cuda().requires_grad_(True)
+    t = torch.rand(P, 1, generator=g).cuda()
+    feat = f(pts, t)
+    planes = [p.detach().clone().contiguous().requires_grad_(True) for gp in f.grids for p in gp]
+    pts2 = pts.detach().clone().requires_grad_(True)
+    ref = oracle.hexplane_features(pts2, t, f.aabb.detach(), planes, 2)
+    assert _rel(feat, ref) < 1e-6
+    w = torch.randn(P, 64, generator=g).cuda()
+    (feat * w).sum().backward(); (ref * w).sum().backward()
+    assert _rel(pts.grad, pts2.grad) < 1e-3
+    for p, q in zip([p for gp in f.grids for p in gp], planes):
+        assert _rel(p.grad, q.grad) < 1e-3
+    # state_dict keys / shapes as the reference's checkpoints expect them
+    net = deform_network(_args([1, 2], 50))
+    keys = set(net.state_dict().keys())
+    for k in ["deformation_net.grid.aabb", "deformation_net.grid.grids.0.0", "deformation_net.grid.grids.1.5",
+              "deformation_net.feature_out.0.weight", "deformation_net.pos_deform.1.weight",
+              "deformation_net.rotations_deform.3.bias", "deformation_net.shs_deform.3.weight", "timenet.0.weight",
+              "timenet.2.bias", "time_poc", "pos_poc", "rotation_scaling_poc", "opacity_poc"]:
+        assert k in keys, k
+    assert len(net.get_grid_parameters()) == 13 and all("grid" not in n for n, _ in net.named_parameters() if False)
