@@ -1,0 +1,181 @@
+"""Host-side hot loop: the model state, `render()` and the view-parallel training step.
+
+This is the part of the reference's L2/L3 layers that the hot path needs, restated so that
+bench.py, the tests and the multi-GPU trainer can drive the kernels without the reference
+tree (which does not exist on the GPU box):
+  * `GaussianState`  — the tensors and optimiser groups of scene/gaussian_model.py:55-70, :190-209
+                       (same attribute names: _xyz, _features_dc, _features_rest, _scaling,
+                       _rotation, _opacity, _scene_flow, _deformation; same 8 Adam groups / lrs)
+  * `render()`       — gaussian_renderer/__init__.py:22-178 (settings, deformation in the fine
+                       stage, exp / normalize / sigmoid activations, rasterizer call, result dict)
+  * `ViewParallelTrainer` — train_4DGS.py:172-297 for a batch of views, with the batch sharded
+                       over ranks: every rank renders its views, one flat NCCL all-reduce sums the
+                       gradients (Gaussians | planes | MLP | screen-space xy), every rank takes
+                       the identical fused Adam step.
+With the real reference tree on sys.path, train_4DGS.py / render_4DGS.py run unchanged through
+b200gs.launcher instead.
+"""
+import math
+import types
+
+import torch
+import torch.nn as nn
+
+from .adam import FusedAdam
+from .field import deform_network
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+
+
+def default_hyper(multires=(1, 2), time_res=50):
+    """ModelHiddenParams as train_4DGS.py sees them with its default config
+    (arguments/__init__.py:75-106 overridden by arguments/dnerf/hellwarrior.py + dnerf_default.py)."""
+    return types.SimpleNamespace(
+        net_width=64, timebase_pe=4, defor_depth=0, posebase_pe=10, scale_rotation_pe=2, opacity_pe=2,
+        timenet_width=64, timenet_output=32, bounds=1.6, plane_tv_weight=0.0001, time_smoothness_weight=0.01,
+        l1_time_planes=0.0001, grid_pe=0,
+        kplanes_config={'grid_dimensions': 2, 'input_coordinate_dim': 4, 'output_coordinate_dim': 32,
+                        'resolution': [64, 64, 64, time_res]},
+        multires=list(multires), no_dx=False, no_grid=False, no_ds=False, no_dr=False, no_do=True, no_dshs=True,
+        empty_voxel=False, static_mlp=False, apply_rotation=False)
+
+
+def default_opt():
+    """OptimizationParams (arguments/__init__.py:110-151 + dnerf_default.py)."""
+    return types.SimpleNamespace(
+        position_lr_init=0.00016, position_lr_final=0.0000016, position_lr_delay_mult=0.01, position_lr_max_steps=20000,
+        deformation_lr_init=0.00016, deformation_lr_final=0.0000016, deformation_lr_delay_mult=0.01,
+        grid_lr_init=0.0016, grid_lr_final=0.000016, feature_lr=0.0025, opacity_lr=0.05, scaling_lr=0.005,
+        rotation_lr=0.001, percent_dense=0.01)
+
+
+class GaussianState(nn.Module):
+    def __init__(self, raw, sh_degree=3, hyper=None, spatial_lr_scale=1.0):
+        """raw: dict from b200gs.synthetic.make_gaussians (xyz, log_scale, rot, opacity_logit, shs, scene_flow)."""
+        super().__init__()
+        self.max_sh_degree = sh_degree
+        self.active_sh_degree = sh_degree
+        self.spatial_lr_scale = spatial_lr_scale
+        self._xyz = nn.Parameter(raw["xyz"].clone())
+        self._features_dc = nn.Parameter(raw["shs"][:, :1, :].clone().contiguous())
+        self._features_rest = nn.Parameter(raw["shs"][:, 1:, :].clone().contiguous())
+        self._scaling = nn.Parameter(raw["log_scale"].clone())
+        self._rotation = nn.Parameter(raw["rot"].clone())
+        self._opacity = nn.Parameter(raw["opacity_logit"].clone())
+        self.register_buffer("_scene_flow", raw["scene_flow"].clone())
+        self._deformation = deform_network(hyper or default_hyper())
+        self.optimizer = None
+
+    # accessors named as in scene/gaussian_model.py:117-147
+    @property
+    def get_xyz(self):
+        return self._xyz
+
+    @property
+    def get_features(self):
+        return torch.cat((self._features_dc, self._features_rest), dim=1)
+
+    @property
+    def get_flow(self):
+        return self._scene_flow
+
+    scaling_activation = staticmethod(torch.exp)
+    opacity_activation = staticmethod(torch.sigmoid)
+    rotation_activation = staticmethod(torch.nn.functional.normalize)
+
+    def training_setup(self, opt=None):
+        opt = opt or default_opt()
+        s = self.spatial_lr_scale
+        groups = [
+            {'params': [self._xyz], 'lr': opt.position_lr_init * s, "name": "xyz"},
+            {'params': list(self._deformation.get_mlp_parameters()), 'lr': opt.deformation_lr_init * s, "name": "deformation"},
+            {'params': list(self._deformation.get_grid_parameters()), 'lr': opt.grid_lr_init * s, "name": "grid"},
+            {'params': [self._features_dc], 'lr': opt.feature_lr, "name": "f_dc"},
+            {'params': [self._features_rest], 'lr': opt.feature_lr / 20.0, "name": "f_rest"},
+            {'params': [self._opacity], 'lr': opt.opacity_lr, "name": "opacity"},
+            {'params': [self._scaling], 'lr': opt.scaling_lr, "name": "scaling"},
+            {'params': [self._rotation], 'lr': opt.rotation_lr, "name": "rotation"}]
+        self.optimizer = FusedAdam(groups, lr=0.0, eps=1e-15)
+        return self.optimizer
+
+
+def render(cam, pc, bg_color, scaling_modifier=1.0, stage="fine", delta_scale=1, debug=False):
+    """gaussian_renderer/__init__.py:22-178 for a b200gs.synthetic.SynthCamera-like `cam`."""
+    means3D = pc.get_xyz
+    screenspace_points = torch.zeros_like(means3D, requires_grad=True)
+    settings = GaussianRasterizationSettings(
+        image_height=int(cam.image_height), image_width=int(cam.image_width), tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+        bg=bg_color, scale_modifier=scaling_modifier, viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix,
+        sh_degree=pc.active_sh_degree, campos=cam.campos, prefiltered=False, debug=debug)
+    rasterizer = GaussianRasterizer(raster_settings=settings)
+    opacity, shs, scales, rotations = pc._opacity, pc.get_features, pc._scaling, pc._rotation
+    if stage == "coarse":
+        m3, sc, rt, op, sh = means3D, scales, rotations, opacity, shs
+    else:
+        time = torch.full((means3D.shape[0], 1), float(cam.time), device=means3D.device)
+        m3, sc, rt, op, sh = pc._deformation(means3D, scales, rotations, opacity, shs, time, pc.get_flow,
+                                             cam.frame_num, delta_scale)
+    sc = pc.scaling_activation(sc)
+    rt = pc.rotation_activation(rt)
+    op = pc.opacity_activation(op)
+    image, radii, depth = rasterizer(means3D=m3, means2D=screenspace_points, shs=sh, colors_precomp=None,
+                                     opacities=op, scales=sc, rotations=rt, cov3D_precomp=None)
+    return {"render": image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii,
+            "depth": depth}
+
+
+class ViewParallelTrainer:
+    """One optimiser step over a batch of views sharded across ranks (replicated model)."""
+
+    def __init__(self, model, bg_color, stage="fine", process_group=None, world_size=1, rank=0):
+        self.model = model
+        self.bg = bg_color
+        self.stage = stage
+        self.pg = process_group
+        self.world_size = world_size
+        self.rank = rank
+        self.params = [p for g in model.optimizer.param_groups for p in g["params"]]
+        P = model.get_xyz.shape[0]
+        # flat gradient arena: [every parameter | screen-space xy per Gaussian]; p.grad are views into
+        # it, so autograd accumulates in place and ONE collective reduces everything
+        self.trainable = [p for p in self.params if p.requires_grad]
+        n = sum(p.numel() for p in self.trainable) + 3 * P
+        self.arena = torch.zeros(n, dtype=torch.float32, device=model.get_xyz.device)
+        self.views, off = [], 0
+        for p in self.trainable:
+            flat = self.arena[off:off + p.numel()]
+            if p.dim() == 4 and p.stride(1) == 1 and not p.is_contiguous():     # channels_last plane
+                N, C, H, W = p.shape
+                v = flat.view(N, H, W, C).permute(0, 3, 1, 2)
+            else:
+                v = flat.view(p.shape)
+            self.views.append(v)
+            off += p.numel()
+        self.viewspace_grad = self.arena[off:off + 3 * P].view(P, 3)
+        self.max_radii = torch.zeros(P, dtype=torch.int32, device=self.arena.device)
+
+    def _bind(self):
+        self.arena.zero_()
+        self.max_radii.zero_()
+        for p, v in zip(self.trainable, self.views):
+            p.grad = v
+
+    def step(self, cams, gts, global_batch=None):
+        """cams / gts: this rank's views. Loss = mean over the GLOBAL batch of per-view L1 means
+        (train_4DGS.py:205-210). Returns the local (already 1/B-scaled) loss tensor."""
+        B = global_batch or (len(cams) * self.world_size)
+        self._bind()
+        total = None
+        for cam, gt in zip(cams, gts):
+            pkg = render(cam, self.model, self.bg, stage=self.stage)
+            loss = (pkg["render"] - gt).abs().mean() / B
+            loss.backward()
+            self.viewspace_grad += pkg["viewspace_points"].grad
+            torch.maximum(self.max_radii, pkg["radii"], out=self.max_radii)
+            total = loss.detach() if total is None else total + loss.detach()
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.arena, op=dist.ReduceOp.SUM, group=self.pg)
+            dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=self.pg)
+        # parameters that never received a gradient keep grad None for the optimiser (torch skips them)
+        self.model.optimizer.step()
+        return total
