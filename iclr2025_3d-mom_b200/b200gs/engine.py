@@ -123,21 +123,36 @@ def render(cam, pc, bg_color, scaling_modifier=1.0, stage="fine", delta_scale=1,
             "depth": depth}
 
 
-class ViewParallelTrainer:
-    """One optimiser step over a batch of views sharded across ranks (replicated model)."""
+def _receives_grad(name, stage):
+    """Parameters the reference's loss reaches (SURVEY.md Appendix C iii): timenet, the opacity /
+    SH heads and the aabb never do; in the coarse stage the whole deformation field is bypassed."""
+    if name.startswith("_deformation."):
+        if stage == "coarse":
+            return False
+        return not ("timenet" in name or "opacity_deform" in name or "shs_deform" in name or name.endswith("grid.aabb"))
+    return True
 
-    def __init__(self, model, bg_color, stage="fine", process_group=None, world_size=1, rank=0):
+
+class ViewParallelTrainer:
+    """One optimiser step over a batch of views sharded across ranks (replicated model).
+
+    `render_fn(cam, model, bg, stage)` defaults to this module's `render`; tests inject a CPU
+    stand-in to exercise the sharding / flat-arena / collective logic over gloo."""
+
+    def __init__(self, model, bg_color, stage="fine", process_group=None, world_size=1, rank=0, render_fn=None):
         self.model = model
         self.bg = bg_color
         self.stage = stage
         self.pg = process_group
         self.world_size = world_size
         self.rank = rank
-        self.params = [p for g in model.optimizer.param_groups for p in g["params"]]
+        self.render_fn = render_fn or (lambda cam, m, bg, st: render(cam, m, bg, stage=st))
         P = model.get_xyz.shape[0]
-        # flat gradient arena: [every parameter | screen-space xy per Gaussian]; p.grad are views into
-        # it, so autograd accumulates in place and ONE collective reduces everything
-        self.trainable = [p for p in self.params if p.requires_grad]
+        # flat gradient arena: [every parameter the loss reaches | screen-space xy per Gaussian];
+        # p.grad are views into it, so autograd accumulates in place and ONE collective (fp32 sum
+        # over NVLink/NVSwitch) reduces everything. Parameters outside it keep grad None and the
+        # optimiser skips them, as torch does in the reference.
+        self.trainable = [p for n, p in model.named_parameters() if p.requires_grad and _receives_grad(n, stage)]
         n = sum(p.numel() for p in self.trainable) + 3 * P
         self.arena = torch.zeros(n, dtype=torch.float32, device=model.get_xyz.device)
         self.views, off = [], 0
@@ -159,23 +174,29 @@ class ViewParallelTrainer:
         for p, v in zip(self.trainable, self.views):
             p.grad = v
 
+    def local_views(self, n_global):
+        """Indices of the global batch this rank renders: view b goes to rank b mod world_size."""
+        return list(range(self.rank, n_global, self.world_size))
+
     def step(self, cams, gts, global_batch=None):
-        """cams / gts: this rank's views. Loss = mean over the GLOBAL batch of per-view L1 means
-        (train_4DGS.py:205-210). Returns the local (already 1/B-scaled) loss tensor."""
+        """cams / gts: THIS rank's views. Loss = mean over the GLOBAL batch of per-view L1 means
+        (train_4DGS.py:205-210: l1 over the concatenated [B,3,H,W] tensor). Returns the summed
+        local loss (already scaled by 1/B) as a tensor."""
         B = global_batch or (len(cams) * self.world_size)
         self._bind()
         total = None
         for cam, gt in zip(cams, gts):
-            pkg = render(cam, self.model, self.bg, stage=self.stage)
+            pkg = self.render_fn(cam, self.model, self.bg, self.stage)
             loss = (pkg["render"] - gt).abs().mean() / B
             loss.backward()
-            self.viewspace_grad += pkg["viewspace_points"].grad
+            vg = pkg["viewspace_points"].grad
+            if vg is not None:
+                self.viewspace_grad += vg
             torch.maximum(self.max_radii, pkg["radii"], out=self.max_radii)
             total = loss.detach() if total is None else total + loss.detach()
         if self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(self.arena, op=dist.ReduceOp.SUM, group=self.pg)
             dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=self.pg)
-        # parameters that never received a gradient keep grad None for the optimiser (torch skips them)
         self.model.optimizer.step()
         return total

@@ -1,0 +1,77 @@
+"""CPU, world_size 2 over gloo: the view-parallel step (sharding of the view batch, flat
+gradient arena, one SUM all-reduce + one MAX all-reduce, identical optimiser step on every rank)
+gives the same parameters as the single-process run over the whole batch.  The CUDA kernels are
+replaced by a small differentiable stand-in for `render`, the optimiser by torch.optim.Adam, so
+only the host-side multi-GPU logic is under test here (the kernels have their own GPU tests)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class TinyModel(nn.Module):
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(0)
+        self._xyz = nn.Parameter(torch.randn(50, 3, generator=g))
+        self._opacity = nn.Parameter(torch.randn(50, 1, generator=g))
+        plane = torch.rand(1, 4, 5, 6, generator=g).contiguous(memory_format=torch.channels_last)
+        self._deformation = nn.ParameterDict({"plane": nn.Parameter(plane), "timenet_w": nn.Parameter(torch.randn(3, 3, generator=g))})
+        self.optimizer = None
+
+    @property
+    def get_xyz(self):
+        return self._xyz
+
+
+def fake_render(cam, model, bg, stage):
+    """Differentiable stand-in: an 'image' that depends on xyz, opacity and the plane."""
+    sp = torch.zeros_like(model._xyz, requires_grad=True)
+    w = torch.sigmoid(model._opacity) * (model._xyz + sp).mul(cam).sum(1, keepdim=True)        # [50,1]
+    img = (w.sum() * model._deformation["plane"].mean(dim=(0, 1))).unsqueeze(0).expand(3, 5, 6) + bg[:, None, None]
+    radii = (model._xyz[:, 0].detach() * cam * 10).to(torch.int32).clamp_min(0)
+    return {"render": img, "viewspace_points": sp, "radii": radii}
+
+
+def _run(rank, world, port, ret):
+    sys.path.insert(0, os.path.join(ROOT, "iclr2025_3d-mom_b200"))
+    from b200gs.engine import ViewParallelTrainer
+    if world > 1:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    model = TinyModel()
+    model.optimizer = torch.optim.Adam([{"params": [model._xyz], "lr": 1e-2}, {"params": [model._opacity], "lr": 5e-2},
+                                        {"params": list(model._deformation.parameters()), "lr": 1e-3}], lr=0.0, eps=1e-15)
+    tr = ViewParallelTrainer(model, torch.tensor([0.1, 0.2, 0.3]), stage="fine", world_size=world, rank=rank,
+                             render_fn=fake_render)
+    cams = [0.5 + 0.25 * b for b in range(4)]
+    g = torch.Generator().manual_seed(1)
+    gts = [torch.rand(3, 5, 6, generator=g) for _ in range(4)]
+    for _ in range(3):
+        mine = tr.local_views(4)
+        tr.step([cams[i] for i in mine], [gts[i] for i in mine], global_batch=4)
+    out = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    out["viewspace"] = tr.viewspace_grad.clone(); out["max_radii"] = tr.max_radii.clone()
+    out["timenet_grad_is_none"] = model._deformation["timenet_w"].grad is None
+    ret[rank if world > 1 else -1] = out
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def test_two_rank_step_equals_single_process():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    _run(0, 1, 0, ret)
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_run, args=(2, port, ret), nprocs=2, join=True)
+    single, r0, r1 = ret[-1], ret[0], ret[1]
+    assert single["timenet_grad_is_none"] and r0["timenet_grad_is_none"]
+    for k in single:
+        if k == "timenet_grad_is_none":
+            continue
+        assert torch.equal(r0[k], r1[k]), f"ranks diverged on {k}"                  # replicas stay identical
+        assert torch.allclose(single[k].float(), r0[k].float(), rtol=1e-5, atol=1e-7), k
