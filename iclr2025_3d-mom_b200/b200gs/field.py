@@ -47,9 +47,39 @@ class _MlpGrads(ctypes.Structure):
 
 _P = ctypes.c_void_p
 _lib.register("b200gs_hexplane_forward", ctypes.c_int,
-              [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, ctypes.c_float, _P, _P])
+              [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, _P, ctypes.c_float, _P, _P])
 _lib.register("b200gs_hexplane_backward", ctypes.c_int,
-              [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, ctypes.c_float, _P, _P, _P])
+              [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, _P, ctypes.c_float, _P, _P, _P])
+_lib.register("b200gs_hexplane_order_scratch_bytes", ctypes.c_size_t, [ctypes.c_longlong])
+_lib.register("b200gs_hexplane_order", ctypes.c_int, [ctypes.c_longlong, _P, _P, _P, _P, ctypes.c_size_t, _P])
+
+_ORDER_CACHE = {}
+ORDER_MIN_POINTS = 1 << 14
+
+
+def _cell_order(pts, aabb):
+    """Cell-sorted visiting order of the query points (performance hint for the sampling kernels).
+    Cached per device on (storage, version): within one training iteration every view and the
+    backward pass query the same positions, so the sort is paid once per optimiser step."""
+    P = int(pts.shape[0])
+    if P < ORDER_MIN_POINTS:
+        return None
+    key = (pts.data_ptr(), pts._version, P, aabb.data_ptr(), aabb._version)
+    hit = _ORDER_CACHE.get(pts.device)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    L = _lib.lib()
+    order = torch.empty((P,), dtype=torch.int32, device=pts.device)
+    nbytes = L.b200gs_hexplane_order_scratch_bytes(P)
+    scratch = torch.empty((nbytes,), dtype=torch.uint8, device=pts.device)
+    check(L.b200gs_hexplane_order(P, pts.data_ptr(), aabb.data_ptr(), order.data_ptr(), scratch.data_ptr(), nbytes,
+                                  current_stream()), "hexplane_order")
+    _ORDER_CACHE[pts.device] = (key, order)
+    return order
+
+
+def _optr(order):
+    return order.data_ptr() if order is not None else None
 _lib.register("b200gs_deform_mlp_saved_floats", ctypes.c_size_t, [ctypes.c_longlong])
 _lib.register("b200gs_deform_mlp_forward", ctypes.c_int,
               [ctypes.POINTER(_MlpWeights), ctypes.c_longlong, _P, _P, _P, _P, _P, ctypes.c_float, _P, ctypes.c_float,
@@ -114,10 +144,13 @@ class _HexPlaneFn(torch.autograd.Function):
         tt, ts = _times_arg(times, P)
         feat = torch.empty((P, 32 * levels), dtype=torch.float32, device=pts.device)
         d = _hex_desc(aabb, planes, levels, res)
-        check(_lib.lib().b200gs_hexplane_forward(ctypes.byref(d), P, pts.data_ptr(), tt.data_ptr() if tt is not None else None,
-                                                 ts, feat.data_ptr(), current_stream()), "hexplane_forward")
+        order = _cell_order(pts, aabb)
+        check(_lib.lib().b200gs_hexplane_forward(ctypes.byref(d), P, pts.data_ptr(), _optr(order),
+                                                 tt.data_ptr() if tt is not None else None, ts, feat.data_ptr(),
+                                                 current_stream()), "hexplane_forward")
         ctx.save_for_backward(pts, tt if tt is not None else torch.empty(0), aabb, *planes)
         ctx.meta = (levels, res, ts, tt is not None)
+        ctx.order = order
         return feat
 
     @staticmethod
@@ -129,8 +162,8 @@ class _HexPlaneFn(torch.autograd.Function):
         grads = [torch.zeros_like(p, memory_format=torch.preserve_format) if n else None for p, n in zip(planes, need_planes)]
         d_pts = torch.empty_like(pts) if ctx.needs_input_grad[0] else None
         d = _hex_desc(aabb, planes, levels, res, grads)
-        check(_lib.lib().b200gs_hexplane_backward(ctypes.byref(d), P, pts.data_ptr(), tt.data_ptr() if has_t else None, ts,
-                                                  d_feat.contiguous().data_ptr(),
+        check(_lib.lib().b200gs_hexplane_backward(ctypes.byref(d), P, pts.data_ptr(), _optr(ctx.order),
+                                                  tt.data_ptr() if has_t else None, ts, d_feat.contiguous().data_ptr(),
                                                   d_pts.data_ptr() if d_pts is not None else None, current_stream()),
               "hexplane_backward")
         return (d_pts, None, None, None, None, *grads)
@@ -157,8 +190,11 @@ class _DeformFn(torch.autograd.Function):
         tt, ts = _times_arg(times, P)
         feat = torch.empty((P, 32 * levels), dtype=torch.float32, device=dev)
         d = _hex_desc(aabb, planes, levels, res)
-        check(L.b200gs_hexplane_forward(ctypes.byref(d), P, xyz.data_ptr(), tt.data_ptr() if tt is not None else None, ts,
-                                        feat.data_ptr(), stream), "hexplane_forward")
+        order = _cell_order(xyz, aabb)
+        ctx.order = order
+        check(L.b200gs_hexplane_forward(ctypes.byref(d), P, xyz.data_ptr(), _optr(order),
+                                        tt.data_ptr() if tt is not None else None, ts, feat.data_ptr(), stream),
+              "hexplane_forward")
         mw = _DeformFn._weights_struct(weights, heads, 32 * levels)
         saved = torch.empty((L.b200gs_deform_mlp_saved_floats(P),), dtype=torch.float32, device=dev)
         pts_o = torch.empty_like(xyz); scales_o = torch.empty_like(scales); rot_o = torch.empty_like(rot)
@@ -215,8 +251,9 @@ class _DeformFn(torch.autograd.Function):
         gplanes = [torch.zeros_like(p, memory_format=torch.preserve_format) for p in planes]
         d_xyz_grid = torch.empty_like(xyz)
         d = _hex_desc(aabb, planes, levels, res, gplanes)
-        check(L.b200gs_hexplane_backward(ctypes.byref(d), P, xyz.data_ptr(), tt.data_ptr() if has_t else None, ts,
-                                         d_feat.data_ptr(), d_xyz_grid.data_ptr(), stream), "hexplane_backward")
+        check(L.b200gs_hexplane_backward(ctypes.byref(d), P, xyz.data_ptr(), _optr(ctx.order),
+                                         tt.data_ptr() if has_t else None, ts, d_feat.data_ptr(), d_xyz_grid.data_ptr(),
+                                         stream), "hexplane_backward")
         # pts = xyz*1 + ..., scales = scales*1 + ds, rot = rot + dr: identity paths
         d_xyz = d_xyz_grid + d_pts if d_pts is not None else d_xyz_grid
         gw_out = [g if (g is not None) else None for g in gws]

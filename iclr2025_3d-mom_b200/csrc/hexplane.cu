@@ -15,6 +15,7 @@
 // [1,32,H,W] shape with torch.channels_last strides): one warp handles one point with one
 // lane per channel, so every texel fetch is a single coalesced 128-byte line.
 #include "common.cuh"
+#include "radix_sort.cuh"
 #include "../../include/b200gs.h"
 
 namespace b200gs {
@@ -24,8 +25,6 @@ namespace {
 constexpr int HP_C = 32;                 // channels per plane (output_coordinate_dim)
 constexpr int HP_MAXL = B200GS_HEXPLANE_MAX_LEVELS;
 
-__constant__ int kPairA[6] = {0, 0, 0, 1, 1, 2};
-__constant__ int kPairB[6] = {1, 2, 3, 2, 3, 3};
 
 struct Bilinear {
     int o_nw, o_ne, o_sw, o_se;          // texel offsets (in texels), -1 if out of bounds
@@ -67,23 +66,29 @@ __device__ __forceinline__ Bilinear bilinear_setup(float x, float y, int W, int 
     return b;
 }
 
-__device__ __forceinline__ float4 load_corners(const float* __restrict__ plane, const Bilinear& b, int lane)
+// ---- 128-bit path: a warp serves FOUR points at once; the 8 lanes of a point slot own 4 channels
+// each, so one LDG.128 per lane fetches a whole 128-byte texel per slot. Points are visited in
+// `order` (a cell-sorted permutation, see hexplane_order below) so that neighbouring warps touch
+// the same few texels and the gathers are served by L1 instead of L2.
+__device__ __forceinline__ float4 ld4(const float* __restrict__ plane, int texel, int cg)
 {
-    float4 v;
-    v.x = b.o_nw >= 0 ? __ldg(plane + (size_t)b.o_nw * HP_C + lane) : 0.f;
-    v.y = b.o_ne >= 0 ? __ldg(plane + (size_t)b.o_ne * HP_C + lane) : 0.f;
-    v.z = b.o_sw >= 0 ? __ldg(plane + (size_t)b.o_sw * HP_C + lane) : 0.f;
-    v.w = b.o_se >= 0 ? __ldg(plane + (size_t)b.o_se * HP_C + lane) : 0.f;
-    return v;
+    return texel >= 0 ? __ldg(reinterpret_cast<const float4*>(plane + (size_t)texel * HP_C) + cg)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-__device__ __forceinline__ float interp(const float4 v, const Bilinear& b)
+__device__ __forceinline__ float interp1(float nw, float ne, float sw, float se, const Bilinear& b)
 {
-    float acc = __fmul_rn(v.x, b.w_nw);
-    acc = __fmaf_rn(v.y, b.w_ne, acc);
-    acc = __fmaf_rn(v.z, b.w_sw, acc);
-    acc = __fmaf_rn(v.w, b.w_se, acc);
+    float acc = __fmul_rn(nw, b.w_nw);
+    acc = __fmaf_rn(ne, b.w_ne, acc);
+    acc = __fmaf_rn(sw, b.w_sw, acc);
+    acc = __fmaf_rn(se, b.w_se, acc);
     return acc;
+}
+
+__device__ __forceinline__ float4 interp4(const float4 nw, const float4 ne, const float4 sw, const float4 se, const Bilinear& b)
+{
+    return make_float4(interp1(nw.x, ne.x, sw.x, se.x, b), interp1(nw.y, ne.y, sw.y, se.y, b),
+                       interp1(nw.z, ne.z, sw.z, se.z, b), interp1(nw.w, ne.w, sw.w, se.w, b));
 }
 
 __device__ __forceinline__ void normalized_coords(const float* __restrict__ pts, const float* __restrict__ times,
@@ -99,104 +104,165 @@ __device__ __forceinline__ void normalized_coords(const float* __restrict__ pts,
     c[3] = times ? __ldg(times + g) : time_scalar;
 }
 
+template <int K> struct Pair;
+template <> struct Pair<0> { static constexpr int a = 0, b = 1; };
+template <> struct Pair<1> { static constexpr int a = 0, b = 2; };
+template <> struct Pair<2> { static constexpr int a = 0, b = 3; };
+template <> struct Pair<3> { static constexpr int a = 1, b = 2; };
+template <> struct Pair<4> { static constexpr int a = 1, b = 3; };
+template <> struct Pair<5> { static constexpr int a = 2, b = 3; };
+
+template <int K>
+__device__ __forceinline__ float4 sample_plane(const b200gs_hexplane_desc& d, int l, const float c[4], int cg, Bilinear& b)
+{
+    b = bilinear_setup(c[Pair<K>::a], c[Pair<K>::b], d.res[l][Pair<K>::a], d.res[l][Pair<K>::b]);
+    const float* plane = d.plane[l][K];
+    return interp4(ld4(plane, b.o_nw, cg), ld4(plane, b.o_ne, cg), ld4(plane, b.o_sw, cg), ld4(plane, b.o_se, cg), b);
+}
+
+__device__ __forceinline__ float4 mul4(const float4 a, const float4 b)
+{
+    return make_float4(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y), __fmul_rn(a.z, b.z), __fmul_rn(a.w, b.w));
+}
+
 __global__ void __launch_bounds__(256)
 hexplane_fwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, long long P, const float* __restrict__ pts,
-                    const float* __restrict__ times, float time_scalar, float* __restrict__ feat)
+                    const unsigned int* __restrict__ order, const float* __restrict__ times, float time_scalar,
+                    float* __restrict__ feat)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, slot = lane >> 3, cg = lane & 7;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int F = d.levels * HP_C;
-    for (long long g = warp0; g < P; g += nwarps) {
+    for (long long base = warp0 * 4; base < P; base += nwarps * 4) {
+        const long long i = base + slot;
+        if (i >= P) continue;
+        const size_t g = order ? (size_t)__ldg(order + i) : (size_t)i;
         float c[4], scale[3];
-        normalized_coords(pts, times, time_scalar, d.aabb, (size_t)g, c, scale);
+        normalized_coords(pts, times, time_scalar, d.aabb, g, c, scale);
         for (int l = 0; l < d.levels; ++l) {
-            float4 v[6];
-            Bilinear bl[6];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const int a = kPairA[k], b = kPairB[k];
-                bl[k] = bilinear_setup(c[a], c[b], d.res[l][a], d.res[l][b]);
-                v[k] = load_corners(d.plane[l][k], bl[k], lane);
-            }
-            float f = 1.f;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) f = __fmul_rn(f, interp(v[k], bl[k]));
-            feat[(size_t)g * F + l * HP_C + lane] = f;
+            Bilinear b;
+            float4 f = make_float4(1.f, 1.f, 1.f, 1.f);
+            f = mul4(f, sample_plane<0>(d, l, c, cg, b));
+            f = mul4(f, sample_plane<1>(d, l, c, cg, b));
+            f = mul4(f, sample_plane<2>(d, l, c, cg, b));
+            f = mul4(f, sample_plane<3>(d, l, c, cg, b));
+            f = mul4(f, sample_plane<4>(d, l, c, cg, b));
+            f = mul4(f, sample_plane<5>(d, l, c, cg, b));
+            *reinterpret_cast<float4*>(feat + g * F + l * HP_C + cg * 4) = f;
         }
     }
 }
 
-// Backward: plane gradients (atomic accumulation of coalesced 128-byte lines) and the
-// gradient w.r.t. the query points (through grid_sample's grid input; the time coordinate
-// is a constant and receives none).
-__global__ void __launch_bounds__(256)
-hexplane_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, long long P, const float* __restrict__ pts,
-                    const float* __restrict__ times, float time_scalar, const float* __restrict__ dfeat,
-                    float* __restrict__ dpts /* [P,3], written */)
+// Backward for one plane: plane-gradient scatter (128-bit vector reductions) and this lane's share of
+// the coordinate gradient (ATen grid_sampler_2d_backward).
+template <int K>
+__device__ __forceinline__ void plane_backward(const b200gs_hexplane_desc& d, int l, const float c[4], int cg,
+                                               const float4 gv, float gc[3])
 {
-    const int lane = threadIdx.x & 31;
+    const Bilinear b = bilinear_setup(c[Pair<K>::a], c[Pair<K>::b], d.res[l][Pair<K>::a], d.res[l][Pair<K>::b]);
+    const float* plane = d.plane[l][K];
+    float* gp = d.grad_plane[l][K];
+    const float4 nw = ld4(plane, b.o_nw, cg), ne = ld4(plane, b.o_ne, cg), sw = ld4(plane, b.o_sw, cg), se = ld4(plane, b.o_se, cg);
+    if (gp != nullptr && (gv.x != 0.f || gv.y != 0.f || gv.z != 0.f || gv.w != 0.f)) {
+        if (b.o_nw >= 0) red_add_v4(gp + (size_t)b.o_nw * HP_C + cg * 4, gv.x * b.w_nw, gv.y * b.w_nw, gv.z * b.w_nw, gv.w * b.w_nw);
+        if (b.o_ne >= 0) red_add_v4(gp + (size_t)b.o_ne * HP_C + cg * 4, gv.x * b.w_ne, gv.y * b.w_ne, gv.z * b.w_ne, gv.w * b.w_ne);
+        if (b.o_sw >= 0) red_add_v4(gp + (size_t)b.o_sw * HP_C + cg * 4, gv.x * b.w_sw, gv.y * b.w_sw, gv.z * b.w_sw, gv.w * b.w_sw);
+        if (b.o_se >= 0) red_add_v4(gp + (size_t)b.o_se * HP_C + cg * 4, gv.x * b.w_se, gv.y * b.w_se, gv.z * b.w_se, gv.w * b.w_se);
+    }
+    const float fx = (float)b.ix_nw, fy = (float)b.iy_nw;
+    const float wx1 = (fx + 1.f) - b.ix, wx0 = b.ix - fx, wy1 = (fy + 1.f) - b.iy, wy0 = b.iy - fy;
+    auto one = [&](float vnw, float vne, float vsw, float vse, float g, float& gix, float& giy) {
+        gix += (-vnw * wy1 + vne * wy1 - vsw * wy0 + vse * wy0) * g;
+        giy += (-vnw * wx1 - vne * wx0 + vsw * wx1 + vse * wx0) * g;
+    };
+    float gix = 0.f, giy = 0.f;
+    one(nw.x, ne.x, sw.x, se.x, gv.x, gix, giy);
+    one(nw.y, ne.y, sw.y, se.y, gv.y, gix, giy);
+    one(nw.z, ne.z, sw.z, se.z, gv.z, gix, giy);
+    one(nw.w, ne.w, sw.w, se.w, gv.w, gix, giy);
+    if (Pair<K>::a < 3) gc[Pair<K>::a] += b.gx_mult * gix;
+    if (Pair<K>::b < 3) gc[Pair<K>::b] += b.gy_mult * giy;
+}
+
+__global__ void __launch_bounds__(256, 2)
+hexplane_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, long long P, const float* __restrict__ pts,
+                    const unsigned int* __restrict__ order, const float* __restrict__ times, float time_scalar,
+                    const float* __restrict__ dfeat, float* __restrict__ dpts /* [P,3], written */)
+{
+    const int lane = threadIdx.x & 31, slot = lane >> 3, cg = lane & 7;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int F = d.levels * HP_C;
-    for (long long g = warp0; g < P; g += nwarps) {
+    for (long long base = warp0 * 4; base < P; base += nwarps * 4) {
+        const long long i = base + slot;
+        const bool valid = i < P;
+        const size_t g = valid ? (order ? (size_t)__ldg(order + i) : (size_t)i) : 0;
         float c[4], scale[3];
-        normalized_coords(pts, times, time_scalar, d.aabb, (size_t)g, c, scale);
-        float gc[3] = {0.f, 0.f, 0.f};          // per-lane partial d loss / d normalised coord
-        for (int l = 0; l < d.levels; ++l) {
-            float4 v[6];
-            Bilinear bl[6];
-            float val[6];
+        normalized_coords(pts, times, time_scalar, d.aabb, g, c, scale);
+        float gc[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+            for (int l = 0; l < d.levels; ++l) {
+                Bilinear b;
+                float4 v[6];
+                v[0] = sample_plane<0>(d, l, c, cg, b); v[1] = sample_plane<1>(d, l, c, cg, b);
+                v[2] = sample_plane<2>(d, l, c, cg, b); v[3] = sample_plane<3>(d, l, c, cg, b);
+                v[4] = sample_plane<4>(d, l, c, cg, b); v[5] = sample_plane<5>(d, l, c, cg, b);
+                const float4 go = __ldg(reinterpret_cast<const float4*>(dfeat + g * F + l * HP_C + cg * 4));
+                float4 pre[6], suf[6];
+                pre[0] = make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const int a = kPairA[k], b = kPairB[k];
-                bl[k] = bilinear_setup(c[a], c[b], d.res[l][a], d.res[l][b]);
-                v[k] = load_corners(d.plane[l][k], bl[k], lane);
-                val[k] = interp(v[k], bl[k]);
-            }
-            const float go = __ldg(dfeat + (size_t)g * F + l * HP_C + lane);
-            // prefix / suffix products give d feature / d val[k] without divisions
-            float pre[6], suf[6];
-            pre[0] = 1.f;
+                for (int k = 1; k < 6; ++k) pre[k] = make_float4(pre[k - 1].x * v[k - 1].x, pre[k - 1].y * v[k - 1].y, pre[k - 1].z * v[k - 1].z, pre[k - 1].w * v[k - 1].w);
+                suf[5] = make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
-            for (int k = 1; k < 6; ++k) pre[k] = pre[k - 1] * val[k - 1];
-            suf[5] = 1.f;
-#pragma unroll
-            for (int k = 4; k >= 0; --k) suf[k] = suf[k + 1] * val[k + 1];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const float gv = go * pre[k] * suf[k];
-                const Bilinear& b = bl[k];
-                float* gp = d.grad_plane[l][k];
-                if (gp != nullptr && gv != 0.f) {
-                    if (b.o_nw >= 0) atomicAdd(gp + (size_t)b.o_nw * HP_C + lane, gv * b.w_nw);
-                    if (b.o_ne >= 0) atomicAdd(gp + (size_t)b.o_ne * HP_C + lane, gv * b.w_ne);
-                    if (b.o_sw >= 0) atomicAdd(gp + (size_t)b.o_sw * HP_C + lane, gv * b.w_sw);
-                    if (b.o_se >= 0) atomicAdd(gp + (size_t)b.o_se * HP_C + lane, gv * b.w_se);
-                }
-                // ATen grid_sampler_2d_backward: gix, giy
-                const float fx = (float)b.ix_nw, fy = (float)b.iy_nw;
-                const float ix_e = fx + 1.f, iy_s = fy + 1.f;
-                float gix = -v[k].x * (iy_s - b.iy) * gv + v[k].y * (iy_s - b.iy) * gv
-                            - v[k].z * (b.iy - fy) * gv + v[k].w * (b.iy - fy) * gv;
-                float giy = -v[k].x * (ix_e - b.ix) * gv - v[k].y * (b.ix - fx) * gv
-                            + v[k].z * (ix_e - b.ix) * gv + v[k].w * (b.ix - fx) * gv;
-                const int a = kPairA[k], bb = kPairB[k];
-                if (a < 3) gc[a] += b.gx_mult * gix;
-                if (bb < 3) gc[bb] += b.gy_mult * giy;
+                for (int k = 4; k >= 0; --k) suf[k] = make_float4(suf[k + 1].x * v[k + 1].x, suf[k + 1].y * v[k + 1].y, suf[k + 1].z * v[k + 1].z, suf[k + 1].w * v[k + 1].w);
+                auto gvk = [&](int k) { return make_float4(go.x * pre[k].x * suf[k].x, go.y * pre[k].y * suf[k].y, go.z * pre[k].z * suf[k].z, go.w * pre[k].w * suf[k].w); };
+                plane_backward<0>(d, l, c, cg, gvk(0), gc); plane_backward<1>(d, l, c, cg, gvk(1), gc);
+                plane_backward<2>(d, l, c, cg, gvk(2), gc); plane_backward<3>(d, l, c, cg, gvk(3), gc);
+                plane_backward<4>(d, l, c, cg, gvk(4), gc); plane_backward<5>(d, l, c, cg, gvk(5), gc);
             }
         }
         if (dpts != nullptr) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 float s = gc[a];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
                 gc[a] = s * scale[a];
             }
-            if (lane < 3) dpts[3 * (size_t)g + lane] = lane == 0 ? gc[0] : (lane == 1 ? gc[1] : gc[2]);
+            if (valid && cg < 3) dpts[3 * g + cg] = cg == 0 ? gc[0] : (cg == 1 ? gc[1] : gc[2]);
         }
     }
+}
+
+// ---- cell order: a permutation of the points sorted by an 8-bit-per-axis Morton code of their
+// normalised position (a pure performance hint: any permutation gives the same results).
+__device__ __forceinline__ unsigned int spread8(unsigned int x)
+{
+    x = (x | (x << 16)) & 0x0300000Fu;
+    x = (x | (x << 8)) & 0x0300F00Fu;
+    x = (x | (x << 4)) & 0x030C30C3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+
+__global__ void __launch_bounds__(256)
+hexplane_cellkey_kernel(long long P, const float* __restrict__ pts, const float* __restrict__ aabb,
+                        unsigned int* __restrict__ keys, unsigned int* __restrict__ ids)
+{
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= P) return;
+    unsigned int key = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float a0 = __ldg(aabb + a), a1 = __ldg(aabb + 3 + a);
+        float n = ((__ldg(pts + 3 * (size_t)i + a) - a0) / (a1 - a0));          // 0..1 inside the box
+        n = fminf(fmaxf(n, 0.f), 1.f);
+        key |= spread8((unsigned int)(n * 255.f)) << a;
+    }
+    keys[i] = key;
+    ids[i] = (unsigned int)i;
 }
 
 int validate(const b200gs_hexplane_desc* d)
@@ -214,7 +280,7 @@ int validate(const b200gs_hexplane_desc* d)
 
 int grid_for(long long P)
 {
-    long long blocks = (P + 7) / 8;                  // 8 warps (= points in flight) per block
+    long long blocks = (P + 31) / 32;                // 8 warps x 4 point slots per block
     const long long cap = (long long)NUM_SMS * 8;    // persistent-style cap: 8 resident blocks per SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
@@ -228,21 +294,45 @@ using namespace b200gs;
 
 extern "C" {
 
-int b200gs_hexplane_forward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const float* times,
-                            float time_scalar, float* features, b200gs_stream_t stream)
+size_t b200gs_hexplane_order_scratch_bytes(long long P)
+{
+    const size_t n = P > 0 ? (size_t)P : 0;
+    return 3 * align_up(n * sizeof(u32), 256) + radix_plan(n, 0, 24).temp_bytes + 256;
+}
+
+int b200gs_hexplane_order(long long P, const float* pts, const float* aabb, unsigned int* order, void* scratch,
+                          size_t scratch_bytes, b200gs_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (P <= 0) return 0;
+    if (scratch_bytes < b200gs_hexplane_order_scratch_bytes(P)) { set_error("hexplane_order: scratch too small"); return -1; }
+    Carver c(scratch);
+    u32* keys_a = c.take<u32>((size_t)P); u32* keys_b = c.take<u32>((size_t)P); u32* ids_b = c.take<u32>((size_t)P);
+    const size_t tb = radix_plan((size_t)P, 0, 24).temp_bytes;
+    void* temp = c.take<char>(tb);
+    hexplane_cellkey_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(P, pts, aabb, keys_a, order);
+    const int side = radix_sort_pairs(keys_a, order, keys_b, ids_b, (size_t)P, 0, 24, temp, tb, stream);
+    if (side < 0) return -1;
+    if (side == 1) cudaMemcpyAsync(order, ids_b, (size_t)P * sizeof(u32), cudaMemcpyDeviceToDevice, stream);
+    return check_launch("hexplane_order");
+}
+
+int b200gs_hexplane_forward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
+                            const float* times, float time_scalar, float* features, b200gs_stream_t stream)
 {
     if (validate(desc)) return -1;
     if (P <= 0) return 0;
-    hexplane_fwd_kernel<<<grid_for(P), 256, 0, (cudaStream_t)stream>>>(*desc, P, pts, times, time_scalar, features);
+    hexplane_fwd_kernel<<<grid_for(P), 256, 0, (cudaStream_t)stream>>>(*desc, P, pts, order, times, time_scalar, features);
     return check_launch("hexplane_forward");
 }
 
-int b200gs_hexplane_backward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const float* times,
-                             float time_scalar, const float* d_features, float* d_pts, b200gs_stream_t stream)
+int b200gs_hexplane_backward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
+                             const float* times, float time_scalar, const float* d_features, float* d_pts,
+                             b200gs_stream_t stream)
 {
     if (validate(desc)) return -1;
     if (P <= 0) return 0;
-    hexplane_bwd_kernel<<<grid_for(P), 256, 0, (cudaStream_t)stream>>>(*desc, P, pts, times, time_scalar, d_features, d_pts);
+    hexplane_bwd_kernel<<<grid_for(P), 256, 0, (cudaStream_t)stream>>>(*desc, P, pts, order, times, time_scalar, d_features, d_pts);
     return check_launch("hexplane_backward");
 }
 

@@ -160,13 +160,20 @@ typedef struct {
     const float* aabb;                              /* device, 6 floats: max xyz, then min xyz (hexplane.py:116-120) */
 } b200gs_hexplane_desc;
 
+/* Optional visiting order: order[P] = permutation of the points sorted by the cell they fall in, so
+ * neighbouring warps touch the same texels (L1 hits instead of L2 gathers). Purely a performance hint:
+ * results do not depend on it; pass null to visit points in index order. */
+size_t b200gs_hexplane_order_scratch_bytes(long long P);
+int b200gs_hexplane_order(long long P, const float* pts, const float* aabb, unsigned int* order, void* scratch,
+                          size_t scratch_bytes, b200gs_stream_t stream);
 /* features[P, 32*levels] = HexPlaneField(pts[P,3], t). times[P] may be null -> time_scalar for all. */
 int b200gs_hexplane_forward(const b200gs_hexplane_desc* desc /* host */, long long P, const float* pts,
-                            const float* times, float time_scalar, float* features, b200gs_stream_t stream);
+                            const unsigned int* order, const float* times, float time_scalar, float* features,
+                            b200gs_stream_t stream);
 /* plane gradients are ACCUMULATED into desc->grad_plane; d_pts[P,3] (may be null) is written. */
 int b200gs_hexplane_backward(const b200gs_hexplane_desc* desc /* host */, long long P, const float* pts,
-                             const float* times, float time_scalar, const float* d_features, float* d_pts,
-                             b200gs_stream_t stream);
+                             const unsigned int* order, const float* times, float time_scalar,
+                             const float* d_features, float* d_pts, b200gs_stream_t stream);
 
 typedef struct {
     int feat_dim;                 /* 32 * levels (64 or 128) */

@@ -51,7 +51,8 @@ def _rel(a, b):
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
 
-@pytest.mark.parametrize("multires,T,P", [([1, 2], 50, 5000), ([1, 2], 50, 64), ([1, 2], 50, 1), ([1, 2, 4, 8], 25, 3001)])
+@pytest.mark.parametrize("multires,T,P", [([1, 2], 50, 5000), ([1, 2], 50, 64), ([1, 2], 50, 1), ([1, 2, 4, 8], 25, 3001),
+                                          ([1, 2], 50, 40003)])   # >= 16384 points: cell-ordered traversal
 def test_deform_network_forward_backward(multires, T, P):
     net = _model(multires, T)
     levels = len(multires)
