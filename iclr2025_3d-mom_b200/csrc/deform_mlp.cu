@@ -1,4 +1,5 @@
-// Deformation MLP (feature decoder + position / scale / rotation heads), forward and backward.
+// Deformation MLP (feature decoder + position / scale / rotation heads), forward and backward,
+// on the tensor cores.
 //
 // Restates scene/deformation.py:55-65 (create_net), :68-85 (query_time) and :97-153
 // (forward_dynamic) for the configuration the reference trains with:
@@ -6,12 +7,18 @@
 //     d{x,s,r} = Linear(64, k)(ReLU(Linear(64, 64)(ReLU(hidden))))      k = 3, 3, 4
 //     pts   = xyz * 1 + (dx + delta_scale * (frame_num * scene_flow))
 //     scale = scales * 1 + ds ;  rot = rotations + dr
-// The reference runs seven cuBLAS SGEMMs with every [P,64] intermediate round-tripping HBM
-// plus ~20 elementwise launches; here a persistent CTA keeps all weights in shared memory,
-// walks 64-point tiles through register-tiled FP32 GEMMs, and only the ReLU'd activations
-// needed by the backward pass (4 x 256 B per point) leave the SM.  The backward pass
-// accumulates every weight gradient in registers across all tiles of a CTA and flushes them
-// with one atomic per element per CTA.
+// The reference runs seven true-FP32 cuBLAS SGEMMs (TF32 is off by default in torch) with every
+// [P,64] intermediate round-tripping HBM.  Here each warp owns 16 points and carries them through
+// the whole chain in REGISTERS: every contraction is an m16n8k8 TF32 tensor-core MMA issued three
+// times on an error-compensated split (x = hi + lo; hi*hi + lo*hi + hi*lo), which restores ~FP32
+// accuracy (2^-21 relative) while the accumulation stays FP32.  The accumulator fragment of one
+// layer is re-used directly as the A fragment of the next by permuting the K index (fragment slot t
+// <-> column 2t, slot t+4 <-> column 2t+1; the weights are laid out in shared memory to match), so
+// no shuffle or shared-memory transpose sits between layers.  Weights are split once per CTA into
+// {hi_k, hi_k+1, lo_k, lo_k+1} float4s (one conflict-free LDS.128 per k-step and n-tile).  Only the
+// ReLU'd activations the backward needs (4 x 256 B per point, plain row-major) leave the SM.
+// The backward accumulates all weight gradients in register fragments across every tile a
+// persistent CTA processes and flushes them with one atomic per element per CTA.
 #include "common.cuh"
 #include "../../include/b200gs.h"
 
@@ -19,10 +26,61 @@ namespace b200gs {
 
 namespace {
 
-constexpr int TM = 64;        // points per tile
-constexpr int MW = 64;        // net_width
-constexpr int MT = 256;       // threads per CTA
-constexpr int LDR = MW + 4;   // row-major tile stride (floats)
+constexpr int MW = 64;             // net_width
+constexpr int MT = 256;            // threads per CTA (8 warps x 16 points)
+constexpr int ROWS = 128;          // points per CTA iteration
+constexpr int LDS_T = MW + 8;      // row stride (floats) of the row-major smem tiles: conflict-free fragment loads
+
+__device__ __forceinline__ u32 to_tf32(float x) { u32 r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void split(float x, u32& hi, u32& lo)
+{
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma(float c[4], const u32 a[4], u32 b0, u32 b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += (ahi + alo) * (bhi + blo) without the lo*lo term, small terms first; b = {hi0, hi1, lo0, lo1}
+__device__ __forceinline__ void mma3(float c[4], const u32 ahi[4], const u32 alo[4], const float4 b)
+{
+    mma(c, alo, __float_as_uint(b.x), __float_as_uint(b.y));
+    mma(c, ahi, __float_as_uint(b.z), __float_as_uint(b.w));
+    mma(c, ahi, __float_as_uint(b.x), __float_as_uint(b.y));
+}
+
+// Pre-split weight operand for  Y[rows][n] = sum_k X[rows][k] * Wm[k][n]:
+// entry (n, j, t) = {hi Wm[8j+2t][n], hi Wm[8j+2t+1][n], lo ..., lo ...}, float4 index n*rs + 4j + t,
+// rs = K/2 + 4 (== 4 mod 8 -> the 8 lanes of an LDS.128 phase hit disjoint banks).
+// `w` holds element Wm[k][n] at w[k*sk + n*sn]; K_real / N_real bound the non-zero part.
+__device__ __forceinline__ void stage_weight(float4* __restrict__ dst, const float* __restrict__ w, int K, int N,
+                                             int K_real, int N_real, int sk, int sn)
+{
+    const int rs = K / 2 + 4;
+    for (int i = threadIdx.x; i < N * (K / 2); i += MT) {
+        const int n = i / (K / 2), kk = i - n * (K / 2);      // kk = 4j + t
+        const int k0 = 2 * kk, k1 = k0 + 1;
+        const float v0 = (n < N_real && k0 < K_real) ? __ldg(w + (size_t)k0 * sk + (size_t)n * sn) : 0.f;
+        const float v1 = (n < N_real && k1 < K_real) ? __ldg(w + (size_t)k1 * sk + (size_t)n * sn) : 0.f;
+        u32 h0, l0, h1, l1;
+        split(v0, h0, l0); split(v1, h1, l1);
+        dst[n * rs + kk] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+    }
+}
+
+// acc[nt] += A(k-step j) * B[:, n-tile nt]  for nt in [0, NT); A given as its 4 fragment values
+template <int NT>
+__device__ __forceinline__ void kstep(float (*acc)[4], const float a[4], const float4* __restrict__ Bq, int rs, int j,
+                                      int g, int t)
+{
+    u32 ahi[4], alo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split(a[i], ahi[i], alo[i]);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) mma3(acc[nt], ahi, alo, Bq[(8 * nt + g) * rs + 4 * j + t]);
+}
 
 struct FwdArgs {
     b200gs_mlp_weights w;
@@ -31,139 +89,121 @@ struct FwdArgs {
     float frame_num, delta_scale;
     const float* frame_num_dev;   // optional device scalar overriding frame_num (avoids a host sync)
     float* pts_out; float* scales_out; float* rot_out;
-    float* saved;            // [4][tiles][64][TM]: relu(hidden), relu(z_pos), relu(z_scale), relu(z_rot)
+    float* saved;                 // [4][P][64] row-major: relu(hidden), relu(z_pos), relu(z_scale), relu(z_rot)
 };
-
-// acc[i][j] += sum_k At[k][r0+i] * B[k][c0+j]
-template <int K, int LDB>
-__device__ __forceinline__ void gemm_AtB(const float* __restrict__ At, const float* __restrict__ B,
-                                         float acc[4][4], int r0, int c0)
-{
-#pragma unroll 8
-    for (int k = 0; k < K; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(At + k * TM + r0);
-        const float4 b = *reinterpret_cast<const float4*>(B + k * LDB + c0);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-        const float bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
-}
-
-// transposed feature tile: At[k][row] <- feat[row0 + row][k]
-template <int F>
-__device__ __forceinline__ void load_feat_tile(float* __restrict__ At, const float* __restrict__ feat,
-                                               long long row0, long long P)
-{
-    const int row = threadIdx.x & 63, kq = threadIdx.x >> 6;
-    const long long g = row0 + row;
-    for (int kk = kq; kk < F / 4; kk += 4) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g < P) v = __ldg(reinterpret_cast<const float4*>(feat + (size_t)g * F) + kk);
-        At[(kk * 4 + 0) * TM + row] = v.x;
-        At[(kk * 4 + 1) * TM + row] = v.y;
-        At[(kk * 4 + 2) * TM + row] = v.z;
-        At[(kk * 4 + 3) * TM + row] = v.w;
-    }
-}
 
 template <int F>
 __global__ void __launch_bounds__(MT, 1) deform_mlp_fwd_kernel(const __grid_constant__ FwdArgs a)
 {
-    extern __shared__ __align__(16) float smem[];
-    float* W1t = smem;                          // [F][64]
-    float* W2t = W1t + F * MW;                  // [3][64][64]
-    float* W3t = W2t + 3 * MW * MW;             // [3][64][4]
-    float* B1 = W3t + 3 * MW * 4;               // [64]
-    float* B2 = B1 + MW;                        // [3][64]
-    float* B3 = B2 + 3 * MW;                    // [3][4]
-    float* At = B3 + 16;                        // [F][TM]
-    float* Ht = At + F * TM;                    // [64][TM]
-    float* Zt = Ht + MW * TM;                   // [64][TM]
-    const int tid = threadIdx.x;
+    extern __shared__ __align__(16) float4 smem4[];
+    constexpr int RS1 = F / 2 + 4, RS2 = MW / 2 + 4;
+    float4* W1q = smem4;                       // [64][RS1]
+    float4* W2q = W1q + MW * RS1;              // [3][64][RS2]
+    float4* W3q = W2q + 3 * MW * RS2;          // [3][8][RS2]   (N padded to 8)
+    float* bias = reinterpret_cast<float*>(W3q + 3 * 8 * RS2);   // b1[64] b2[3][64] b3[3][8]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int kdim[3] = {3, 3, 4};
 
-    for (int i = tid; i < MW * F; i += MT) { int o = i / F, in = i - o * F; W1t[in * MW + o] = __ldg(a.w.w1 + i); }
-    for (int i = tid; i < MW; i += MT) B1[i] = __ldg(a.w.b1 + i);
+    // forward: Wm[k][n] = W_torch[n][k]  ->  sk = 1, sn = K
+    stage_weight(W1q, a.w.w1, F, MW, F, MW, 1, F);
+    for (int i = tid; i < MW; i += MT) bias[i] = __ldg(a.w.b1 + i);
     for (int h = 0; h < 3; ++h) {
         if (!a.w.w2[h]) continue;
-        for (int i = tid; i < MW * MW; i += MT) { int o = i >> 6, in = i & 63; W2t[h * MW * MW + in * MW + o] = __ldg(a.w.w2[h] + i); }
-        for (int i = tid; i < MW; i += MT) B2[h * MW + i] = __ldg(a.w.b2[h] + i);
-        for (int i = tid; i < MW * 4; i += MT) {
-            int in = i >> 2, o = i & 3;
-            W3t[h * MW * 4 + i] = o < kdim[h] ? __ldg(a.w.w3[h] + o * MW + in) : 0.f;
-        }
-        if (tid < 4) B3[h * 4 + tid] = tid < kdim[h] ? __ldg(a.w.b3[h] + tid) : 0.f;
+        stage_weight(W2q + h * MW * RS2, a.w.w2[h], MW, MW, MW, MW, 1, MW);
+        stage_weight(W3q + h * 8 * RS2, a.w.w3[h], MW, 8, MW, kdim[h], 1, MW);
+        for (int i = tid; i < MW; i += MT) bias[MW + h * MW + i] = __ldg(a.w.b2[h] + i);
+        if (tid < 8) bias[4 * MW + h * 8 + tid] = tid < kdim[h] ? __ldg(a.w.b3[h] + tid) : 0.f;
     }
     __syncthreads();
 
-    const int r0 = (tid & 15) * 4, c0 = (tid >> 4) * 4;
-    const long long ntiles = (a.P + TM - 1) / TM;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long row0 = tile * TM;
-        load_feat_tile<F>(At, a.feat, row0, a.P);
-        __syncthreads();
-        {
-            float acc[4][4];
+    const long long nblocks = (a.P + ROWS - 1) / ROWS;
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const long long r_lo = blk * ROWS + warp * 16 + g, r_hi = r_lo + 8;
+        const bool v_lo = r_lo < a.P, v_hi = r_hi < a.P;
+        // ---- hidden = feature W1^T + b1 ----
+        float hC[8][4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = B1[c0 + j];
-            gemm_AtB<F, MW>(At, W1t, acc, r0, c0);
-            float* sv = a.saved + ((size_t)0 * ntiles + tile) * MW * TM;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 v = make_float4(fmaxf(acc[0][j], 0.f), fmaxf(acc[1][j], 0.f), fmaxf(acc[2][j], 0.f), fmaxf(acc[3][j], 0.f));
-                *reinterpret_cast<float4*>(Ht + (c0 + j) * TM + r0) = v;
-                *reinterpret_cast<float4*>(sv + (c0 + j) * TM + r0) = v;
-            }
+        for (int nt = 0; nt < 8; ++nt) {
+            hC[nt][0] = hC[nt][2] = bias[8 * nt + 2 * t];
+            hC[nt][1] = hC[nt][3] = bias[8 * nt + 2 * t + 1];
         }
-        __syncthreads();
+#pragma unroll 2
+        for (int j = 0; j < F / 8; ++j) {
+            const float2 lo2 = v_lo ? __ldg(reinterpret_cast<const float2*>(a.feat + (size_t)r_lo * F + 8 * j + 2 * t)) : make_float2(0.f, 0.f);
+            const float2 hi2 = v_hi ? __ldg(reinterpret_cast<const float2*>(a.feat + (size_t)r_hi * F + 8 * j + 2 * t)) : make_float2(0.f, 0.f);
+            const float af[4] = {lo2.x, hi2.x, lo2.y, hi2.y};
+            kstep<8>(hC, af, W1q, RS1, j, g, t);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hC[nt][i] = fmaxf(hC[nt][i], 0.f);
+            if (v_lo) *reinterpret_cast<float2*>(a.saved + (size_t)r_lo * MW + 8 * nt + 2 * t) = make_float2(hC[nt][0], hC[nt][1]);
+            if (v_hi) *reinterpret_cast<float2*>(a.saved + (size_t)r_hi * MW + 8 * nt + 2 * t) = make_float2(hC[nt][2], hC[nt][3]);
+        }
+        // ---- heads ----
+#pragma unroll
         for (int h = 0; h < 3; ++h) {
-            const int row = tid & 63, j = tid >> 6;
-            const long long g = row0 + row;
-            if (a.w.w2[h]) {
-                float acc[4][4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) acc[i][jj] = B2[h * MW + c0 + jj];
-                gemm_AtB<MW, MW>(Ht, W2t + h * MW * MW, acc, r0, c0);
-                float* sv = a.saved + ((size_t)(1 + h) * ntiles + tile) * MW * TM;
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const float4 v = make_float4(fmaxf(acc[0][jj], 0.f), fmaxf(acc[1][jj], 0.f), fmaxf(acc[2][jj], 0.f), fmaxf(acc[3][jj], 0.f));
-                    *reinterpret_cast<float4*>(Zt + (c0 + jj) * TM + r0) = v;
-                    *reinterpret_cast<float4*>(sv + (c0 + jj) * TM + r0) = v;
+            const int kd = kdim[h];
+            if (!a.w.w2[h]) {            // head disabled (no_dx / no_ds / no_dr): pass through
+                const float* src = h == 0 ? a.xyz : (h == 1 ? a.scales : a.rot);
+                float* dst = h == 0 ? a.pts_out : (h == 1 ? a.scales_out : a.rot_out);
+                for (int c = 2 * t; c < 2 * t + 2 && c < kd; ++c) {
+                    if (v_lo) dst[(size_t)r_lo * kd + c] = __ldg(src + (size_t)r_lo * kd + c);
+                    if (v_hi) dst[(size_t)r_hi * kd + c] = __ldg(src + (size_t)r_hi * kd + c);
                 }
-                __syncthreads();
-                if (j < kdim[h] && g < a.P) {
-                    float o = B3[h * 4 + j];
-                    const float* w3 = W3t + h * MW * 4 + j;
-#pragma unroll 8
-                    for (int k = 0; k < MW; ++k) o = fmaf(Zt[k * TM + row], w3[k * 4], o);
+                continue;
+            }
+            float zC[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                zC[nt][0] = zC[nt][2] = bias[MW + h * MW + 8 * nt + 2 * t];
+                zC[nt][1] = zC[nt][3] = bias[MW + h * MW + 8 * nt + 2 * t + 1];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float af[4] = {hC[j][0], hC[j][2], hC[j][1], hC[j][3]};
+                kstep<8>(zC, af, W2q + h * MW * RS2, RS2, j, g, t);
+            }
+            float* sv = a.saved + (size_t)(1 + h) * a.P * MW;
+            float oC[1][4];
+            oC[0][0] = oC[0][2] = bias[4 * MW + h * 8 + 2 * t];
+            oC[0][1] = oC[0][3] = bias[4 * MW + h * 8 + 2 * t + 1];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) zC[nt][i] = fmaxf(zC[nt][i], 0.f);
+                if (v_lo) *reinterpret_cast<float2*>(sv + (size_t)r_lo * MW + 8 * nt + 2 * t) = make_float2(zC[nt][0], zC[nt][1]);
+                if (v_hi) *reinterpret_cast<float2*>(sv + (size_t)r_hi * MW + 8 * nt + 2 * t) = make_float2(zC[nt][2], zC[nt][3]);
+                const float af[4] = {zC[nt][0], zC[nt][2], zC[nt][1], zC[nt][3]};
+                kstep<1>(oC, af, W3q + h * 8 * RS2, RS2, nt, g, t);
+            }
+            // epilogue: columns 2t, 2t+1 of rows r_lo / r_hi
+            const float fn = a.frame_num_dev ? __ldg(a.frame_num_dev) : a.frame_num;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const long long r = half ? r_hi : r_lo;
+                if (!(half ? v_hi : v_lo)) continue;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = 2 * t + cc;
+                    if (c >= kd) continue;
+                    const float o = oC[0][2 * half + cc];
                     if (h == 0) {
-                        const float fn = a.frame_num_dev ? __ldg(a.frame_num_dev) : a.frame_num;
-                        const float flow = __fmul_rn(a.delta_scale, __fmul_rn(fn, __ldg(a.scene_flow + 3 * g + j)));
-                        a.pts_out[3 * g + j] = __fadd_rn(__fmul_rn(__ldg(a.xyz + 3 * g + j), 1.0f), __fadd_rn(o, flow));
+                        const float flow = __fmul_rn(a.delta_scale, __fmul_rn(fn, __ldg(a.scene_flow + 3 * r + c)));
+                        a.pts_out[3 * r + c] = __fadd_rn(__fmul_rn(__ldg(a.xyz + 3 * r + c), 1.0f), __fadd_rn(o, flow));
                     } else if (h == 1) {
-                        a.scales_out[3 * g + j] = __fadd_rn(__fmul_rn(__ldg(a.scales + 3 * g + j), 1.0f), o);
+                        a.scales_out[3 * r + c] = __fadd_rn(__fmul_rn(__ldg(a.scales + 3 * r + c), 1.0f), o);
                     } else {
-                        a.rot_out[4 * g + j] = __fadd_rn(__ldg(a.rot + 4 * g + j), o);
+                        a.rot_out[4 * r + c] = __fadd_rn(__ldg(a.rot + 4 * r + c), o);
                     }
                 }
-                __syncthreads();
-            } else if (g < a.P) {       // head disabled (no_dx / no_ds / no_dr): pass through
-                if (h == 0 && j < 3) a.pts_out[3 * g + j] = __ldg(a.xyz + 3 * g + j);
-                if (h == 1 && j < 3) a.scales_out[3 * g + j] = __ldg(a.scales + 3 * g + j);
-                if (h == 2 && j < 4) a.rot_out[4 * g + j] = __ldg(a.rot + 4 * g + j);
             }
         }
     }
 }
 
+// ---------------------------------------------------------------------------------------------
 struct BwdArgs {
     b200gs_mlp_weights w;
     b200gs_mlp_grads gw;
@@ -173,26 +213,32 @@ struct BwdArgs {
     float* d_feat;
 };
 
-// acc[i][j] += sum_r dYrm[r][o0+i] * Xt[i0+j][r]     (o: rows of dW = out features, i: in features)
-__device__ __forceinline__ void outer_acc(const float* __restrict__ dYrm, const float* __restrict__ Xt,
-                                          float acc[4][4], int o0, int i0)
+// dW tile accumulation: acc[nt] (16 out x 8 in) += sum over the CTA tile's rows of
+// dY[row][16*mt + .] * X[row][8*(nt0+nt) + .]; dY from the row-major smem tile (stride LDS_T),
+// X from global row-major memory (stride ldx); 3xTF32.
+template <int NT>
+__device__ __forceinline__ void dw_accumulate(float (*acc)[4], const float* __restrict__ dYs, int mt,
+                                              const float* __restrict__ X, size_t ldx, long long row0, long long P,
+                                              int nt0, int g, int t)
 {
 #pragma unroll 2
-    for (int r = 0; r < TM; r += 4) {
-        float x[4][4];     // x[j][rr] = Xt[i0+j][r+rr]
+    for (int ks = 0; ks < ROWS / 8; ++ks) {
+        const int r0 = 8 * ks + t, r1 = r0 + 4;
+        const float af[4] = {dYs[r0 * LDS_T + 16 * mt + g], dYs[r0 * LDS_T + 16 * mt + g + 8],
+                             dYs[r1 * LDS_T + 16 * mt + g], dYs[r1 * LDS_T + 16 * mt + g + 8]};
+        u32 ahi[4], alo[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 v = *reinterpret_cast<const float4*>(Xt + (i0 + j) * TM + r);
-            x[j][0] = v.x; x[j][1] = v.y; x[j][2] = v.z; x[j][3] = v.w;
-        }
+        for (int i = 0; i < 4; ++i) split(af[i], ahi[i], alo[i]);
+        const bool v0 = row0 + r0 < P, v1 = row0 + r1 < P;
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            const float4 dy = *reinterpret_cast<const float4*>(dYrm + (r + rr) * LDR + o0);
-            const float d[4] = {dy.x, dy.y, dy.z, dy.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(d[i], x[j][rr], acc[i][j]);
+        for (int nt = 0; nt < NT; ++nt) {
+            const float x0 = v0 ? __ldg(X + (size_t)(row0 + r0) * ldx + 8 * (nt0 + nt) + g) : 0.f;
+            const float x1 = v1 ? __ldg(X + (size_t)(row0 + r1) * ldx + 8 * (nt0 + nt) + g) : 0.f;
+            u32 h0, l0, h1, l1;
+            split(x0, h0, l0); split(x1, h1, l1);
+            mma(acc[nt], alo, h0, h1);
+            mma(acc[nt], ahi, l0, l1);
+            mma(acc[nt], ahi, h0, h1);
         }
     }
 }
@@ -200,213 +246,225 @@ __device__ __forceinline__ void outer_acc(const float* __restrict__ dYrm, const 
 template <int F>
 __global__ void __launch_bounds__(MT, 1) deform_mlp_bwd_kernel(const __grid_constant__ BwdArgs a)
 {
-    extern __shared__ __align__(16) float smem[];
-    float* W1 = smem;                           // [64][F]   (out, in) as stored by torch
-    float* W2 = W1 + MW * F;                    // [3][64][64]
-    float* W3 = W2 + 3 * MW * MW;               // [3][4][64]
-    float* At = W3 + 3 * 4 * MW;                // [F][TM]   feature tile, transposed
-    float* Ht = At + F * TM;                    // [64][TM]  relu(hidden), transposed
-    float* Zt = Ht + MW * TM;                   // [64][TM]  relu(z) of the current head
-    float* Dt = Zt + MW * TM;                   // [64][TM]  dz (then d hidden), transposed
-    float* Drm = Dt + MW * TM;                  // [TM][LDR] same, row-major
-    float* Dout = Drm + TM * LDR;               // [TM][4]   upstream gradient of the current head
-    const int tid = threadIdx.x;
+    extern __shared__ __align__(16) float4 smem4[];
+    constexpr int RS2 = MW / 2 + 4;            // K = 64 operands
+    constexpr int RS3 = 4;                     // K = 8 operand (W3): 4 float4 per row, contiguous -> conflict-free
+    constexpr bool RESIDENT = (F == 64);       // F = 128: one W2 slot, re-staged per head (shared memory budget)
+    constexpr int NT1 = F / 8;                 // n-tiles of d_feature / in-features of W1
+    float4* W3b = smem4;                       // [3][64][RS3]   Wm[k=out(pad 8)][n=in 64]  = W3[k][n]
+    float4* W2b = W3b + 3 * MW * RS3;          // [3][64][RS2]   Wm[k=out][n=in]            = W2[k][n]
+    float4* W1b = W2b + (RESIDENT ? 3 : 1) * MW * RS2;   // [F][RS2]  Wm[k=out 64][n=in F]       = W1[k][n]
+    float* Ds = reinterpret_cast<float*>(W1b + F * RS2);          // [ROWS][LDS_T]  dz / d hidden, row-major
+    float* Dout = Ds + ROWS * LDS_T;                              // [ROWS][8]      upstream gradient of the head
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int kdim[3] = {3, 3, 4};
 
-    for (int i = tid; i < MW * F; i += MT) W1[i] = __ldg(a.w.w1 + i);
+    // backward dX = dY W: Wm[k][n] = W_torch[k][n] -> sk = row length, sn = 1
+    stage_weight(W1b, a.w.w1, MW, F, MW, F, F, 1);
     for (int h = 0; h < 3; ++h) {
         if (!a.w.w2[h]) continue;
-        for (int i = tid; i < MW * MW; i += MT) W2[h * MW * MW + i] = __ldg(a.w.w2[h] + i);
-        for (int i = tid; i < 4 * MW; i += MT) { int o = i >> 6; W3[h * 4 * MW + i] = o < kdim[h] ? __ldg(a.w.w3[h] + i) : 0.f; }
+        if (RESIDENT) stage_weight(W2b + h * MW * RS2, a.w.w2[h], MW, MW, MW, MW, MW, 1);
+        for (int i = tid; i < MW * 4; i += MT) {                     // K = 8 (padded outputs), rs = 4
+            const int n = i >> 2, kk = i & 3, k0 = 2 * kk, k1 = k0 + 1;
+            const float v0 = k0 < kdim[h] ? __ldg(a.w.w3[h] + k0 * MW + n) : 0.f;
+            const float v1 = k1 < kdim[h] ? __ldg(a.w.w3[h] + k1 * MW + n) : 0.f;
+            u32 h0, l0, h1, l1;
+            split(v0, h0, l0); split(v1, h1, l1);
+            W3b[h * MW * RS3 + n * RS3 + kk] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+        }
     }
     __syncthreads();
 
-    const int r0 = (tid & 15) * 4, c0 = (tid >> 4) * 4;      // C-tile of the dX GEMMs (rows, cols)
-    const int o0 = (tid & 15) * 4, i0 = (tid >> 4) * 4;      // block of the dW accumulators (out, in)
-    float gW2[3][4][4], gW1[F / MW][4][4];
-    float gW3[3][4][4];      // [head][out j][in c0+i], partial over this thread's rows
-    float gB3[3] = {0.f, 0.f, 0.f}, gB2[3] = {0.f, 0.f, 0.f}, gB1 = 0.f;
+    // weight-gradient fragments owned by this warp (persist over all tiles of the CTA)
+    const int mt = warp >> 1;                  // 16-row block of `out` features
+    const int ntb = (warp & 1) * 4;            // first of 4 n-tiles of `in` features (W2)
+    float gW2[3][4][4], gW1[NT1 / 2][4], gW3[3][4];
+    float gB2[3] = {0.f, 0.f, 0.f}, gB1 = 0.f, gB3[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int h = 0; h < 3; ++h)
+    for (int h = 0; h < 3; ++h) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i) {
+            gW3[h][i] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) gW3[h][i][j] = 0.f;
-#pragma unroll
-    for (int h = 0; h < 3; ++h)
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) gW2[h][i][j] = 0.f;
-#pragma unroll
-    for (int q = 0; q < F / MW; ++q)
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) gW1[q][i][j] = 0.f;
-
-    const long long ntiles = (a.P + TM - 1) / TM;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long row0 = tile * TM;
-        load_feat_tile<F>(At, a.feat, row0, a.P);
-        {
-            const float4* sv = reinterpret_cast<const float4*>(a.saved + ((size_t)0 * ntiles + tile) * MW * TM);
-            for (int i = tid; i < MW * TM / 4; i += MT) reinterpret_cast<float4*>(Ht)[i] = __ldg(sv + i);
+            for (int n = 0; n < 4; ++n) gW2[h][n][i] = 0.f;
         }
-        float dRh[4][4];
+    }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+    for (int n = 0; n < NT1 / 2; ++n)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dRh[i][j] = 0.f;
+        for (int i = 0; i < 4; ++i) gW1[n][i] = 0.f;
 
+    const long long nblocks = (a.P + ROWS - 1) / ROWS;
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const long long row0 = blk * ROWS;
+        const int lr_lo = warp * 16 + g, lr_hi = lr_lo + 8;          // local rows of this lane
+        const long long r_lo = row0 + lr_lo, r_hi = row0 + lr_hi;
+        const bool v_lo = r_lo < a.P, v_hi = r_hi < a.P;
+        float hC[8][4], dRh[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float2 x = v_lo ? __ldg(reinterpret_cast<const float2*>(a.saved + (size_t)r_lo * MW + 8 * nt + 2 * t)) : make_float2(0.f, 0.f);
+            const float2 y = v_hi ? __ldg(reinterpret_cast<const float2*>(a.saved + (size_t)r_hi * MW + 8 * nt + 2 * t)) : make_float2(0.f, 0.f);
+            hC[nt][0] = x.x; hC[nt][1] = x.y; hC[nt][2] = y.x; hC[nt][3] = y.y;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dRh[nt][i] = 0.f;
+        }
 #pragma unroll
         for (int h = 0; h < 3; ++h) {
             if (!a.w.w2[h]) continue;
-            {
-                const float4* sv = reinterpret_cast<const float4*>(a.saved + ((size_t)(1 + h) * ntiles + tile) * MW * TM);
-                for (int i = tid; i < MW * TM / 4; i += MT) reinterpret_cast<float4*>(Zt)[i] = __ldg(sv + i);
-                const float* dsrc = h == 0 ? a.d_pts : (h == 1 ? a.d_scales : a.d_rot);
-                const int kd = kdim[h];
-                const int row = tid >> 2, j = tid & 3;
-                const long long g = row0 + row;
-                Dout[tid] = (j < kd && g < a.P && dsrc) ? __ldg(dsrc + (size_t)g * kd + j) : 0.f;
+            const int kd = kdim[h];
+            const float* dsrc = h == 0 ? a.d_pts : (h == 1 ? a.d_scales : a.d_rot);
+            const float* zsv = a.saved + (size_t)(1 + h) * a.P * MW;
+            const float4* W2h = W2b + (RESIDENT ? h : 0) * MW * RS2;
+            if (!RESIDENT) {            // every warp is past the previous head's use of the slot (trailing barrier below)
+                stage_weight(W2b, a.w.w2[h], MW, MW, MW, MW, MW, 1);
+                __syncthreads();
             }
-            __syncthreads();
-            // dz = (d_out . W3) masked by relu(z) > 0, in both layouts
+            // upstream gradient as an A fragment (one k-step, columns >= kd are zero) and as a smem tile
+            float df[4];
             {
-                float dA[4][4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 dv = *reinterpret_cast<const float4*>(Dout + (r0 + i) * 4);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float* w3 = W3 + h * 4 * MW + c0 + j;
-                        dA[i][j] = dv.x * w3[0] + dv.y * w3[MW] + dv.z * w3[2 * MW] + dv.w * w3[3 * MW];
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 z = *reinterpret_cast<const float4*>(Zt + (c0 + j) * TM + r0);
-                    dA[0][j] = z.x > 0.f ? dA[0][j] : 0.f;
-                    dA[1][j] = z.y > 0.f ? dA[1][j] : 0.f;
-                    dA[2][j] = z.z > 0.f ? dA[2][j] : 0.f;
-                    dA[3][j] = z.w > 0.f ? dA[3][j] : 0.f;
-                    *reinterpret_cast<float4*>(Dt + (c0 + j) * TM + r0) = make_float4(dA[0][j], dA[1][j], dA[2][j], dA[3][j]);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    *reinterpret_cast<float4*>(Drm + (r0 + i) * LDR + c0) = make_float4(dA[i][0], dA[i][1], dA[i][2], dA[i][3]);
+                const int c0 = 2 * t, c1 = c0 + 1;
+                df[0] = (v_lo && dsrc && c0 < kd) ? __ldg(dsrc + (size_t)r_lo * kd + c0) : 0.f;
+                df[1] = (v_hi && dsrc && c0 < kd) ? __ldg(dsrc + (size_t)r_hi * kd + c0) : 0.f;
+                df[2] = (v_lo && dsrc && c1 < kd) ? __ldg(dsrc + (size_t)r_lo * kd + c1) : 0.f;
+                df[3] = (v_hi && dsrc && c1 < kd) ? __ldg(dsrc + (size_t)r_hi * kd + c1) : 0.f;
+                *reinterpret_cast<float2*>(Dout + lr_lo * 8 + c0) = make_float2(df[0], df[2]);
+                *reinterpret_cast<float2*>(Dout + lr_hi * 8 + c0) = make_float2(df[1], df[3]);
             }
-            // dW3[j][in] partial over this thread's 4 rows (kept per thread across tiles), db3[j]
-            {
-                float zv[4][4];    // zv[i][rr] = relu(z)[r0+rr][c0+i]
+            // dz = (d_out W3) masked by relu(z) > 0
+            float dz[8][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 v = *reinterpret_cast<const float4*>(Zt + (c0 + i) * TM + r0);
-                    zv[i][0] = v.x; zv[i][1] = v.y; zv[i][2] = v.z; zv[i][3] = v.w;
-                }
+            for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
-                    const float4 dv = *reinterpret_cast<const float4*>(Dout + (r0 + rr) * 4);
-                    const float d[4] = {dv.x, dv.y, dv.z, dv.w};
+                for (int i = 0; i < 4; ++i) dz[nt][i] = 0.f;
+            kstep<8>(dz, df, W3b + h * MW * RS3, RS3, 0, g, t);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) gW3[h][j][i] = fmaf(d[j], zv[i][rr], gW3[h][j][i]);
-                }
-                if (tid < kdim[h]) {
-                    float sacc = 0.f;
-                    for (int r = 0; r < TM; ++r) sacc += Dout[r * 4 + tid];
-                    gB3[h] += sacc;
-                }
+            for (int nt = 0; nt < 8; ++nt) {
+                const float2 x = v_lo ? __ldg(reinterpret_cast<const float2*>(zsv + (size_t)r_lo * MW + 8 * nt + 2 * t)) : make_float2(0.f, 0.f);
+                const float2 y = v_hi ? __ldg(reinterpret_cast<const float2*>(zsv + (size_t)r_hi * MW + 8 * nt + 2 * t)) : make_float2(0.f, 0.f);
+                dz[nt][0] = x.x > 0.f ? dz[nt][0] : 0.f; dz[nt][1] = x.y > 0.f ? dz[nt][1] : 0.f;
+                dz[nt][2] = y.x > 0.f ? dz[nt][2] : 0.f; dz[nt][3] = y.y > 0.f ? dz[nt][3] : 0.f;
+                *reinterpret_cast<float2*>(Ds + lr_lo * LDS_T + 8 * nt + 2 * t) = make_float2(dz[nt][0], dz[nt][1]);
+                *reinterpret_cast<float2*>(Ds + lr_hi * LDS_T + 8 * nt + 2 * t) = make_float2(dz[nt][2], dz[nt][3]);
             }
-            __syncthreads();
-            outer_acc(Drm, Ht, gW2[h], o0, i0);                       // dW2 += dz^T relu(h)
+            // d relu(h) += dz W2
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float af[4] = {dz[j][0], dz[j][2], dz[j][1], dz[j][3]};
+                kstep<8>(dRh, af, W2h, RS2, j, g, t);
+            }
+            __syncthreads();                                             // dz and d_out tiles complete
+            dw_accumulate<4>(gW2[h], Ds, mt, a.saved, MW, row0, a.P, ntb, g, t);            // dW2 += dz^T relu(h)
+            // dW3 (out padded to one 16-row m-tile; n-tile `warp` of the 64 in-features) += d_out^T relu(z)
+#pragma unroll 2
+            for (int ks = 0; ks < ROWS / 8; ++ks) {
+                const int r0 = 8 * ks + t, r1 = r0 + 4;
+                const float af[4] = {Dout[r0 * 8 + g], 0.f, Dout[r1 * 8 + g], 0.f};      // rows g+8 of the m-tile are padding
+                u32 ahi[4], alo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split(af[i], ahi[i], alo[i]);
+                const float x0 = row0 + r0 < a.P ? __ldg(zsv + (size_t)(row0 + r0) * MW + 8 * warp + g) : 0.f;
+                const float x1 = row0 + r1 < a.P ? __ldg(zsv + (size_t)(row0 + r1) * MW + 8 * warp + g) : 0.f;
+                u32 h0, l0, h1, l1;
+                split(x0, h0, l0); split(x1, h1, l1);
+                mma(gW3[h], alo, h0, h1);
+                mma(gW3[h], ahi, l0, l1);
+                mma(gW3[h], ahi, h0, h1);
+            }
             if (tid < MW) {
                 float s = 0.f;
 #pragma unroll 8
-                for (int r = 0; r < TM; ++r) s += Drm[r * LDR + tid];
+                for (int r = 0; r < ROWS; ++r) s += Ds[r * LDS_T + tid];
                 gB2[h] += s;
+            } else if (tid < MW + 8) {
+                float s = 0.f;
+                for (int r = 0; r < ROWS; ++r) s += Dout[r * 8 + (tid - MW)];
+                gB3[h] += s;
             }
-            gemm_AtB<MW, MW>(Dt, W2 + h * MW * MW, dRh, r0, c0);       // d relu(h) += dz W2
-            __syncthreads();
+            __syncthreads();                                             // before the next head overwrites the tiles
         }
-        // d hidden = d relu(h) masked by relu(h) > 0
+        // d hidden = d relu(h) masked; tile for dW1; d feature = dh W1
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 hv = *reinterpret_cast<const float4*>(Ht + (c0 + j) * TM + r0);
-            dRh[0][j] = hv.x > 0.f ? dRh[0][j] : 0.f;
-            dRh[1][j] = hv.y > 0.f ? dRh[1][j] : 0.f;
-            dRh[2][j] = hv.z > 0.f ? dRh[2][j] : 0.f;
-            dRh[3][j] = hv.w > 0.f ? dRh[3][j] : 0.f;
-            *reinterpret_cast<float4*>(Dt + (c0 + j) * TM + r0) = make_float4(dRh[0][j], dRh[1][j], dRh[2][j], dRh[3][j]);
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dRh[nt][i] = hC[nt][i] > 0.f ? dRh[nt][i] : 0.f;
+            *reinterpret_cast<float2*>(Ds + lr_lo * LDS_T + 8 * nt + 2 * t) = make_float2(dRh[nt][0], dRh[nt][1]);
+            *reinterpret_cast<float2*>(Ds + lr_hi * LDS_T + 8 * nt + 2 * t) = make_float2(dRh[nt][2], dRh[nt][3]);
         }
+        {
+            float dF[NT1][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<float4*>(Drm + (r0 + i) * LDR + c0) = make_float4(dRh[i][0], dRh[i][1], dRh[i][2], dRh[i][3]);
+            for (int nt = 0; nt < NT1; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dF[nt][i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float af[4] = {dRh[j][0], dRh[j][2], dRh[j][1], dRh[j][3]};
+                kstep<NT1>(dF, af, W1b, RS2, j, g, t);
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT1; ++nt) {
+                if (v_lo) *reinterpret_cast<float2*>(a.d_feat + (size_t)r_lo * F + 8 * nt + 2 * t) = make_float2(dF[nt][0], dF[nt][1]);
+                if (v_hi) *reinterpret_cast<float2*>(a.d_feat + (size_t)r_hi * F + 8 * nt + 2 * t) = make_float2(dF[nt][2], dF[nt][3]);
+            }
+        }
         __syncthreads();
-#pragma unroll
-        for (int q = 0; q < F / MW; ++q) outer_acc(Drm, At + q * MW * TM, gW1[q], o0, i0);     // dW1 += dh^T feat
+        dw_accumulate<NT1 / 2>(gW1, Ds, mt, a.feat, F, row0, a.P, (warp & 1) * (NT1 / 2), g, t);     // dW1 += dh^T feature
         if (tid < MW) {
             float s = 0.f;
 #pragma unroll 8
-            for (int r = 0; r < TM; ++r) s += Drm[r * LDR + tid];
+            for (int r = 0; r < ROWS; ++r) s += Ds[r * LDS_T + tid];
             gB1 += s;
-        }
-        // d feature = dh W1   ([TM x 64] x [64 x F]), written row-major
-#pragma unroll
-        for (int q = 0; q < F / MW; ++q) {
-            float acc[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-            gemm_AtB<MW, F>(Dt, W1 + q * MW, acc, r0, c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const long long g = row0 + r0 + i;
-                if (g < a.P)
-                    *reinterpret_cast<float4*>(a.d_feat + (size_t)g * F + q * MW + c0) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-            }
         }
         __syncthreads();
     }
 
-    // flush the per-CTA weight gradients
+    // flush: C fragment (16 x 8): c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
 #pragma unroll
-    for (int q = 0; q < F / MW; ++q)
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) atomicAdd(a.gw.w1 + (size_t)(o0 + i) * F + q * MW + i0 + j, gW1[q][i][j]);
+    for (int n = 0; n < NT1 / 2; ++n) {
+        const int in0 = 8 * ((warp & 1) * (NT1 / 2) + n) + 2 * t;
+        atomicAdd(a.gw.w1 + (size_t)(16 * mt + g) * F + in0, gW1[n][0]);
+        atomicAdd(a.gw.w1 + (size_t)(16 * mt + g) * F + in0 + 1, gW1[n][1]);
+        atomicAdd(a.gw.w1 + (size_t)(16 * mt + g + 8) * F + in0, gW1[n][2]);
+        atomicAdd(a.gw.w1 + (size_t)(16 * mt + g + 8) * F + in0 + 1, gW1[n][3]);
+    }
     if (tid < MW) atomicAdd(a.gw.b1 + tid, gB1);
 #pragma unroll
     for (int h = 0; h < 3; ++h) {
         if (!a.w.w2[h]) continue;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) atomicAdd(a.gw.w2[h] + (o0 + i) * MW + i0 + j, gW2[h][i][j]);
+        for (int n = 0; n < 4; ++n) {
+            const int in0 = 8 * (ntb + n) + 2 * t;
+            atomicAdd(a.gw.w2[h] + (16 * mt + g) * MW + in0, gW2[h][n][0]);
+            atomicAdd(a.gw.w2[h] + (16 * mt + g) * MW + in0 + 1, gW2[h][n][1]);
+            atomicAdd(a.gw.w2[h] + (16 * mt + g + 8) * MW + in0, gW2[h][n][2]);
+            atomicAdd(a.gw.w2[h] + (16 * mt + g + 8) * MW + in0 + 1, gW2[h][n][3]);
+        }
+        if (g < kdim[h]) {           // row g of the padded m-tile = out feature; columns 8*warp + 2t (+1)
+            atomicAdd(a.gw.w3[h] + g * MW + 8 * warp + 2 * t, gW3[h][0]);
+            atomicAdd(a.gw.w3[h] + g * MW + 8 * warp + 2 * t + 1, gW3[h][1]);
+        }
         if (tid < MW) atomicAdd(a.gw.b2[h] + tid, gB2[h]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j < kdim[h]) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) atomicAdd(a.gw.w3[h] + j * MW + c0 + i, gW3[h][j][i]);
-            }
-        if (tid < kdim[h]) atomicAdd(a.gw.b3[h] + tid, gB3[h]);
+        else if (tid < MW + 8 && tid - MW < kdim[h]) atomicAdd(a.gw.b3[h] + (tid - MW), gB3[h]);
     }
 }
 
-size_t fwd_smem(int F) { return (size_t)(F * MW + 3 * MW * MW + 3 * MW * 4 + MW + 3 * MW + 16 + F * TM + 2 * MW * TM) * sizeof(float); }
-size_t bwd_smem(int F) { return (size_t)(MW * F + 3 * MW * MW + 3 * 4 * MW + F * TM + 3 * MW * TM + TM * LDR + TM * 4) * sizeof(float); }
+size_t fwd_smem(int F)
+{
+    return (size_t)(MW * (F / 2 + 4) + 3 * MW * (MW / 2 + 4) + 3 * 8 * (MW / 2 + 4)) * sizeof(float4) +
+           (size_t)(4 * MW + 24 + 8) * sizeof(float);
+}
+size_t bwd_smem(int F)
+{
+    return (size_t)(3 * MW * 4 + (F == 64 ? 3 : 1) * MW * (MW / 2 + 4) + F * (MW / 2 + 4)) * sizeof(float4) +
+           (size_t)(ROWS * LDS_T + ROWS * 8) * sizeof(float);
+}
 
 int check_weights(const b200gs_mlp_weights* w)
 {
     if (!w) { set_error("deform_mlp: null weights"); return -1; }
     if (w->width != MW) { set_error("deform_mlp: net_width=%d unsupported (need %d)", w->width, MW); return -1; }
-    if (w->feat_dim != 32 && w->feat_dim != 64 && w->feat_dim != 96 && w->feat_dim != 128) { set_error("deform_mlp: feature dim %d unsupported", w->feat_dim); return -1; }
-    if (w->feat_dim == 32 || w->feat_dim == 96) { set_error("deform_mlp: feature dim %d (1 or 3 levels) not compiled in", w->feat_dim); return -1; }
+    if (w->feat_dim != 64 && w->feat_dim != 128) { set_error("deform_mlp: feature dim %d unsupported (64 or 128: 2 or 4 HexPlane levels)", w->feat_dim); return -1; }
     if (!w->w1 || !w->b1) { set_error("deform_mlp: feature_out weights missing"); return -1; }
     for (int h = 0; h < 3; ++h)
         if (w->w2[h] && (!w->b2[h] || !w->w3[h] || !w->b3[h])) { set_error("deform_mlp: head %d incomplete", h); return -1; }
@@ -420,25 +478,21 @@ using namespace b200gs;
 
 extern "C" {
 
-size_t b200gs_deform_mlp_saved_floats(long long P)
-{
-    const long long ntiles = (P + TM - 1) / TM;
-    return (size_t)4 * ntiles * MW * TM;
-}
+size_t b200gs_deform_mlp_saved_floats(long long P) { return P > 0 ? (size_t)4 * (size_t)P * MW : 0; }
 
 int b200gs_deform_mlp_forward(const b200gs_mlp_weights* w, long long P, const float* feat, const float* xyz,
                               const float* scales, const float* rot, const float* scene_flow, float frame_num,
-                              const float* frame_num_dev, float delta_scale, float* pts_out, float* scales_out, float* rot_out, float* saved,
-                              b200gs_stream_t stream)
+                              const float* frame_num_dev, float delta_scale, float* pts_out, float* scales_out,
+                              float* rot_out, float* saved, b200gs_stream_t stream)
 {
     if (check_weights(w)) return -1;
     if (P <= 0) return 0;
     FwdArgs a;
     a.w = *w; a.P = P; a.feat = feat; a.xyz = xyz; a.scales = scales; a.rot = rot; a.scene_flow = scene_flow;
-    a.frame_num = frame_num; a.frame_num_dev = frame_num_dev; a.delta_scale = delta_scale; a.pts_out = pts_out; a.scales_out = scales_out;
-    a.rot_out = rot_out; a.saved = saved;
-    const long long ntiles = (P + TM - 1) / TM;
-    const int grid = (int)(ntiles < NUM_SMS ? ntiles : NUM_SMS);
+    a.frame_num = frame_num; a.frame_num_dev = frame_num_dev; a.delta_scale = delta_scale; a.pts_out = pts_out;
+    a.scales_out = scales_out; a.rot_out = rot_out; a.saved = saved;
+    const long long nblocks = (P + ROWS - 1) / ROWS;
+    const int grid = (int)(nblocks < NUM_SMS ? nblocks : NUM_SMS);
     const size_t smem = fwd_smem(w->feat_dim);
     if (w->feat_dim == 64) {
         cudaFuncSetAttribute(deform_mlp_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -460,8 +514,8 @@ int b200gs_deform_mlp_backward(const b200gs_mlp_weights* w, const b200gs_mlp_gra
     BwdArgs a;
     a.w = *w; a.gw = *gw; a.P = P; a.feat = feat; a.saved = saved; a.d_pts = d_pts; a.d_scales = d_scales;
     a.d_rot = d_rot; a.d_feat = d_feat;
-    const long long ntiles = (P + TM - 1) / TM;
-    const int grid = (int)(ntiles < NUM_SMS ? ntiles : NUM_SMS);
+    const long long nblocks = (P + ROWS - 1) / ROWS;
+    const int grid = (int)(nblocks < NUM_SMS ? nblocks : NUM_SMS);
     const size_t smem = bwd_smem(w->feat_dim);
     if (w->feat_dim == 64) {
         cudaFuncSetAttribute(deform_mlp_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
