@@ -58,10 +58,12 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ l
     const size_t HW = (size_t)H * W;
 
     const u32 last_contributor = inside ? n_contrib[pid] : 0;
+    const float patch_x = (float)(tx * TILE_X + (warp & 1) * 8), patch_y = (float)(ty * TILE_Y + (warp >> 1) * 4);
     // nothing behind the deepest contributor of the tile can receive gradient
     u32 m = last_contributor;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const u32 warp_last = m;
     if (lane == 0) s_max[warp] = m;
     for (u32 i = tid; i < CB * ACC; i += TILE_PIXELS) s_acc[i] = 0.f;
     __syncthreads();
@@ -83,7 +85,6 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ l
     float rec0 = 0.f, rec1 = 0.f, rec2 = 0.f, recd = 0.f;
     float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ld = 0.f;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-    u32 contributor = n_eff;     // 1-based list position of the splat about to be visited
 
     bstage_fill(stage[0], list, range.x, n_eff, 0, recA, recB, recC);
     cp_async_commit();
@@ -94,8 +95,23 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ l
         __syncthreads();
         const BStage& st = stage[r & 1];
         const int cnt = (int)min((u32)CB, n_eff - (u32)r * CB);
-        for (int j = 0; j < cnt; ++j) {
-            --contributor;
+        // per-warp culling against the 8x4 pixel patch (see splat_may_touch_patch) and against the
+        // deepest contributor of the warp's pixels; survivors are walked back to front in lock-step
+        u32 masks[CB / 32];
+#pragma unroll
+        for (int q = 0; q < CB / 32; ++q) {
+            const int j = q * 32 + (int)lane;
+            const u32 p = n_eff - 1u - ((u32)r * CB + (u32)j);          // 0-based list position of staged slot j
+            const bool keep = j < cnt && p < warp_last && splat_may_touch_patch(st.A[j], st.B[j], patch_x, patch_y);
+            masks[q] = __ballot_sync(0xffffffffu, keep);
+        }
+#pragma unroll
+        for (int q = 0; q < CB / 32; ++q) {
+          u32 mq = masks[q];
+          while (mq != 0) {
+            const int j = q * 32 + __ffs(mq) - 1;
+            mq &= mq - 1;
+            const u32 contributor = n_eff - 1u - ((u32)r * CB + (u32)j);
             bool act = contributor < last_contributor;      // false for pixels outside the image
             const float4 A = st.A[j];
             const float4 B = st.B[j];
@@ -165,6 +181,7 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ l
                     if (y != 0.f) atomicAdd(&s_acc[j * ACC + slot], y);
                 }
             }
+          }
         }
         __syncthreads();
         // flush this batch: one thread per instance, three 128-bit reductions

@@ -446,6 +446,7 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ l
     const u32 py = ty * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < (u32)W && py < (u32)H;
     const float fxp = (float)px, fyp = (float)py;
+    const float patch_x = (float)(tx * TILE_X + (warp & 1) * 8), patch_y = (float)(ty * TILE_Y + (warp >> 1) * 4);
     const uint2 range = ranges[tile];
     const u32 n = range.y - range.x;
     const int rounds = (int)((n + CB - 1) / CB);
@@ -464,31 +465,47 @@ composite_fwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ l
         if (__syncthreads_count(done) == TILE_PIXELS) break;
         const Stage& st = stage[r & 1];
         const int cnt = (int)min((u32)CB, n - (u32)r * CB);
-        // Every lane walks the batch in lock-step (finished pixels are predicated off): the
-        // warp vote both ends the batch early and keeps the 32 lanes converged, which the
-        // data-dependent `continue`s of the reference loop (forward.cu:328-366) do not.
-        for (int j = 0; j < cnt; ++j) {
-            if (__all_sync(0xffffffffu, done)) break;
-            const float4 A = st.A[j];
-            const float4 B = st.B[j];
-            const float dx = A.x - fxp, dy = A.y - fyp;
-            const float power = -0.5f * (A.z * dx * dx + B.x * dy * dy) - A.w * dx * dy;
-            if (!done && !(power > 0.0f) && !(power < B.w)) {
-                const float alpha = fminf(0.99f, B.y * expf(power));
-                if (!(alpha < 1.0f / 255.0f)) {
-                    const float test_T = T * (1 - alpha);
-                    if (test_T < 0.0001f) {
-                        done = true;
-                    } else {
-                        const float4 Cc = st.C[j];
-                        C0 += Cc.x * alpha * T;
-                        C1 += Cc.y * alpha * T;
-                        C2 += Cc.z * alpha * T;
-                        Dp += B.z * alpha * T;
-                        T = test_T;
-                        last = (u32)r * CB + (u32)j + 1u;
+        // Each warp first tests the 256 staged splats against its own 8x4 pixel patch (one splat per
+        // lane and round, conservative ellipse-vs-box bound) and then walks only the survivors, all 32
+        // lanes in lock-step (finished pixels are predicated off).  Rejected (patch, splat) pairs thus
+        // cost ~1.6 instructions instead of a full per-pixel evaluation, and the warp-uniform loop keeps
+        // the lanes converged, which the data-dependent `continue`s of forward.cu:328-366 do not.
+        u32 masks[CB / 32];
+#pragma unroll
+        for (int q = 0; q < CB / 32; ++q) {
+            const int j = q * 32 + (int)lane;
+            const bool keep = j < cnt && splat_may_touch_patch(st.A[j], st.B[j], patch_x, patch_y);
+            masks[q] = __ballot_sync(0xffffffffu, keep);
+        }
+        bool all_done = __all_sync(0xffffffffu, done);
+#pragma unroll
+        for (int q = 0; q < CB / 32; ++q) {
+            u32 m = masks[q];
+            while (m != 0 && !all_done) {
+                const int j = q * 32 + __ffs(m) - 1;
+                m &= m - 1;
+                const float4 A = st.A[j];
+                const float4 B = st.B[j];
+                const float dx = A.x - fxp, dy = A.y - fyp;
+                const float power = -0.5f * (A.z * dx * dx + B.x * dy * dy) - A.w * dx * dy;
+                if (!done && !(power > 0.0f) && !(power < B.w)) {
+                    const float alpha = fminf(0.99f, B.y * expf(power));
+                    if (!(alpha < 1.0f / 255.0f)) {
+                        const float test_T = T * (1 - alpha);
+                        if (test_T < 0.0001f) {
+                            done = true;
+                        } else {
+                            const float4 Cc = st.C[j];
+                            C0 += Cc.x * alpha * T;
+                            C1 += Cc.y * alpha * T;
+                            C2 += Cc.z * alpha * T;
+                            Dp += B.z * alpha * T;
+                            T = test_T;
+                            last = (u32)r * CB + (u32)j + 1u;
+                        }
                     }
                 }
+                all_done = __all_sync(0xffffffffu, done);
             }
         }
         __syncthreads();   // batch r fully consumed before its buffer is refilled

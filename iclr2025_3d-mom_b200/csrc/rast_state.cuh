@@ -88,6 +88,29 @@ struct ImgState {
     }
 };
 
+
+// Conservative per-warp culling for the compositing kernels. A warp covers the pixel-centre box
+// [bx, bx+7] x [by, by+3]; a splat (centre x,y; conic a,b,c; exponent bound `reject`) can only
+// contribute to one of those pixels if max over the box of power = -0.5 q(d) reaches `reject`,
+// q(d) = a dx^2 + 2 b dx dy + c dy^2, d = centre - pixel.  The minimum of the convex q over the box is
+// attained at the box point closest to the centre along one of the two facing edges, so two
+// candidates suffice.  Anything doubtful (non-PD conic, NaNs) is kept; survivors still run the exact
+// per-pixel test, so results are unchanged.
+__device__ __forceinline__ bool splat_may_touch_patch(const float4 A, const float4 B, float bx, float by)
+{
+    const float a = A.z, b = A.w, c = B.x;
+    if (!(a > 0.f) || !(c > 0.f)) return true;
+    const float dx_hi = A.x - bx, dx_lo = dx_hi - 7.f;          // d.x range over the patch
+    const float dy_hi = A.y - by, dy_lo = dy_hi - 3.f;
+    const float cx = fminf(fmaxf(0.f, dx_lo), dx_hi), cy = fminf(fmaxf(0.f, dy_lo), dy_hi);
+    const float y1 = fminf(fmaxf(__fdividef(-b * cx, c), dy_lo), dy_hi);
+    const float x2 = fminf(fmaxf(__fdividef(-b * cy, a), dx_lo), dx_hi);
+    const float q1 = a * cx * cx + 2.f * b * cx * y1 + c * y1 * y1;
+    const float q2 = a * x2 * x2 + 2.f * b * x2 * cy + c * cy * cy;
+    const float pmax = -0.5f * fminf(q1, q2);
+    return !(pmax < B.w - 1e-3f);
+}
+
 inline int tile_bits_for(size_t tiles) {
     int b = 1;
     while (((size_t)1 << b) < tiles) ++b;
