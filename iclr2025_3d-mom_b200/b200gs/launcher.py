@@ -1,0 +1,66 @@
+"""Run the reference's own scripts, byte-identical, on top of the B200 kernels.
+
+    python -m b200gs.launcher --reference /path/to/ICLR2025_3D-MOM train_4DGS.py -s <scene> --expname <name> ...
+    python -m b200gs.launcher --reference /path/to/ICLR2025_3D-MOM render_4DGS.py --input_dir <dir> ...
+
+`install()` (1) puts the drop-in `diff_gaussian_rasterization` / `simple_knn` packages in front of the
+reference's compiled extensions, (2) appends import shims for third-party modules this image lacks
+(compat/), (3) swaps `deform_network` for the fused-kernel module where
+`GaussianModel` looks it up (scene/gaussian_model.py:21,53), (4) makes `training_setup` build the fused
+multi-tensor Adam from the very param groups the reference assembles (gaussian_model.py:197-209), and
+(5) installs the one-launch prune / cat bookkeeping (gaussian_model.py:424-482). The reference tree is
+never modified.
+"""
+import os
+import runpy
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG = os.path.dirname(_HERE)
+
+
+def install(reference_root):
+    reference_root = os.path.abspath(reference_root)
+    for p in (reference_root, _PKG, os.path.join(_PKG, "dropin")):
+        if p in sys.path:
+            sys.path.remove(p)
+        sys.path.insert(0, p)
+    compat = os.path.join(_PKG, "compat")
+    if compat not in sys.path:
+        sys.path.append(compat)            # last: real installations win
+    import scene.gaussian_model as gm       # the reference's module (imports scene.deformation etc.)
+    from . import densify
+    from .adam import FusedAdam
+    from .field import deform_network
+    gm.deform_network = deform_network
+    densify.patch_gaussian_model(gm.GaussianModel)
+    if not getattr(gm.GaussianModel, "_b200gs_patched", False):
+        for name in ("training_setup", "training_setup_jih"):
+            if not hasattr(gm.GaussianModel, name):
+                continue
+            orig = getattr(gm.GaussianModel, name)
+
+            def wrapped(self, *a, __orig=orig, **k):
+                out = __orig(self, *a, **k)
+                groups = [{kk: vv for kk, vv in g.items() if kk in ("params", "lr", "name")} for g in self.optimizer.param_groups]
+                self.optimizer = FusedAdam(groups, lr=0.0, eps=1e-15)
+                return out
+            setattr(gm.GaussianModel, name, wrapped)
+        gm.GaussianModel._b200gs_patched = True
+    return gm
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if len(argv) < 3 or argv[0] != "--reference":
+        raise SystemExit(__doc__)
+    ref, script, rest = argv[1], argv[2], argv[3:]
+    install(ref)
+    path = script if os.path.isabs(script) else os.path.join(os.path.abspath(ref), script)
+    os.chdir(os.path.abspath(ref))          # the scripts use paths relative to the repository root
+    sys.argv = [path] + rest
+    runpy.run_path(path, run_name="__main__")
+
+
+if __name__ == "__main__":
+    main()
