@@ -26,6 +26,7 @@ namespace b200gs {
 
 namespace {
 
+constexpr bool USE_TCGEN05_FORWARD = true;
 constexpr int MW = 64;             // net_width
 constexpr int MT = 256;            // threads per CTA (8 warps x 16 points)
 constexpr int ROWS = 128;          // points per CTA iteration
@@ -39,7 +40,7 @@ __device__ __forceinline__ void split(float x, u32& hi, u32& lo)
 }
 __device__ __forceinline__ void mma(float c[4], const u32 a[4], u32 b0, u32 b1)
 {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -70,7 +71,9 @@ __device__ __forceinline__ void stage_weight(float4* __restrict__ dst, const flo
     }
 }
 
-// acc[nt] += A(k-step j) * B[:, n-tile nt]  for nt in [0, NT); A given as its 4 fragment values
+// acc[nt] += A(k-step j) * B[:, n-tile nt]  for nt in [0, NT); A given as its 4 fragment values.
+// The three passes of the split are issued pass-major over groups of four n-tiles, so that back-to-back
+// MMAs never depend on each other (a dependent HMMA would wait out the full pipe latency).
 template <int NT>
 __device__ __forceinline__ void kstep(float (*acc)[4], const float a[4], const float4* __restrict__ Bq, int rs, int j,
                                       int g, int t)
@@ -78,8 +81,19 @@ __device__ __forceinline__ void kstep(float (*acc)[4], const float a[4], const f
     u32 ahi[4], alo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) split(a[i], ahi[i], alo[i]);
+    constexpr int G = NT < 4 ? NT : 4;
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) mma3(acc[nt], ahi, alo, Bq[(8 * nt + g) * rs + 4 * j + t]);
+    for (int n0 = 0; n0 < NT; n0 += G) {
+        float4 b[G];
+#pragma unroll
+        for (int q = 0; q < G; ++q) b[q] = Bq[(8 * (n0 + q) + g) * rs + 4 * j + t];
+#pragma unroll
+        for (int q = 0; q < G; ++q) mma(acc[n0 + q], alo, __float_as_uint(b[q].x), __float_as_uint(b[q].y));
+#pragma unroll
+        for (int q = 0; q < G; ++q) mma(acc[n0 + q], ahi, __float_as_uint(b[q].z), __float_as_uint(b[q].w));
+#pragma unroll
+        for (int q = 0; q < G; ++q) mma(acc[n0 + q], ahi, __float_as_uint(b[q].x), __float_as_uint(b[q].y));
+    }
 }
 
 struct FwdArgs {
@@ -239,12 +253,13 @@ __device__ __forceinline__ void dw_accumulate(float (*acc)[4], const float* __re
         u32 ahi[4], alo[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) split(af[i], ahi[i], alo[i]);
+        u32 b0[NT], b1[NT];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const u32 b0 = to_tf32(x0[nt]), b1 = to_tf32(x1[nt]);
-            mma(acc[nt], alo, b0, b1);
-            mma(acc[nt], ahi, b0, b1);
-        }
+        for (int nt = 0; nt < NT; ++nt) { b0[nt] = to_tf32(x0[nt]); b1[nt] = to_tf32(x1[nt]); }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma(acc[nt], alo, b0[nt], b1[nt]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma(acc[nt], ahi, b0[nt], b1[nt]);
     }
 }
 
@@ -476,6 +491,13 @@ int check_weights(const b200gs_mlp_weights* w)
 }  // namespace
 }  // namespace b200gs
 
+namespace b200gs {
+int deform_mlp_forward_tc5(const b200gs_mlp_weights* w, long long P, const float* feat, const float* xyz,
+                           const float* scales, const float* rot, const float* scene_flow, float frame_num,
+                           const float* frame_num_dev, float delta_scale, float* pts_out, float* scales_out,
+                           float* rot_out, float* saved, cudaStream_t stream);
+}
+
 using namespace b200gs;
 
 extern "C" {
@@ -489,6 +511,9 @@ int b200gs_deform_mlp_forward(const b200gs_mlp_weights* w, long long P, const fl
 {
     if (check_weights(w)) return -1;
     if (P <= 0) return 0;
+    if (USE_TCGEN05_FORWARD)
+        return deform_mlp_forward_tc5(w, P, feat, xyz, scales, rot, scene_flow, frame_num, frame_num_dev, delta_scale,
+                                      pts_out, scales_out, rot_out, saved, (cudaStream_t)stream);
     FwdArgs a;
     a.w = *w; a.P = P; a.feat = feat; a.xyz = xyz; a.scales = scales; a.rot = rot; a.scene_flow = scene_flow;
     a.frame_num = frame_num; a.frame_num_dev = frame_num_dev; a.delta_scale = delta_scale; a.pts_out = pts_out;

@@ -1,0 +1,336 @@
+// Deformation MLP forward on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Same function as the mma.sync forward it replaces (see deform_mlp.cu for the maths and the
+// reference citations): hidden = Linear(F,64)(feature); three heads ReLU-Linear(64,64)-ReLU-Linear(64,k).
+// One CTA (128 threads = one warpgroup) walks 128-point tiles:
+//   * thread r of the CTA owns point r of the tile = TMEM lane r;
+//   * activations live in TMEM as the A operand (lane = point, column = feature), written with
+//     tcgen05.st after bias / ReLU / TF32 hi-lo split, so no activation ever touches shared memory;
+//   * weights live in shared memory as K-major, un-swizzled UMMA operands (8-row x 16-byte core
+//     matrices), pre-split into hi and lo TF32 copies once per CTA;
+//   * every contraction is issued by ONE thread as 3 x (K/8) tcgen05.mma.kind::tf32 instructions
+//     (lo*hi + hi*lo + hi*hi, FP32 accumulation in TMEM: ~FP32 accuracy, the reference computes in
+//     true FP32), completion is signalled through tcgen05.commit -> mbarrier;
+//   * the epilogue reads the accumulator with tcgen05.ld (32 lanes x 32 bit, 32 columns at a time).
+// TMEM columns: [0, 2F) feature hi|lo, re-used as relu(hidden) hi [0,64) | lo [64,128);
+//               [2F, 2F+128) relu(z) hi|lo; [2F+128, +64) accumulator; [2F+192, +16) head output.
+#include "common.cuh"
+#include "../../include/b200gs.h"
+
+namespace b200gs {
+
+namespace tc5 {
+
+constexpr int MW = 64;
+constexpr int ROWS = 128;
+constexpr int NT = 128;            // threads per CTA
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u32 to_tf32(float x) { u32 r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity)
+{
+    u32 ok = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        if (++spins > (1u << 24)) __trap();      // never hang the GPU on a protocol error
+    }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(u64* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void mma_ts(u32 d_tmem, u32 a_tmem, u64 b_desc, u32 idesc, u32 accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+
+// K-major, no swizzle: element (n, k) of an [N x K] operand at byte (k/4)*(N*16) + n*16 + (k%4)*4
+// -> core matrix = 8 rows x 16 B contiguous (SBO = 128 B), next 16-byte K chunk at LBO = N*16 B.
+__device__ __forceinline__ u64 kmajor_desc(u32 smem_addr, int N)
+{
+    const u64 lbo = (u64)((N * 16) >> 4), sbo = (u64)(128 >> 4);
+    return (u64)((smem_addr >> 4) & 0x3FFF) | (lbo << 16) | (sbo << 32) | (1ull << 46);
+}
+__device__ __forceinline__ u32 make_idesc(int M, int N)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((u32)(N >> 3) << 17) | ((u32)(M >> 4) << 24);   // F32 accum, TF32 x TF32, K-major A and B
+}
+
+#define R8(v, o) "=r"(v[o]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
+#define W8(v, o) "r"(v[o]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]), "r"(v[o + 7])
+__device__ __forceinline__ void tmem_ld32(u32 addr, u32* v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : R8(v, 0), R8(v, 8), R8(v, 16), R8(v, 24) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(u32 addr, u32* v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : R8(v, 0), R8(v, 8) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(u32 addr, const u32* v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 :: "r"(addr), W8(v, 0), W8(v, 8), W8(v, 16), W8(v, 24) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// weights: torch [N_real x K] row-major -> hi / lo K-major UMMA operands with N rows (zero padded)
+__device__ __forceinline__ void stage_kmajor(float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ w,
+                                             int N, int N_real, int K)
+{
+    for (int i = threadIdx.x; i < N * K; i += NT) {
+        const int n = i / K, k = i - n * K;
+        const float v = n < N_real ? __ldg(w + (size_t)n * K + k) : 0.f;
+        const u32 h = to_tf32(v), l = to_tf32(v - __uint_as_float(h));
+        const int off = (k >> 2) * (N * 4) + n * 4 + (k & 3);
+        hi[off] = __uint_as_float(h);
+        lo[off] = __uint_as_float(l);
+    }
+}
+
+// 3 x (K/8) MMAs: D = (Ahi + Alo) (Bhi + Blo) without lo*lo, small terms first
+__device__ __forceinline__ void issue_layer(u32 d_tmem, u32 a_hi, u32 a_lo, u32 b_hi_smem, u32 b_lo_smem, int N, int K, u32 idesc)
+{
+    const u64 dh = kmajor_desc(b_hi_smem, N), dl = kmajor_desc(b_lo_smem, N);
+    const u64 step = (u64)((2 * N * 16) >> 4);         // two 16-byte K chunks per instruction
+    for (int j = 0; j < K / 8; ++j) {
+        mma_ts(d_tmem, a_lo + 8 * j, dh + step * j, idesc, j > 0);
+        mma_ts(d_tmem, a_hi + 8 * j, dl + step * j, idesc, 1u);
+        mma_ts(d_tmem, a_hi + 8 * j, dh + step * j, idesc, 1u);
+    }
+}
+
+struct FwdArgs {
+    b200gs_mlp_weights w;
+    long long P;
+    const float* feat; const float* xyz; const float* scales; const float* rot; const float* scene_flow;
+    float frame_num, delta_scale;
+    const float* frame_num_dev;
+    float* pts_out; float* scales_out; float* rot_out;
+    float* saved;                 // [4][P][64] row-major: relu(hidden), relu(z_pos), relu(z_scale), relu(z_rot)
+};
+
+template <int F>
+__global__ void __launch_bounds__(NT, 1) deform_mlp_fwd_tc5_kernel(const __grid_constant__ FwdArgs a)
+{
+    extern __shared__ __align__(1024) float smem[];
+    float* W1h = smem;                         // [F/4][64][4]
+    float* W1l = W1h + MW * F;
+    float* W2h = W1l + MW * F;                 // [3][16][64][4]
+    float* W2l = W2h + 3 * MW * MW;
+    float* W3h = W2l + 3 * MW * MW;            // [3][16][16][4]  (N padded to 16)
+    float* W3l = W3h + 3 * 16 * MW;
+    float* bias = W3l + 3 * 16 * MW;           // b1[64] b2[3][64] b3[3][16]
+    u64* bar = reinterpret_cast<u64*>(bias + 4 * MW + 48);
+    u32* tmem_slot = reinterpret_cast<u32*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int kdim[3] = {3, 3, 4};
+
+    stage_kmajor(W1h, W1l, a.w.w1, MW, MW, F);
+    for (int i = tid; i < MW; i += NT) bias[i] = __ldg(a.w.b1 + i);
+    for (int h = 0; h < 3; ++h) {
+        if (!a.w.w2[h]) continue;
+        stage_kmajor(W2h + h * MW * MW, W2l + h * MW * MW, a.w.w2[h], MW, MW, MW);
+        stage_kmajor(W3h + h * 16 * MW, W3l + h * 16 * MW, a.w.w3[h], 16, kdim[h], MW);
+        for (int i = tid; i < MW; i += NT) bias[MW + h * MW + i] = __ldg(a.w.b2[h] + i);
+        if (tid < 16) bias[4 * MW + h * 16 + tid] = tid < kdim[h] ? __ldg(a.w.b3[h] + tid) : 0.f;
+    }
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // make the generic-proxy weight writes visible to the tensor-core (async) proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const u32 tbase = *tmem_slot;
+    const u32 lane_addr = tbase + ((u32)(warp * 32) << 16);     // this warp's 32 TMEM lanes
+    constexpr u32 C_H_HI = 0, C_H_LO = 64, C_FE_LO = F, C_Z_HI = 2 * F, C_Z_LO = 2 * F + 64, C_D = 2 * F + 128, C_D3 = 2 * F + 192;
+    const u32 idesc64 = make_idesc(128, 64), idesc16 = make_idesc(128, 16);
+    u32 phase = 0;
+
+    const long long nblocks = (a.P + ROWS - 1) / ROWS;
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const long long r = blk * ROWS + tid;
+        const bool valid = r < a.P;
+        // ---- features -> TMEM (hi | lo) ----
+#pragma unroll
+        for (int c = 0; c < F / 32; ++c) {
+            u32 hi[32], lo[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 v = valid ? __ldg(reinterpret_cast<const float4*>(a.feat + (size_t)r * F + 32 * c) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { hi[4 * q + e] = to_tf32(x[e]); lo[4 * q + e] = to_tf32(x[e] - __uint_as_float(hi[4 * q + e])); }
+            }
+            tmem_st32(lane_addr + 32 * c, hi);
+            tmem_st32(lane_addr + C_FE_LO + 32 * c, lo);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer(tbase + C_D, tbase, tbase + C_FE_LO, smem_u32(W1h), smem_u32(W1l), MW, F, idesc64);
+            tc_commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+        // ---- hidden: bias, ReLU, stash, split, back to TMEM as the next A operand ----
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            u32 v[32], lo[32];
+            tmem_ld32(lane_addr + C_D + 32 * c, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const float x = fmaxf(__uint_as_float(v[e]) + bias[32 * c + e], 0.f);
+                v[e] = __float_as_uint(x);
+            }
+            if (valid) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    reinterpret_cast<float4*>(a.saved + (size_t)r * MW + 32 * c)[q] =
+                        make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const float x = __uint_as_float(v[e]);
+                v[e] = to_tf32(x);
+                lo[e] = to_tf32(x - __uint_as_float(v[e]));
+            }
+            tmem_st32(lane_addr + C_H_HI + 32 * c, v);
+            tmem_st32(lane_addr + C_H_LO + 32 * c, lo);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncthreads();
+        // ---- heads ----
+        for (int h = 0; h < 3; ++h) {
+            const int kd = kdim[h];
+            if (!a.w.w2[h]) {            // head disabled (no_dx / no_ds / no_dr): pass through
+                if (valid) {
+                    const float* src = h == 0 ? a.xyz : (h == 1 ? a.scales : a.rot);
+                    float* dst = h == 0 ? a.pts_out : (h == 1 ? a.scales_out : a.rot_out);
+                    for (int c = 0; c < kd; ++c) dst[(size_t)r * kd + c] = __ldg(src + (size_t)r * kd + c);
+                }
+                continue;
+            }
+            if (tid == 0) {
+                tc_fence_after();
+                issue_layer(tbase + C_D, tbase + C_H_HI, tbase + C_H_LO, smem_u32(W2h + h * MW * MW), smem_u32(W2l + h * MW * MW), MW, MW, idesc64);
+                tc_commit(bar);
+            }
+            mbar_wait(bar, phase); phase ^= 1;
+            tc_fence_after();
+            float* sv = a.saved + (size_t)(1 + h) * a.P * MW;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                u32 v[32], lo[32];
+                tmem_ld32(lane_addr + C_D + 32 * c, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(fmaxf(__uint_as_float(v[e]) + bias[MW + h * MW + 32 * c + e], 0.f));
+                if (valid) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        reinterpret_cast<float4*>(sv + (size_t)r * MW + 32 * c)[q] =
+                            make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                }
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float x = __uint_as_float(v[e]);
+                    v[e] = to_tf32(x);
+                    lo[e] = to_tf32(x - __uint_as_float(v[e]));
+                }
+                tmem_st32(lane_addr + C_Z_HI + 32 * c, v);
+                tmem_st32(lane_addr + C_Z_LO + 32 * c, lo);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                issue_layer(tbase + C_D3, tbase + C_Z_HI, tbase + C_Z_LO, smem_u32(W3h + h * 16 * MW), smem_u32(W3l + h * 16 * MW), 16, MW, idesc16);
+                tc_commit(bar);
+            }
+            mbar_wait(bar, phase); phase ^= 1;
+            tc_fence_after();
+            u32 o[16];
+            tmem_ld16(lane_addr + C_D3, o);
+            tmem_wait_ld();
+            if (valid) {
+                const float fn = a.frame_num_dev ? __ldg(a.frame_num_dev) : a.frame_num;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c >= kd) continue;
+                    const float ov = __uint_as_float(o[c]) + bias[4 * MW + h * 16 + c];
+                    if (h == 0) {
+                        const float flow = __fmul_rn(a.delta_scale, __fmul_rn(fn, __ldg(a.scene_flow + 3 * r + c)));
+                        a.pts_out[3 * r + c] = __fadd_rn(__fmul_rn(__ldg(a.xyz + 3 * r + c), 1.0f), __fadd_rn(ov, flow));
+                    } else if (h == 1) {
+                        a.scales_out[3 * r + c] = __fadd_rn(__fmul_rn(__ldg(a.scales + 3 * r + c), 1.0f), ov);
+                    } else {
+                        a.rot_out[4 * r + c] = __fadd_rn(__ldg(a.rot + 4 * r + c), ov);
+                    }
+                }
+            }
+            // all reads of this head's accumulators are done before the next MMA overwrites them
+            tc_fence_before();
+            __syncthreads();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(512u) : "memory");
+    }
+}
+
+size_t fwd_smem(int F) { return (size_t)(2 * MW * F + 6 * MW * MW + 6 * 16 * MW + 4 * MW + 48) * sizeof(float) + 64; }
+
+}  // namespace tc5
+
+int deform_mlp_forward_tc5(const b200gs_mlp_weights* w, long long P, const float* feat, const float* xyz,
+                           const float* scales, const float* rot, const float* scene_flow, float frame_num,
+                           const float* frame_num_dev, float delta_scale, float* pts_out, float* scales_out,
+                           float* rot_out, float* saved, cudaStream_t stream)
+{
+    tc5::FwdArgs a;
+    a.w = *w; a.P = P; a.feat = feat; a.xyz = xyz; a.scales = scales; a.rot = rot; a.scene_flow = scene_flow;
+    a.frame_num = frame_num; a.frame_num_dev = frame_num_dev; a.delta_scale = delta_scale; a.pts_out = pts_out;
+    a.scales_out = scales_out; a.rot_out = rot_out; a.saved = saved;
+    const long long nblocks = (P + tc5::ROWS - 1) / tc5::ROWS;
+    const int grid = (int)(nblocks < NUM_SMS ? nblocks : NUM_SMS);
+    const size_t smem = tc5::fwd_smem(w->feat_dim);
+    if (w->feat_dim == 64) {
+        cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc5::deform_mlp_fwd_tc5_kernel<64><<<grid, tc5::NT, smem, stream>>>(a);
+    } else {
+        cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc5::deform_mlp_fwd_tc5_kernel<128><<<grid, tc5::NT, smem, stream>>>(a);
+    }
+    return check_launch("deform_mlp_forward(tcgen05)");
+}
+
+}  // namespace b200gs
