@@ -1,0 +1,14 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, both bench arms, rasterizer timing, ncu launch list + full captures.
+# usage: tools/gpu_round.sh <tag> [kernel-regex for --set full]
+TAG=${1:-rX}
+KRE=${2:-deform_mlp_bwd}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" ; tail -3 gpurun_out/pytest_$TAG.log
+python bench.py --steps 5 --warmup 3 > gpurun_out/bench_b200_$TAG.json 2> gpurun_out/bench_b200_$TAG.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref rc=$?"
+python tools/time_raster.py > gpurun_out/time_raster_$TAG.log 2>&1
+V=2 python tools/profile_step.py > gpurun_out/kernels_$TAG.log 2>&1
+V=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv python tools/profile_step.py > gpurun_out/ncu_launch_$TAG.log 2>&1
+V=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$KRE" -s 3 -c 3 -f -o gpurun_out/prof_$TAG python tools/profile_step.py > gpurun_out/ncu_full_$TAG.log 2>&1
+cat gpurun_out/bench_b200_$TAG.json | cut -c1-400; cat gpurun_out/time_raster_$TAG.log | tail -4; head -14 gpurun_out/kernels_$TAG.log
