@@ -27,6 +27,7 @@ namespace b200gs {
 namespace {
 
 constexpr bool USE_TCGEN05_FORWARD = true;
+constexpr bool USE_TCGEN05_BACKWARD = true;     // F = 64 only; F = 128 keeps the mma.sync kernel below
 constexpr int MW = 64;             // net_width
 constexpr int MT = 256;            // threads per CTA (8 warps x 16 points)
 constexpr int ROWS = 128;          // points per CTA iteration
@@ -496,6 +497,9 @@ int deform_mlp_forward_tc5(const b200gs_mlp_weights* w, long long P, const float
                            const float* scales, const float* rot, const float* scene_flow, float frame_num,
                            const float* frame_num_dev, float delta_scale, float* pts_out, float* scales_out,
                            float* rot_out, float* saved, cudaStream_t stream);
+int deform_mlp_backward_tc5(const b200gs_mlp_weights* w, const b200gs_mlp_grads* gw, long long P, const float* feat,
+                            const float* saved, const float* d_pts, const float* d_scales, const float* d_rot,
+                            float* d_feat, cudaStream_t stream);
 }
 
 using namespace b200gs;
@@ -538,6 +542,8 @@ int b200gs_deform_mlp_backward(const b200gs_mlp_weights* w, const b200gs_mlp_gra
     if (check_weights(w)) return -1;
     if (!gw) { set_error("deform_mlp_backward: null gradient table"); return -1; }
     if (P <= 0) return 0;
+    if (USE_TCGEN05_BACKWARD && w->feat_dim == 64)
+        return deform_mlp_backward_tc5(w, gw, P, feat, saved, d_pts, d_scales, d_rot, d_feat, (cudaStream_t)stream);
     BwdArgs a;
     a.w = *w; a.gw = *gw; a.P = P; a.feat = feat; a.saved = saved; a.d_pts = d_pts; a.d_scales = d_scales;
     a.d_rot = d_rot; a.d_feat = d_feat;

@@ -1,0 +1,386 @@
+// Deformation MLP backward on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a, F = 64.
+//
+// Maths (scene/deformation.py:55-65, :97-153 differentiated; see deform_mlp.cu for the forward):
+//     dz_h   = (d_out_h W3_h) * [relu(z_h) > 0]                      h = pos, scales, rotations
+//     d relu(hidden) = sum_h dz_h W2_h ;  dh = d relu(hidden) * [relu(hidden) > 0]
+//     d feature = dh W1
+//     dW3_h = d_out_h^T relu(z_h), dW2_h = dz_h^T relu(hidden), dW1 = dh^T feature, db = column sums
+//
+// One persistent CTA per SM (256 threads) walks 128-point tiles.
+//   * SIMT side, thread = (4-column chunk q, 8 points): dz (the K <= 4 contraction with W3), the
+//     ReLU masks, dW3 and every bias gradient are plain FP32 in registers (dW3 / biases accumulate in
+//     registers over all tiles of the CTA).  Eight lanes cover one 128-byte row, so every global load
+//     and every shared-memory store below is a full line / conflict free.
+//   * dX chain on the tensor cores, SS mode:  D_RH[p][in] += (dz_hi + dz_lo)[p][out] tf32(W2_h)[out][in],
+//     D_FE = (dh_hi + dh_lo) tf32(W1).  A = DYK, un-swizzled K-major core matrices (chunk stride padded
+//     to 2064 B so the column-chunk-per-lane stores do not collide), hi and lo planes -> dY is exact,
+//     only the weights are rounded (2^-12 relative, random sign).
+//   * weight gradients on the tensor cores: D_W[out][in] += tf32(dY)^T tf32(X), contraction over the 128
+//     points of the tile, with M = 128 rows = [dY_hi ; dY_lo] (the two halves are added at the flush, so
+//     dY is exact and only X is rounded).  Both operands are MN-major; for TF32 the only MN-major shared-memory layout
+//     tcgen05 accepts is SWIZZLE_128B_BASE32B (descriptor layout type 1): atoms of 4 k-rows x 128 B
+//     (32 MN elements), the 32-byte granule index XORed with the row index (probed on hardware,
+//     tools/probe/umma_probe.cu).  The accumulators D_W2[3], D_W1 stay in TMEM for the whole life of
+//     the CTA and are flushed with one atomic per element per CTA at the end.
+// Shared memory (~225 KB): W2B 48 K | W1B 16 K | DYM 64 K | XH 32 K | DYK 2 x 33 K.
+// TMEM columns: D_RH [0,64)  D_FE [64,128)  D_W2[h] [128 + 64 h, +64)  D_W1 [320,384).
+#include "tc5_common.cuh"
+#include "../../include/b200gs.h"
+
+namespace b200gs {
+namespace tc5 {
+
+constexpr int BT = 256;                     // threads per CTA
+constexpr u32 KCH = 2064;                   // DYK: bytes between 4-column chunks (2048 + 16 pad)
+constexpr u32 KPLANE = 16 * KCH;            // one hi / lo plane of DYK
+constexpr u64 DESC_SW128_32B = 1ull << 61;  // smem descriptor layout type SWIZZLE_128B_BASE32B
+
+struct BwdArgs {
+    b200gs_mlp_weights w;
+    b200gs_mlp_grads gw;
+    long long P;
+    const float* feat; const float* saved;
+    const float* d_pts; const float* d_scales; const float* d_rot;
+    float* d_feat;
+};
+
+// B operand for D[p][n] = sum_k A[p][k] Wm[k][n] with Wm[k][n] = w[k*ld + n]: K-major [N][K], tf32 rounded
+__device__ __forceinline__ void stage_b_kmajor(float* __restrict__ dst, const float* __restrict__ w, int N, int K, int ld)
+{
+    for (int i = threadIdx.x; i < N * K; i += BT) {
+        const int k = i / N, n = i - k * N;                         // coalesced global reads along n
+        dst[(k >> 2) * (N * 4) + n * 4 + (k & 3)] = __uint_as_float(to_tf32(__ldg(w + (size_t)k * ld + n)));
+    }
+}
+
+__device__ __forceinline__ float4 tf32x4(float4 v)
+{
+    return make_float4(__uint_as_float(to_tf32(v.x)), __uint_as_float(to_tf32(v.y)), __uint_as_float(to_tf32(v.z)), __uint_as_float(to_tf32(v.w)));
+}
+__device__ __forceinline__ void split4(const float* x, float4& hi, float4& lo)
+{
+    float h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { h[e] = __uint_as_float(to_tf32(x[e])); l[e] = __uint_as_float(to_tf32(x[e] - h[e])); }
+    hi = make_float4(h[0], h[1], h[2], h[3]); lo = make_float4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void sts128(u32 addr, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(u32 addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_constant__ BwdArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float* W2B = reinterpret_cast<float*>(smem_raw);                 // [3][16 k-chunks][64 n][4]
+    float* W1B = W2B + 3 * MW * MW;                                  // [16][64][4]
+    unsigned char* DYM = smem_raw + (3 * MW * MW + MW * MW) * 4;      // 64 KB, MN-major swizzled  [out: 64 hi rows | 64 lo rows][p 128]
+    unsigned char* XH = DYM + 65536;                                 // 32 KB, MN-major swizzled  [in 64][p 128]
+    unsigned char* DYK = XH + 32768;                                 // 2 planes x 16 chunks x 2064 B, K-major  [p 128][out 64]
+    u64* bar = reinterpret_cast<u64*>(DYK + 2 * KPLANE);
+    u32* tmem_slot = reinterpret_cast<u32*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // SIMT mapping: columns 32 c + 4 q + e, points 32 pg + 4 i + sub (i = 0..7)
+    const int q = lane & 7, sub = lane >> 3, c = warp & 1, pg = warp >> 1;
+    const int col0 = 32 * c + 4 * q;
+    // TMEM mapping (tcgen05.ld 32x32b): lane = point, 32 consecutive columns
+    const int pT = (warp & 3) * 32 + lane, cT = warp >> 2;
+    const int kdim[3] = {3, 3, 4};
+
+    // ---- one-time staging ----
+    for (int h = 0; h < 3; ++h) {
+        if (!a.w.w2[h]) continue;
+        stage_b_kmajor(W2B + h * MW * MW, a.w.w2[h], MW, MW, MW);     // Wm[k = out][n = in] = W2[out][in]
+    }
+    stage_b_kmajor(W1B, a.w.w1, MW, MW, MW);                           // Wm[k = out][n = feature] = W1[out][f]  (F = 64)
+    for (int i = tid; i < 98304 / 16; i += BT) reinterpret_cast<float4*>(DYM)[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // DYM + XH
+    if (tid == 0) {
+        if (smem_u32(DYM) & 1023u) __trap();                          // the swizzle below assumes 1 KB aligned tiles
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const u32 tbase = *tmem_slot;
+    const u32 lane_addr = tbase + ((u32)((warp & 3) * 32) << 16);
+    constexpr u32 C_RH = 0, C_FE = 64, C_W2 = 128, C_W1 = 320;
+    const u32 id_kk = make_idesc(128, 64);
+    const u32 id_mn = make_idesc(128, 64) | IDESC_A_MN | IDESC_B_MN;
+    const u32 sDYM = smem_u32(DYM), sXH = smem_u32(XH), sDYK = smem_u32(DYK), sW2 = smem_u32(W2B), sW1 = smem_u32(W1B);
+    // this thread's store offsets: MN tiles  c * 16 KB + p * 128 + (granule ^ (p & 3)) * 32 + half * 16 with p & 3 == sub
+    const u32 mn_off = (u32)c * 16384u + (u32)((((q >> 1) ^ sub) << 5) | ((q & 1) << 4));
+    const u32 k_off = (u32)(8 * c + q) * KCH;
+    const int p0 = 32 * pg + sub;                                     // point of iteration i: p0 + 4 i
+
+    u32 phase = 0;
+    bool pending = false;            // an MMA group has been committed and not yet waited for
+    bool first_tile = true;
+    long long prev_row = -1;         // row (TMEM mapping) whose d_feature is still in D_FE
+    float gW3[3][4][4], gB2[3][4], gB3[3][4], gB1[4];
+#pragma unroll
+    for (int h = 0; h < 3; ++h)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            gB2[h][k] = 0.f; gB3[h][k] = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) gW3[h][k][e] = 0.f;
+        }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) gB1[e] = 0.f;
+
+    auto drain = [&]() {             // wait for the committed MMA group; then D_FE of the previous tile can be stored
+        if (pending) {
+            mbar_wait(bar, phase); phase ^= 1; pending = false;
+            tc_fence_after();
+        }
+        if (prev_row >= 0) {
+            u32 v[32];
+            tmem_ld32(lane_addr + C_FE + 32 * cT, v);
+            tmem_wait_ld();
+            if (prev_row < a.P) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    reinterpret_cast<float4*>(a.d_feat + (size_t)prev_row * MW + 32 * cT)[j] =
+                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+            prev_row = -1;
+        }
+    };
+
+    const long long nblocks = (a.P + ROWS - 1) / ROWS;
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const long long row0 = blk * ROWS + p0;
+        // ---- relu(hidden): sign mask for dh + B operand of dW2 ----
+        float4 hrow[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            hrow[i] = row0 + 4 * i < a.P ? __ldg(reinterpret_cast<const float4*>(a.saved + (size_t)(row0 + 4 * i) * MW + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        u32 hmask = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            hmask |= (hrow[i].x > 0.f ? 1u : 0u) << (4 * i) | (hrow[i].y > 0.f ? 1u : 0u) << (4 * i + 1) |
+                     (hrow[i].z > 0.f ? 1u : 0u) << (4 * i + 2) | (hrow[i].w > 0.f ? 1u : 0u) << (4 * i + 3);
+        bool h_staged = false, rh_started = false;
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+            if (!a.w.w2[h]) continue;
+            const int kd = kdim[h];
+            const float* dsrc = h == 0 ? a.d_pts : (h == 1 ? a.d_scales : a.d_rot);
+            const float* zsv = a.saved + (size_t)(1 + h) * a.P * MW;
+            float4 w3[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w3[k] = k < kd ? __ldg(reinterpret_cast<const float4*>(a.w.w3[h] + k * MW + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 zrow[8];
+            float dout[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long long r = row0 + 4 * i;
+                const bool valid = r < a.P;
+                zrow[i] = valid ? __ldg(reinterpret_cast<const float4*>(zsv + (size_t)r * MW + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dout[i][k] = (valid && dsrc && k < kd) ? __ldg(dsrc + (size_t)r * kd + k) : 0.f;
+            }
+            float4 dzh[8], dzl[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float zz[4] = {zrow[i].x, zrow[i].y, zrow[i].z, zrow[i].w};
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float wk[4] = {e == 0 ? w3[0].x : e == 1 ? w3[0].y : e == 2 ? w3[0].z : w3[0].w,
+                                         e == 0 ? w3[1].x : e == 1 ? w3[1].y : e == 2 ? w3[1].z : w3[1].w,
+                                         e == 0 ? w3[2].x : e == 1 ? w3[2].y : e == 2 ? w3[2].z : w3[2].w,
+                                         e == 0 ? w3[3].x : e == 1 ? w3[3].y : e == 2 ? w3[3].z : w3[3].w};
+                    float s = dout[i][0] * wk[0];
+                    s = fmaf(dout[i][1], wk[1], s);
+                    s = fmaf(dout[i][2], wk[2], s);
+                    if (kd > 3) s = fmaf(dout[i][3], wk[3], s);
+                    v[e] = zz[e] > 0.f ? s : 0.f;
+                    gB2[h][e] += v[e];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < kd) gW3[h][k][e] = fmaf(dout[i][k], zz[e], gW3[h][k][e]);
+                }
+                split4(v, dzh[i], dzl[i]);
+                if (q == 0 && c == 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) gB3[h][k] += dout[i][k];
+                }
+            }
+            drain();                 // the previous MMA group still reads DYK / DYM / XH
+            if (!h_staged) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sts128(sXH + mn_off + (u32)(p0 + 4 * i) * 128u, tf32x4(hrow[i]));
+                h_staged = true;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const u32 pp = (u32)(p0 + 4 * i);
+                sts128(sDYK + k_off + pp * 16u, dzh[i]);
+                sts128(sDYK + KPLANE + k_off + pp * 16u, dzl[i]);
+                sts128(sDYM + mn_off + pp * 128u, dzh[i]);
+                sts128(sDYM + 32768u + mn_off + pp * 128u, dzl[i]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const u32 w2 = sW2 + h * MW * MW * 4;
+                for (int j = 0; j < 8; ++j) {          // K = 64 out features, 8 per instruction
+                    const u64 bd = smem_desc(w2 + j * 2 * (MW * 16), MW * 16, 128);
+                    mma_ss(tbase + C_RH, smem_desc(sDYK + KPLANE + j * 2 * KCH, KCH, 128), bd, id_kk, (rh_started || j > 0) ? 1u : 0u);
+                    mma_ss(tbase + C_RH, smem_desc(sDYK + j * 2 * KCH, KCH, 128), bd, id_kk, 1u);
+                }
+                for (int j = 0; j < 16; ++j)           // K = 128 points, 8 per instruction (two 4-row atoms)
+                    mma_ss(tbase + C_W2 + 64 * h, smem_desc(sDYM + j * 1024, 16384, 512) | DESC_SW128_32B,
+                           smem_desc(sXH + j * 1024, 16384, 512) | DESC_SW128_32B, id_mn, (first_tile && j == 0) ? 0u : 1u);
+                tc_commit(bar);
+            }
+            pending = true;
+            rh_started = true;
+        }
+        // ---- dh = d relu(hidden) masked ; d feature = dh W1 ; dW1 += dh^T feature ----
+        float4 frow[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            frow[i] = row0 + 4 * i < a.P ? __ldg(reinterpret_cast<const float4*>(a.feat + (size_t)(row0 + 4 * i) * MW + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        drain();
+        {   // D_RH comes out of TMEM as (lane = point, 32 columns); bounce it through the DYK hi plane to reach the SIMT mapping
+            u32 v[32];
+            if (rh_started) {
+                tmem_ld32(lane_addr + C_RH + 32 * cT, v);
+                tmem_wait_ld();
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                sts128(sDYK + (u32)(8 * cT + j) * KCH + (u32)pT * 16u,
+                       make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+        }
+        tc_fence_before();
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const u32 pp = (u32)(p0 + 4 * i);
+            const float4 r4 = lds128(sDYK + k_off + pp * 16u);
+            float x[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                x[e] = (hmask >> (4 * i + e)) & 1u ? x[e] : 0.f;
+                gB1[e] += x[e];
+            }
+            float4 hi, lo;
+            split4(x, hi, lo);
+            sts128(sDYK + k_off + pp * 16u, hi);
+            sts128(sDYK + KPLANE + k_off + pp * 16u, lo);
+            sts128(sDYM + mn_off + pp * 128u, hi);
+            sts128(sDYM + 32768u + mn_off + pp * 128u, lo);
+            sts128(sXH + mn_off + pp * 128u, tf32x4(frow[i]));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int j = 0; j < 8; ++j) {
+                const u64 bd = smem_desc(sW1 + j * 2 * (MW * 16), MW * 16, 128);
+                mma_ss(tbase + C_FE, smem_desc(sDYK + KPLANE + j * 2 * KCH, KCH, 128), bd, id_kk, j > 0 ? 1u : 0u);
+                mma_ss(tbase + C_FE, smem_desc(sDYK + j * 2 * KCH, KCH, 128), bd, id_kk, 1u);
+            }
+            for (int j = 0; j < 16; ++j)
+                mma_ss(tbase + C_W1, smem_desc(sDYM + j * 1024, 16384, 512) | DESC_SW128_32B,
+                       smem_desc(sXH + j * 1024, 16384, 512) | DESC_SW128_32B, id_mn, (first_tile && j == 0) ? 0u : 1u);
+            tc_commit(bar);
+        }
+        pending = true;
+        prev_row = blk * ROWS + pT;
+        first_tile = false;
+    }
+    drain();
+
+    // ---- flush ----
+    if (!first_tile) {
+        // TMEM-resident weight gradients: lanes 0..63 = out feature from dY_hi, lanes 64..127 the same from dY_lo
+        {
+            for (int m = 0; m < 4; ++m) {
+                if (m < 3 && !a.w.w2[m]) continue;
+                float* dst = m < 3 ? a.gw.w2[m] : a.gw.w1;
+                u32 v[32];
+                tmem_ld32(lane_addr + (m < 3 ? C_W2 + 64 * m : C_W1) + 32 * cT, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) atomicAdd(dst + (pT & 63) * MW + 32 * cT + e, __uint_as_float(v[e]));
+            }
+        }
+        // register-resident partial sums: fold the 4 `sub` lanes, then one atomic per column per warp
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float s = gB1[e];
+            s += __shfl_xor_sync(0xffffffffu, s, 8); s += __shfl_xor_sync(0xffffffffu, s, 16);
+            if (sub == 0) atomicAdd(a.gw.b1 + col0 + e, s);
+        }
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+            if (!a.w.w2[h]) continue;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float s = gB2[h][e];
+                s += __shfl_xor_sync(0xffffffffu, s, 8); s += __shfl_xor_sync(0xffffffffu, s, 16);
+                if (sub == 0) atomicAdd(a.gw.b2[h] + col0 + e, s);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float t = gW3[h][k][e];
+                    t += __shfl_xor_sync(0xffffffffu, t, 8); t += __shfl_xor_sync(0xffffffffu, t, 16);
+                    if (sub == 0 && k < kdim[h]) atomicAdd(a.gw.w3[h] + k * MW + col0 + e, t);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float s = gB3[h][k];                     // non-zero only in lanes with q == 0 of the c == 0 warps
+                s += __shfl_xor_sync(0xffffffffu, s, 8); s += __shfl_xor_sync(0xffffffffu, s, 16);
+                if (lane == 0 && c == 0 && k < kdim[h]) atomicAdd(a.gw.b3[h] + k, s);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(512u) : "memory");
+    }
+}
+
+size_t bwd_smem() { return (size_t)(3 * MW * MW + MW * MW) * 4 + 98304 + 2 * KPLANE + 64; }
+
+}  // namespace tc5
+
+int deform_mlp_backward_tc5(const b200gs_mlp_weights* w, const b200gs_mlp_grads* gw, long long P, const float* feat,
+                            const float* saved, const float* d_pts, const float* d_scales, const float* d_rot,
+                            float* d_feat, cudaStream_t stream)
+{
+    tc5::BwdArgs a;
+    a.w = *w; a.gw = *gw; a.P = P; a.feat = feat; a.saved = saved; a.d_pts = d_pts; a.d_scales = d_scales; a.d_rot = d_rot;
+    a.d_feat = d_feat;
+    const long long nblocks = (P + tc5::ROWS - 1) / tc5::ROWS;
+    const int grid = (int)(nblocks < NUM_SMS ? nblocks : NUM_SMS);
+    const size_t smem = tc5::bwd_smem();
+    cudaFuncSetAttribute(tc5::deform_mlp_bwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc5::deform_mlp_bwd_tc5_kernel<<<grid, tc5::BT, smem, stream>>>(a);
+    return check_launch("deform_mlp_backward(tcgen05)");
+}
+
+}  // namespace b200gs

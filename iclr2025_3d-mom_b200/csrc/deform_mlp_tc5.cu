@@ -14,79 +14,14 @@
 //   * the epilogue reads the accumulator with tcgen05.ld (32 lanes x 32 bit, 32 columns at a time).
 // TMEM columns: [0, 2F) feature hi|lo, re-used as relu(hidden) hi [0,64) | lo [64,128);
 //               [2F, 2F+128) relu(z) hi|lo; [2F+128, +64) accumulator; [2F+192, +16) head output.
-#include "common.cuh"
+#include "tc5_common.cuh"
 #include "../../include/b200gs.h"
 
 namespace b200gs {
 
 namespace tc5 {
 
-constexpr int MW = 64;
-constexpr int ROWS = 128;
 constexpr int NT = 128;            // threads per CTA
-
-__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ u32 to_tf32(float x) { u32 r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
-
-__device__ __forceinline__ void mbar_init(u64* bar, u32 count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity)
-{
-    u32 ok = 0, spins = 0;
-    while (true) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (ok) break;
-        if (++spins > (1u << 24)) __trap();      // never hang the GPU on a protocol error
-    }
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(u64* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void mma_ts(u32 d_tmem, u32 a_tmem, u64 b_desc, u32 idesc, u32 accumulate)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-
-// K-major, no swizzle: element (n, k) of an [N x K] operand at byte (k/4)*(N*16) + n*16 + (k%4)*4
-// -> core matrix = 8 rows x 16 B contiguous (SBO = 128 B), next 16-byte K chunk at LBO = N*16 B.
-__device__ __forceinline__ u64 kmajor_desc(u32 smem_addr, int N)
-{
-    const u64 lbo = (u64)((N * 16) >> 4), sbo = (u64)(128 >> 4);
-    return (u64)((smem_addr >> 4) & 0x3FFF) | (lbo << 16) | (sbo << 32) | (1ull << 46);
-}
-__device__ __forceinline__ u32 make_idesc(int M, int N)
-{
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((u32)(N >> 3) << 17) | ((u32)(M >> 4) << 24);   // F32 accum, TF32 x TF32, K-major A and B
-}
-
-#define R8(v, o) "=r"(v[o]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
-#define W8(v, o) "r"(v[o]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]), "r"(v[o + 7])
-__device__ __forceinline__ void tmem_ld32(u32 addr, u32* v)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : R8(v, 0), R8(v, 8), R8(v, 16), R8(v, 24) : "r"(addr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(u32 addr, u32* v)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : R8(v, 0), R8(v, 8) : "r"(addr) : "memory");
-}
-__device__ __forceinline__ void tmem_st32(u32 addr, const u32* v)
-{
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-                 :: "r"(addr), W8(v, 0), W8(v, 8), W8(v, 16), W8(v, 24) : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // weights: torch [N_real x K] row-major -> hi / lo K-major UMMA operands with N rows (zero padded)
 __device__ __forceinline__ void stage_kmajor(float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ w,
