@@ -159,14 +159,40 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
         }
     };
 
+    // Global loads run one phase ahead of their use (phases of a tile: head 0, 1, 2, then the feature rows for dW1;
+    // the relu(hidden) rows of the NEXT tile are fetched during the last phase), so their latency hides behind the
+    // MMA drain + shared-memory stores of the phase before.
+    const bool en0 = a.w.w2[0] != nullptr, en1 = a.w.w2[1] != nullptr, en2 = a.w.w2[2] != nullptr;
+    auto next_phase = [&](int ph) { return (ph < 0 && en0) ? 0 : (ph < 1 && en1) ? 1 : (ph < 2 && en2) ? 2 : 3; };
+    auto load_rows = [&](float4* x, const float* src, long long r0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            x[i] = r0 + 4 * i < a.P ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(r0 + 4 * i) * MW + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto load_phase_rows = [&](int ph, float4* x, long long r0) {
+        load_rows(x, ph >= 3 ? a.feat : a.saved + (size_t)(1 + ph) * a.P * MW, r0);
+    };
+    auto load_phase_dout = [&](int ph, float (*d)[4], long long r0) {
+        if (ph >= 3) return;
+        const float* dsrc = ph == 0 ? a.d_pts : (ph == 1 ? a.d_scales : a.d_rot);
+        const int kd = ph == 2 ? 4 : 3;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long r = r0 + 4 * i;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d[i][k] = (r < a.P && dsrc && k < kd) ? __ldg(dsrc + (size_t)r * kd + k) : 0.f;
+        }
+    };
+
     const long long nblocks = (a.P + ROWS - 1) / ROWS;
+    float4 hrow[8], xin[8];
+    if ((long long)blockIdx.x < nblocks) {
+        load_rows(hrow, a.saved, (long long)blockIdx.x * ROWS + p0);
+        load_phase_rows(next_phase(-1), xin, (long long)blockIdx.x * ROWS + p0);
+    }
     for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const long long row0 = blk * ROWS + p0;
         // ---- relu(hidden): sign mask for dh + B operand of dW2 ----
-        float4 hrow[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            hrow[i] = row0 + 4 * i < a.P ? __ldg(reinterpret_cast<const float4*>(a.saved + (size_t)(row0 + 4 * i) * MW + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
         u32 hmask = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -177,48 +203,37 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
         for (int h = 0; h < 3; ++h) {
             if (!a.w.w2[h]) continue;
             const int kd = kdim[h];
-            const float* dsrc = h == 0 ? a.d_pts : (h == 1 ? a.d_scales : a.d_rot);
-            const float* zsv = a.saved + (size_t)(1 + h) * a.P * MW;
             float4 w3[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) w3[k] = k < kd ? __ldg(reinterpret_cast<const float4*>(a.w.w3[h] + k * MW + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 zrow[8];
-            float dout[8][4];
+            float din[8][4];
+            load_phase_dout(h, din, row0);
+            float dz[8][4];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const long long r = row0 + 4 * i;
-                const bool valid = r < a.P;
-                zrow[i] = valid ? __ldg(reinterpret_cast<const float4*>(zsv + (size_t)r * MW + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) dout[i][k] = (valid && dsrc && k < kd) ? __ldg(dsrc + (size_t)r * kd + k) : 0.f;
-            }
-            float4 dzh[8], dzl[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float zz[4] = {zrow[i].x, zrow[i].y, zrow[i].z, zrow[i].w};
-                float v[4];
+                const float zz[4] = {xin[i].x, xin[i].y, xin[i].z, xin[i].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float wk[4] = {e == 0 ? w3[0].x : e == 1 ? w3[0].y : e == 2 ? w3[0].z : w3[0].w,
                                          e == 0 ? w3[1].x : e == 1 ? w3[1].y : e == 2 ? w3[1].z : w3[1].w,
                                          e == 0 ? w3[2].x : e == 1 ? w3[2].y : e == 2 ? w3[2].z : w3[2].w,
                                          e == 0 ? w3[3].x : e == 1 ? w3[3].y : e == 2 ? w3[3].z : w3[3].w};
-                    float s = dout[i][0] * wk[0];
-                    s = fmaf(dout[i][1], wk[1], s);
-                    s = fmaf(dout[i][2], wk[2], s);
-                    if (kd > 3) s = fmaf(dout[i][3], wk[3], s);
-                    v[e] = zz[e] > 0.f ? s : 0.f;
-                    gB2[h][e] += v[e];
+                    float s = din[i][0] * wk[0];
+                    s = fmaf(din[i][1], wk[1], s);
+                    s = fmaf(din[i][2], wk[2], s);
+                    if (kd > 3) s = fmaf(din[i][3], wk[3], s);
+                    dz[i][e] = zz[e] > 0.f ? s : 0.f;
+                    gB2[h][e] += dz[i][e];
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (k < kd) gW3[h][k][e] = fmaf(dout[i][k], zz[e], gW3[h][k][e]);
+                        if (k < kd) gW3[h][k][e] = fmaf(din[i][k], zz[e], gW3[h][k][e]);
                 }
-                split4(v, dzh[i], dzl[i]);
                 if (q == 0 && c == 0) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) gB3[h][k] += dout[i][k];
+                    for (int k = 0; k < 4; ++k) gB3[h][k] += din[i][k];
                 }
             }
+            load_phase_rows(next_phase(h), xin, row0);          // next head's rows, or the feature rows
             drain();                 // the previous MMA group still reads DYK / DYM / XH
             if (!h_staged) {
 #pragma unroll
@@ -228,10 +243,12 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const u32 pp = (u32)(p0 + 4 * i);
-                sts128(sDYK + k_off + pp * 16u, dzh[i]);
-                sts128(sDYK + KPLANE + k_off + pp * 16u, dzl[i]);
-                sts128(sDYM + mn_off + pp * 128u, dzh[i]);
-                sts128(sDYM + 32768u + mn_off + pp * 128u, dzl[i]);
+                float4 hi, lo;
+                split4(dz[i], hi, lo);
+                sts128(sDYK + k_off + pp * 16u, hi);
+                sts128(sDYK + KPLANE + k_off + pp * 16u, lo);
+                sts128(sDYM + mn_off + pp * 128u, hi);
+                sts128(sDYM + 32768u + mn_off + pp * 128u, lo);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_before();
@@ -253,10 +270,14 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
             rh_started = true;
         }
         // ---- dh = d relu(hidden) masked ; d feature = dh W1 ; dW1 += dh^T feature ----
+        if (next_phase(-1) == 3) load_rows(xin, a.feat, row0);        // every head disabled: nothing was prefetched
         float4 frow[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            frow[i] = row0 + 4 * i < a.P ? __ldg(reinterpret_cast<const float4*>(a.feat + (size_t)(row0 + 4 * i) * MW + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i) frow[i] = xin[i];
+        if (blk + gridDim.x < nblocks) {                              // next tile: relu(hidden) rows and the first phase's inputs
+            load_rows(hrow, a.saved, (blk + gridDim.x) * ROWS + p0);
+            load_phase_rows(next_phase(-1), xin, (blk + gridDim.x) * ROWS + p0);
+        }
         drain();
         {   // D_RH comes out of TMEM as (lane = point, 32 columns); bounce it through the DYK hi plane to reach the SIMT mapping
             u32 v[32];
