@@ -98,8 +98,10 @@ class GaussianState(nn.Module):
         return self.optimizer
 
 
-def render(cam, pc, bg_color, scaling_modifier=1.0, stage="fine", delta_scale=1, debug=False):
-    """gaussian_renderer/__init__.py:22-178 for a b200gs.synthetic.SynthCamera-like `cam`."""
+def render(cam, pc, bg_color, scaling_modifier=1.0, stage="fine", delta_scale=1, debug=False, shs=None):
+    """gaussian_renderer/__init__.py:22-178 for a b200gs.synthetic.SynthCamera-like `cam`.
+    `shs`: optional pre-concatenated [P,16,3] SH tensor standing in for `pc.get_features` (the trainer
+    concatenates once per optimiser step instead of once per view; the values are identical)."""
     means3D = pc.get_xyz
     screenspace_points = torch.zeros_like(means3D, requires_grad=True)
     settings = GaussianRasterizationSettings(
@@ -107,7 +109,9 @@ def render(cam, pc, bg_color, scaling_modifier=1.0, stage="fine", delta_scale=1,
         bg=bg_color, scale_modifier=scaling_modifier, viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix,
         sh_degree=pc.active_sh_degree, campos=cam.campos, prefiltered=False, debug=debug)
     rasterizer = GaussianRasterizer(raster_settings=settings)
-    opacity, shs, scales, rotations = pc._opacity, pc.get_features, pc._scaling, pc._rotation
+    opacity, scales, rotations = pc._opacity, pc._scaling, pc._rotation
+    if shs is None:
+        shs = pc.get_features
     if stage == "coarse":
         m3, sc, rt, op, sh = means3D, scales, rotations, opacity, shs
     else:
@@ -146,7 +150,9 @@ class ViewParallelTrainer:
         self.pg = process_group
         self.world_size = world_size
         self.rank = rank
-        self.render_fn = render_fn or (lambda cam, m, bg, st: render(cam, m, bg, stage=st))
+        # our own render() takes the per-step SH tensor; an injected render_fn keeps the 4-argument form
+        self.shared_shs = render_fn is None
+        self.render_fn = render_fn or (lambda cam, m, bg, st, shs=None: render(cam, m, bg, stage=st, shs=shs))
         P = model.get_xyz.shape[0]
         # flat gradient arena: [every parameter the loss reaches | screen-space xy per Gaussian];
         # p.grad are views into it, so autograd accumulates in place and ONE collective (fp32 sum
@@ -185,8 +191,15 @@ class ViewParallelTrainer:
         B = global_batch or (len(cams) * self.world_size)
         self._bind()
         total = None
+        shs = None
+        if self.shared_shs:
+            # get_features (scene/gaussian_model.py:136-140) is the same tensor for every view of the step: build it once
+            # as a leaf, let the views' SH gradients accumulate in it, and split them back after the last view
+            m = self.model
+            shs = torch.cat((m._features_dc, m._features_rest), dim=1).detach().requires_grad_(True)
         for cam, gt in zip(cams, gts):
-            pkg = self.render_fn(cam, self.model, self.bg, self.stage)
+            pkg = self.render_fn(cam, self.model, self.bg, self.stage, shs) if self.shared_shs else \
+                self.render_fn(cam, self.model, self.bg, self.stage)
             loss = (pkg["render"] - gt).abs().mean() / B
             loss.backward()
             vg = pkg["viewspace_points"].grad
@@ -194,6 +207,9 @@ class ViewParallelTrainer:
                 self.viewspace_grad += vg
             torch.maximum(self.max_radii, pkg["radii"], out=self.max_radii)
             total = loss.detach() if total is None else total + loss.detach()
+        if shs is not None and shs.grad is not None:
+            self.model._features_dc.grad += shs.grad[:, :1]
+            self.model._features_rest.grad += shs.grad[:, 1:]
         if self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(self.arena, op=dist.ReduceOp.SUM, group=self.pg)
