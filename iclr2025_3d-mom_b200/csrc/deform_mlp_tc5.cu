@@ -242,7 +242,231 @@ __global__ void __launch_bounds__(NT, 1) deform_mlp_fwd_tc5_kernel(const __grid_
     }
 }
 
-size_t fwd_smem(int F) { return (size_t)(2 * MW * F + 6 * MW * MW + 6 * 16 * MW + 4 * MW + 48) * sizeof(float) + 64; }
+// ---------------------------------------------------------------------------------------------
+// v2: same maths and TMEM / shared-memory operands as the kernel above, but pipelined inside a tile.
+//   * 256 threads: warp w reads / writes the TMEM lanes of quarter w & 3 (lane = point) and the 32-column
+//     half w >> 2 of every 64-wide accumulator, so each epilogue is half as long per thread;
+//   * every MMA group has its own mbarrier (one completion per tile, parity = tile parity), so several
+//     groups are in flight: the three heads' 64x64 layers are issued ahead of the epilogues
+//     (L2_0, L2_1 | L3_0, L2_2 | L3_1 | L3_2), the tensor pipe works through them while the threads
+//     run bias / ReLU / stash / split for the head before;
+//   * the next tile's feature rows and this tile's xyz / scales / rotations / scene_flow are fetched into
+//     registers while the first layer's MMAs run.
+// Requires all three heads enabled (the reference's configuration); otherwise the kernel above is used.
+// TMEM columns: A0 [0, 2F) feature hi|lo, then relu(hidden) hi [0,64) | lo [64,128); Z [128,256) relu(z) hi|lo
+// (F = 128: the feature lo half overlaps Z, it is dead once layer 1 has completed); D2 [256,448) the three
+// heads' accumulators (layer 1 accumulates into the first 64 of them); D3 [448,496) the head outputs.
+constexpr int NT2 = 256;
+
+__device__ __forceinline__ void stage_kmajor2(float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ w,
+                                              int N, int N_real, int K)
+{
+    for (int i = threadIdx.x; i < N * K; i += NT2) {
+        const int n = i / K, k = i - n * K;
+        const float v = n < N_real ? __ldg(w + (size_t)n * K + k) : 0.f;
+        const u32 h = to_tf32(v), l = to_tf32(v - __uint_as_float(h));
+        const int off = (k >> 2) * (N * 4) + n * 4 + (k & 3);
+        hi[off] = __uint_as_float(h);
+        lo[off] = __uint_as_float(l);
+    }
+}
+
+template <int F>
+__global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __grid_constant__ FwdArgs a)
+{
+    extern __shared__ __align__(1024) float smem[];
+    float* W1h = smem;                         // [F/4][64][4]
+    float* W1l = W1h + MW * F;
+    float* W2h = W1l + MW * F;                 // [3][16][64][4]
+    float* W2l = W2h + 3 * MW * MW;
+    float* W3h = W2l + 3 * MW * MW;            // [3][16][16][4]  (N padded to 16)
+    float* W3l = W3h + 3 * 16 * MW;
+    float* bias = W3l + 3 * 16 * MW;           // b1[64] b2[3][64] b3[3][16]
+    u64* bars = reinterpret_cast<u64*>(bias + 4 * MW + 48);     // [0] L1, [1..3] L2_h, [4..6] L3_h
+    u32* tmem_slot = reinterpret_cast<u32*>(bars + 7);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int pT = (warp & 3) * 32 + lane, cT = warp >> 2;
+    const int kdim[3] = {3, 3, 4};
+
+    stage_kmajor2(W1h, W1l, a.w.w1, MW, MW, F);
+    for (int i = tid; i < MW; i += NT2) bias[i] = __ldg(a.w.b1 + i);
+    for (int h = 0; h < 3; ++h) {
+        stage_kmajor2(W2h + h * MW * MW, W2l + h * MW * MW, a.w.w2[h], MW, MW, MW);
+        stage_kmajor2(W3h + h * 16 * MW, W3l + h * 16 * MW, a.w.w3[h], 16, kdim[h], MW);
+        for (int i = tid; i < MW; i += NT2) bias[MW + h * MW + i] = __ldg(a.w.b2[h] + i);
+        if (tid < 16) bias[4 * MW + h * 16 + tid] = tid < kdim[h] ? __ldg(a.w.b3[h] + tid) : 0.f;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 7; ++i) mbar_init(bars + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const u32 tbase = *tmem_slot;
+    const u32 lane_addr = tbase + ((u32)((warp & 3) * 32) << 16);
+    constexpr u32 C_H_HI = 0, C_H_LO = 64, C_FE_LO = F, C_Z_HI = 128, C_Z_LO = 192, C_D2 = 256, C_D3 = 448;
+    constexpr int FH = F / 2;                  // feature columns per thread
+    const u32 idesc64 = make_idesc(128, 64), idesc16 = make_idesc(128, 16);
+    u32 parity = 0;
+
+    auto sync_then = [&]() { tmem_wait_st(); tc_fence_before(); __syncthreads(); };
+    // epilogue of one 64-wide layer for this thread's 32 columns: bias, ReLU, stash, split; returns hi / lo in v / lo
+    auto layer_epilogue = [&](u32 d_col, const float* b, float* stash_row, bool valid, u32* v, u32* lo) {
+        tmem_ld32(lane_addr + d_col + 32 * cT, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(fmaxf(__uint_as_float(v[e]) + b[32 * cT + e], 0.f));
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                reinterpret_cast<float4*>(stash_row + 32 * cT)[j] =
+                    make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const float x = __uint_as_float(v[e]);
+            v[e] = to_tf32(x);
+            lo[e] = to_tf32(x - __uint_as_float(v[e]));
+        }
+    };
+
+    const long long nblocks = (a.P + ROWS - 1) / ROWS;
+    float4 fr[FH / 4];                          // this thread's half of its point's feature row
+    {
+        const long long r = (long long)blockIdx.x * ROWS + pT;
+#pragma unroll
+        for (int j = 0; j < FH / 4; ++j)
+            fr[j] = (blockIdx.x < nblocks && r < a.P) ? __ldg(reinterpret_cast<const float4*>(a.feat + (size_t)r * F + FH * cT) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const long long r = blk * ROWS + pT;
+        const bool valid = r < a.P;
+        // ---- features -> TMEM (hi | lo) ----
+#pragma unroll
+        for (int c = 0; c < FH / 32; ++c) {
+            u32 hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float x[4] = {fr[8 * c + j].x, fr[8 * c + j].y, fr[8 * c + j].z, fr[8 * c + j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { hi[4 * j + e] = to_tf32(x[e]); lo[4 * j + e] = to_tf32(x[e] - __uint_as_float(hi[4 * j + e])); }
+            }
+            tmem_st32(lane_addr + FH * cT + 32 * c, hi);
+            tmem_st32(lane_addr + C_FE_LO + FH * cT + 32 * c, lo);
+        }
+        sync_then();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer(tbase + C_D2, tbase, tbase + C_FE_LO, smem_u32(W1h), smem_u32(W1l), MW, F, idesc64);
+            tc_commit(bars + 0);
+        }
+        // while layer 1 runs: next tile's features, this tile's pass-through inputs
+        {
+            const long long rn = (blk + gridDim.x) * ROWS + pT;
+            const bool vn = blk + gridDim.x < nblocks && rn < a.P;
+#pragma unroll
+            for (int j = 0; j < FH / 4; ++j)
+                fr[j] = vn ? __ldg(reinterpret_cast<const float4*>(a.feat + (size_t)rn * F + FH * cT) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float in_x[3] = {0.f, 0.f, 0.f}, in_s[3] = {0.f, 0.f, 0.f}, in_r[4] = {0.f, 0.f, 0.f, 0.f}, in_f[3] = {0.f, 0.f, 0.f};
+        if (valid && cT == 0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                in_x[c] = __ldg(a.xyz + 3 * r + c); in_s[c] = __ldg(a.scales + 3 * r + c); in_f[c] = __ldg(a.scene_flow + 3 * r + c);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) in_r[c] = __ldg(a.rot + 4 * r + c);
+        }
+        u32 v[32], lo[32];
+        // ---- hidden ----
+        mbar_wait(bars + 0, parity);
+        tc_fence_after();
+        layer_epilogue(C_D2, bias, a.saved + (size_t)r * MW, valid, v, lo);
+        tmem_st32(lane_addr + C_H_HI + 32 * cT, v);
+        tmem_st32(lane_addr + C_H_LO + 32 * cT, lo);
+        sync_then();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer(tbase + C_D2, tbase + C_H_HI, tbase + C_H_LO, smem_u32(W2h), smem_u32(W2l), MW, MW, idesc64);
+            tc_commit(bars + 1);
+            issue_layer(tbase + C_D2 + 64, tbase + C_H_HI, tbase + C_H_LO, smem_u32(W2h + MW * MW), smem_u32(W2l + MW * MW), MW, MW, idesc64);
+            tc_commit(bars + 2);
+        }
+        // ---- heads ----
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+            mbar_wait(bars + 1 + h, parity);
+            tc_fence_after();
+            layer_epilogue(C_D2 + 64 * h, bias + MW + h * MW, a.saved + (size_t)(1 + h) * a.P * MW + (size_t)r * MW, valid, v, lo);
+            if (h > 0) {                         // the previous head's last layer still reads Z
+                mbar_wait(bars + 4 + (h - 1), parity);
+                tc_fence_after();
+            }
+            tmem_st32(lane_addr + C_Z_HI + 32 * cT, v);
+            tmem_st32(lane_addr + C_Z_LO + 32 * cT, lo);
+            sync_then();
+            if (tid == 0) {
+                tc_fence_after();
+                issue_layer(tbase + C_D3 + 16 * h, tbase + C_Z_HI, tbase + C_Z_LO, smem_u32(W3h + h * 16 * MW), smem_u32(W3l + h * 16 * MW), 16, MW, idesc16);
+                tc_commit(bars + 4 + h);
+                if (h == 0) {
+                    issue_layer(tbase + C_D2 + 128, tbase + C_H_HI, tbase + C_H_LO, smem_u32(W2h + 2 * MW * MW), smem_u32(W2l + 2 * MW * MW), MW, MW, idesc64);
+                    tc_commit(bars + 3);
+                }
+            }
+        }
+        // ---- outputs ----
+        mbar_wait(bars + 6, parity);
+        tc_fence_after();
+        if (cT == 0) {
+            u32 o[16];
+            const float fn = a.frame_num_dev ? __ldg(a.frame_num_dev) : a.frame_num;
+            tmem_ld16(lane_addr + C_D3, o);
+            tmem_wait_ld();
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float ov = __uint_as_float(o[c]) + bias[4 * MW + c];
+                    const float flow = __fmul_rn(a.delta_scale, __fmul_rn(fn, in_f[c]));
+                    a.pts_out[3 * r + c] = __fadd_rn(__fmul_rn(in_x[c], 1.0f), __fadd_rn(ov, flow));
+                }
+            }
+            tmem_ld16(lane_addr + C_D3 + 16, o);
+            tmem_wait_ld();
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    a.scales_out[3 * r + c] = __fadd_rn(__fmul_rn(in_s[c], 1.0f), __uint_as_float(o[c]) + bias[4 * MW + 16 + c]);
+            }
+            tmem_ld16(lane_addr + C_D3 + 32, o);
+            tmem_wait_ld();
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    a.rot_out[4 * r + c] = __fadd_rn(in_r[c], __uint_as_float(o[c]) + bias[4 * MW + 32 + c]);
+            }
+        }
+        parity ^= 1;
+        // the next tile's feature stores overwrite A0 / Z: every MMA of this tile has completed (bars[6] is the last
+        // commit), and its D3 reads above are ordered before the next tile's layer-3 MMAs by the syncs in between
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(512u) : "memory");
+    }
+}
+
+size_t fwd_smem(int F) { return (size_t)(2 * MW * F + 6 * MW * MW + 6 * 16 * MW + 4 * MW + 48) * sizeof(float) + 128; }
 
 }  // namespace tc5
 
@@ -258,6 +482,16 @@ int deform_mlp_forward_tc5(const b200gs_mlp_weights* w, long long P, const float
     const long long nblocks = (P + tc5::ROWS - 1) / tc5::ROWS;
     const int grid = (int)(nblocks < NUM_SMS ? nblocks : NUM_SMS);
     const size_t smem = tc5::fwd_smem(w->feat_dim);
+    if (w->w2[0] && w->w2[1] && w->w2[2]) {          // all heads on (the reference's configuration): pipelined kernel
+        if (w->feat_dim == 64) {
+            cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5v2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            tc5::deform_mlp_fwd_tc5v2_kernel<64><<<grid, tc5::NT2, smem, stream>>>(a);
+        } else {
+            cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5v2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            tc5::deform_mlp_fwd_tc5v2_kernel<128><<<grid, tc5::NT2, smem, stream>>>(a);
+        }
+        return check_launch("deform_mlp_forward(tcgen05 v2)");
+    }
     if (w->feat_dim == 64) {
         cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         tc5::deform_mlp_fwd_tc5_kernel<64><<<grid, tc5::NT, smem, stream>>>(a);
