@@ -19,7 +19,7 @@
 // ReLU'd activations the backward needs (4 x 256 B per point, plain row-major) leave the SM.
 // The backward accumulates all weight gradients in register fragments across every tile a
 // persistent CTA processes and flushes them with one atomic per element per CTA.
-#include "common.cuh"
+#include "tc5_common.cuh"
 #include "../../include/b200gs.h"
 
 namespace b200gs {
@@ -28,9 +28,10 @@ namespace {
 
 constexpr bool USE_TCGEN05_FORWARD = true;
 constexpr bool USE_TCGEN05_BACKWARD = true;     // F = 64 only; F = 128 keeps the mma.sync kernel below
-constexpr int MW = 64;             // net_width
+using tc5::MW;                     // net_width
+using tc5::stash_off; using tc5::stash_plane_floats;
 constexpr int MT = 256;            // threads per CTA (8 warps x 16 points)
-constexpr int ROWS = 128;          // points per CTA iteration
+using tc5::ROWS;                   // points per CTA iteration
 constexpr int LDS_T = MW + 8;      // row stride (floats) of the row-major smem tiles: conflict-free fragment loads
 
 __device__ __forceinline__ u32 to_tf32(float x) { u32 r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
@@ -153,8 +154,8 @@ __global__ void __launch_bounds__(MT, 1) deform_mlp_fwd_kernel(const __grid_cons
         for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) hC[nt][i] = fmaxf(hC[nt][i], 0.f);
-            if (v_lo) *reinterpret_cast<float2*>(a.saved + (size_t)r_lo * MW + 8 * nt + 2 * t) = make_float2(hC[nt][0], hC[nt][1]);
-            if (v_hi) *reinterpret_cast<float2*>(a.saved + (size_t)r_hi * MW + 8 * nt + 2 * t) = make_float2(hC[nt][2], hC[nt][3]);
+            if (v_lo) *reinterpret_cast<float2*>(a.saved + stash_off(r_lo, 8 * nt + 2 * t)) = make_float2(hC[nt][0], hC[nt][1]);
+            if (v_hi) *reinterpret_cast<float2*>(a.saved + stash_off(r_hi, 8 * nt + 2 * t)) = make_float2(hC[nt][2], hC[nt][3]);
         }
         // ---- heads ----
 #pragma unroll
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(MT, 1) deform_mlp_fwd_kernel(const __grid_cons
                 const float af[4] = {hC[j][0], hC[j][2], hC[j][1], hC[j][3]};
                 kstep<8>(zC, af, W2q + h * MW * RS2, RS2, j, g, t);
             }
-            float* sv = a.saved + (size_t)(1 + h) * a.P * MW;
+            float* sv = a.saved + (size_t)(1 + h) * stash_plane_floats(a.P);
             float oC[1][4];
             oC[0][0] = oC[0][2] = bias[4 * MW + h * 8 + 2 * t];
             oC[0][1] = oC[0][3] = bias[4 * MW + h * 8 + 2 * t + 1];
@@ -188,8 +189,8 @@ __global__ void __launch_bounds__(MT, 1) deform_mlp_fwd_kernel(const __grid_cons
             for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) zC[nt][i] = fmaxf(zC[nt][i], 0.f);
-                if (v_lo) *reinterpret_cast<float2*>(sv + (size_t)r_lo * MW + 8 * nt + 2 * t) = make_float2(zC[nt][0], zC[nt][1]);
-                if (v_hi) *reinterpret_cast<float2*>(sv + (size_t)r_hi * MW + 8 * nt + 2 * t) = make_float2(zC[nt][2], zC[nt][3]);
+                if (v_lo) *reinterpret_cast<float2*>(sv + stash_off(r_lo, 8 * nt + 2 * t)) = make_float2(zC[nt][0], zC[nt][1]);
+                if (v_hi) *reinterpret_cast<float2*>(sv + stash_off(r_hi, 8 * nt + 2 * t)) = make_float2(zC[nt][2], zC[nt][3]);
                 const float af[4] = {zC[nt][0], zC[nt][2], zC[nt][1], zC[nt][3]};
                 kstep<1>(oC, af, W3q + h * 8 * RS2, RS2, nt, g, t);
             }
@@ -234,7 +235,7 @@ struct BwdArgs {
 // rows accumulated in FP32: dY is kept exact (hi + lo split, 2 MMAs), X is rounded to TF32 once
 // (relative 2^-12 per term, random sign), well inside the 1e-3 gradient tolerance; the full 3-pass
 // split is kept for the dX chain, whose errors would compound through the layers.
-template <int NT>
+template <int NT, bool TILED>
 __device__ __forceinline__ void dw_accumulate(float (*acc)[4], const float* __restrict__ dYs, int mt,
                                               const float* __restrict__ X, size_t ldx, long long row0, long long P,
                                               int nt0, int g, int t)
@@ -246,8 +247,8 @@ __device__ __forceinline__ void dw_accumulate(float (*acc)[4], const float* __re
         float x0[NT], x1[NT];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-            x0[nt] = v0 ? __ldg(X + (size_t)(row0 + r0) * ldx + 8 * (nt0 + nt) + g) : 0.f;
-            x1[nt] = v1 ? __ldg(X + (size_t)(row0 + r1) * ldx + 8 * (nt0 + nt) + g) : 0.f;
+            x0[nt] = v0 ? __ldg(X + (TILED ? stash_off(row0 + r0, 8 * (nt0 + nt) + g) : (size_t)(row0 + r0) * ldx + 8 * (nt0 + nt) + g)) : 0.f;
+            x1[nt] = v1 ? __ldg(X + (TILED ? stash_off(row0 + r1, 8 * (nt0 + nt) + g) : (size_t)(row0 + r1) * ldx + 8 * (nt0 + nt) + g)) : 0.f;
         }
         const float af[4] = {dYs[r0 * LDS_T + 16 * mt + g], dYs[r0 * LDS_T + 16 * mt + g + 8],
                              dYs[r1 * LDS_T + 16 * mt + g], dYs[r1 * LDS_T + 16 * mt + g + 8]};
@@ -324,8 +325,8 @@ __global__ void __launch_bounds__(MT, 1) deform_mlp_bwd_kernel(const __grid_cons
         float hC[8][4], dRh[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            const float2 x = v_lo ? __ldg(reinterpret_cast<const float2*>(a.saved + (size_t)r_lo * MW + 8 * nt + 2 * t)) : make_float2(0.f, 0.f);
-            const float2 y = v_hi ? __ldg(reinterpret_cast<const float2*>(a.saved + (size_t)r_hi * MW + 8 * nt + 2 * t)) : make_float2(0.f, 0.f);
+            const float2 x = v_lo ? __ldg(reinterpret_cast<const float2*>(a.saved + stash_off(r_lo, 8 * nt + 2 * t))) : make_float2(0.f, 0.f);
+            const float2 y = v_hi ? __ldg(reinterpret_cast<const float2*>(a.saved + stash_off(r_hi, 8 * nt + 2 * t))) : make_float2(0.f, 0.f);
             hC[nt][0] = x.x; hC[nt][1] = x.y; hC[nt][2] = y.x; hC[nt][3] = y.y;
 #pragma unroll
             for (int i = 0; i < 4; ++i) dRh[nt][i] = 0.f;
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(MT, 1) deform_mlp_bwd_kernel(const __grid_cons
             if (!a.w.w2[h]) continue;
             const int kd = kdim[h];
             const float* dsrc = h == 0 ? a.d_pts : (h == 1 ? a.d_scales : a.d_rot);
-            const float* zsv = a.saved + (size_t)(1 + h) * a.P * MW;
+            const float* zsv = a.saved + (size_t)(1 + h) * stash_plane_floats(a.P);
             const float4* W2h = W2b + (RESIDENT ? h : 0) * MW * RS2;
             if (!RESIDENT) {            // every warp is past the previous head's use of the slot (trailing barrier below)
                 stage_weight(W2b, a.w.w2[h], MW, MW, MW, MW, MW, 1);
@@ -361,8 +362,8 @@ __global__ void __launch_bounds__(MT, 1) deform_mlp_bwd_kernel(const __grid_cons
             kstep<8>(dz, df, W3b + h * MW * RS3, RS3, 0, g, t);
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
-                const float2 x = v_lo ? __ldg(reinterpret_cast<const float2*>(zsv + (size_t)r_lo * MW + 8 * nt + 2 * t)) : make_float2(0.f, 0.f);
-                const float2 y = v_hi ? __ldg(reinterpret_cast<const float2*>(zsv + (size_t)r_hi * MW + 8 * nt + 2 * t)) : make_float2(0.f, 0.f);
+                const float2 x = v_lo ? __ldg(reinterpret_cast<const float2*>(zsv + stash_off(r_lo, 8 * nt + 2 * t))) : make_float2(0.f, 0.f);
+                const float2 y = v_hi ? __ldg(reinterpret_cast<const float2*>(zsv + stash_off(r_hi, 8 * nt + 2 * t))) : make_float2(0.f, 0.f);
                 dz[nt][0] = x.x > 0.f ? dz[nt][0] : 0.f; dz[nt][1] = x.y > 0.f ? dz[nt][1] : 0.f;
                 dz[nt][2] = y.x > 0.f ? dz[nt][2] : 0.f; dz[nt][3] = y.y > 0.f ? dz[nt][3] : 0.f;
                 *reinterpret_cast<float2*>(Ds + lr_lo * LDS_T + 8 * nt + 2 * t) = make_float2(dz[nt][0], dz[nt][1]);
@@ -375,13 +376,13 @@ __global__ void __launch_bounds__(MT, 1) deform_mlp_bwd_kernel(const __grid_cons
                 kstep<8>(dRh, af, W2h, RS2, j, g, t);
             }
             __syncthreads();                                             // dz and d_out tiles complete
-            dw_accumulate<4>(gW2[h], Ds, mt, a.saved, MW, row0, a.P, ntb, g, t);            // dW2 += dz^T relu(h)
+            dw_accumulate<4, true>(gW2[h], Ds, mt, a.saved, MW, row0, a.P, ntb, g, t);            // dW2 += dz^T relu(h)
             // dW3 (out padded to one 16-row m-tile; n-tile `warp` of the 64 in-features) += d_out^T relu(z)
 #pragma unroll 4
             for (int ks = 0; ks < ROWS / 8; ++ks) {
                 const int r0 = 8 * ks + t, r1 = r0 + 4;
-                const float x0 = row0 + r0 < a.P ? __ldg(zsv + (size_t)(row0 + r0) * MW + 8 * warp + g) : 0.f;
-                const float x1 = row0 + r1 < a.P ? __ldg(zsv + (size_t)(row0 + r1) * MW + 8 * warp + g) : 0.f;
+                const float x0 = row0 + r0 < a.P ? __ldg(zsv + stash_off(row0 + r0, 8 * warp + g)) : 0.f;
+                const float x1 = row0 + r1 < a.P ? __ldg(zsv + stash_off(row0 + r1, 8 * warp + g)) : 0.f;
                 u32 ahi[4] = {0u, 0u, 0u, 0u}, alo[4] = {0u, 0u, 0u, 0u};      // rows g+8 of the m-tile are padding
                 split(Dout[r0 * 8 + g], ahi[0], alo[0]);
                 split(Dout[r1 * 8 + g], ahi[2], alo[2]);
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(MT, 1) deform_mlp_bwd_kernel(const __grid_cons
             }
         }
         __syncthreads();
-        dw_accumulate<NT1 / 2>(gW1, Ds, mt, a.feat, F, row0, a.P, (warp & 1) * (NT1 / 2), g, t);     // dW1 += dh^T feature
+        dw_accumulate<NT1 / 2, false>(gW1, Ds, mt, a.feat, F, row0, a.P, (warp & 1) * (NT1 / 2), g, t);     // dW1 += dh^T feature
         if (tid < MW) {
             float s = 0.f;
 #pragma unroll 8
@@ -506,7 +507,7 @@ using namespace b200gs;
 
 extern "C" {
 
-size_t b200gs_deform_mlp_saved_floats(long long P) { return P > 0 ? (size_t)4 * (size_t)P * MW : 0; }
+size_t b200gs_deform_mlp_saved_floats(long long P) { return P > 0 ? 4 * stash_plane_floats(P) : 0; }
 
 int b200gs_deform_mlp_forward(const b200gs_mlp_weights* w, long long P, const float* feat, const float* xyz,
                               const float* scales, const float* rot, const float* scene_flow, float frame_num,

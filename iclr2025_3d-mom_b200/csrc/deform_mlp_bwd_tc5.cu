@@ -164,13 +164,20 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
     // MMA drain + shared-memory stores of the phase before.
     const bool en0 = a.w.w2[0] != nullptr, en1 = a.w.w2[1] != nullptr, en2 = a.w.w2[2] != nullptr;
     auto next_phase = [&](int ph) { return (ph < 0 && en0) ? 0 : (ph < 1 && en1) ? 1 : (ph < 2 && en2) ? 2 : 3; };
-    auto load_rows = [&](float4* x, const float* src, long long r0) {
+    auto load_rows = [&](float4* x, const float* src, long long r0) {          // row-major [P][64] (features)
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             x[i] = r0 + 4 * i < a.P ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(r0 + 4 * i) * MW + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
+    auto load_stash = [&](float4* x, int plane, long long r0) {                  // tiled stash plane, see stash_off
+        // r0 = tile * 128 + 32 pg + sub: the 8 rows r0 + 4 i are the same slot of 8 consecutive 4-point groups
+        const float* src = a.saved + (size_t)plane * stash_plane_floats(a.P) + stash_off(r0, col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            x[i] = r0 + 4 * i < a.P ? __ldg(reinterpret_cast<const float4*>(src + 256 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
     auto load_phase_rows = [&](int ph, float4* x, long long r0) {
-        load_rows(x, ph >= 3 ? a.feat : a.saved + (size_t)(1 + ph) * a.P * MW, r0);
+        if (ph >= 3) load_rows(x, a.feat, r0); else load_stash(x, 1 + ph, r0);
     };
     auto load_phase_dout = [&](int ph, float (*d)[4], long long r0) {
         if (ph >= 3) return;
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
     const long long nblocks = (a.P + ROWS - 1) / ROWS;
     float4 hrow[8], xin[8];
     if ((long long)blockIdx.x < nblocks) {
-        load_rows(hrow, a.saved, (long long)blockIdx.x * ROWS + p0);
+        load_stash(hrow, 0, (long long)blockIdx.x * ROWS + p0);
         load_phase_rows(next_phase(-1), xin, (long long)blockIdx.x * ROWS + p0);
     }
     for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
@@ -275,7 +282,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
 #pragma unroll
         for (int i = 0; i < 8; ++i) frow[i] = xin[i];
         if (blk + gridDim.x < nblocks) {                              // next tile: relu(hidden) rows and the first phase's inputs
-            load_rows(hrow, a.saved, (blk + gridDim.x) * ROWS + p0);
+            load_stash(hrow, 0, (blk + gridDim.x) * ROWS + p0);
             load_phase_rows(next_phase(-1), xin, (blk + gridDim.x) * ROWS + p0);
         }
         drain();

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(NT, 1) deform_mlp_fwd_tc5_kernel(const __grid_
             if (valid) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                    reinterpret_cast<float4*>(a.saved + (size_t)r * MW + 32 * c)[q] =
+                    *reinterpret_cast<float4*>(a.saved + stash_off(r, 32 * c + 4 * q)) =
                         make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
             }
 #pragma unroll
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(NT, 1) deform_mlp_fwd_tc5_kernel(const __grid_
             }
             mbar_wait(bar, phase); phase ^= 1;
             tc_fence_after();
-            float* sv = a.saved + (size_t)(1 + h) * a.P * MW;
+            float* sv = a.saved + (size_t)(1 + h) * stash_plane_floats(a.P);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 u32 v[32], lo[32];
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(NT, 1) deform_mlp_fwd_tc5_kernel(const __grid_
                 if (valid) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
-                        reinterpret_cast<float4*>(sv + (size_t)r * MW + 32 * c)[q] =
+                        *reinterpret_cast<float4*>(sv + stash_off(r, 32 * c + 4 * q)) =
                             make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
                 }
 #pragma unroll
@@ -317,15 +317,16 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
 
     auto sync_then = [&]() { tmem_wait_st(); tc_fence_before(); __syncthreads(); };
     // epilogue of one 64-wide layer for this thread's 32 columns: bias, ReLU, stash, split; returns hi / lo in v / lo
-    auto layer_epilogue = [&](u32 d_col, const float* b, float* stash_row, bool valid, u32* v, u32* lo) {
+    auto layer_epilogue = [&](u32 d_col, const float* b, float* stash_plane, long long row, bool valid, u32* v, u32* lo) {
         tmem_ld32(lane_addr + d_col + 32 * cT, v);
         tmem_wait_ld();
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(fmaxf(__uint_as_float(v[e]) + b[32 * cT + e], 0.f));
         if (valid) {
+            float* dst = stash_plane + stash_off(row, 32 * cT);          // this thread's 8 chunks are 16 floats apart
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                reinterpret_cast<float4*>(stash_row + 32 * cT)[j] =
+                *reinterpret_cast<float4*>(dst + 16 * j) =
                     make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         }
 #pragma unroll
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
         // ---- hidden ----
         mbar_wait(bars + 0, parity);
         tc_fence_after();
-        layer_epilogue(C_D2, bias, a.saved + (size_t)r * MW, valid, v, lo);
+        layer_epilogue(C_D2, bias, a.saved, r, valid, v, lo);
         tmem_st32(lane_addr + C_H_HI + 32 * cT, v);
         tmem_st32(lane_addr + C_H_LO + 32 * cT, lo);
         sync_then();
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
         for (int h = 0; h < 3; ++h) {
             mbar_wait(bars + 1 + h, parity);
             tc_fence_after();
-            layer_epilogue(C_D2 + 64 * h, bias + MW + h * MW, a.saved + (size_t)(1 + h) * a.P * MW + (size_t)r * MW, valid, v, lo);
+            layer_epilogue(C_D2 + 64 * h, bias + MW + h * MW, a.saved + (size_t)(1 + h) * stash_plane_floats(a.P), r, valid, v, lo);
             if (h > 0) {                         // the previous head's last layer still reads Z
                 mbar_wait(bars + 4 + (h - 1), parity);
                 tc_fence_after();

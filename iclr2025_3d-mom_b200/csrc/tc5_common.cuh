@@ -8,6 +8,16 @@ namespace tc5 {
 constexpr int MW = 64;
 constexpr int ROWS = 128;
 
+// Activation stash layout (forward -> backward, opaque to callers): 4 planes (relu(hidden), relu(z_pos),
+// relu(z_scale), relu(z_rot)) of ceil(P/128) tiles; a tile is [32 groups of 4 points][16 column chunks][4 points]
+// [4 floats].  The backward reads 8 chunks x 4 points per warp instruction = one contiguous 512-byte run; the
+// forward (one lane per point) writes 64-byte runs, 8 lines per instruction instead of the 32 of a row-major stash.
+__host__ __device__ __forceinline__ size_t stash_plane_floats(long long P) { return (size_t)((P + ROWS - 1) / ROWS) * ROWS * MW; }
+__host__ __device__ __forceinline__ size_t stash_off(long long row, int col)
+{
+    return (size_t)(row >> 7) * (ROWS * MW) + (size_t)((row & 127) >> 2) * 256 + (size_t)(col >> 2) * 16 + (size_t)(row & 3) * 4 + (col & 3);
+}
+
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ u32 to_tf32(float x) { u32 r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
 
