@@ -21,6 +21,7 @@ import types
 import torch
 import torch.nn as nn
 
+from . import fusedops
 from .adam import FusedAdam
 from .field import deform_network
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
@@ -118,9 +119,10 @@ def render(cam, pc, bg_color, scaling_modifier=1.0, stage="fine", delta_scale=1,
         time = torch.full((means3D.shape[0], 1), float(cam.time), device=means3D.device)
         m3, sc, rt, op, sh = pc._deformation(means3D, scales, rotations, opacity, shs, time, pc.get_flow,
                                              cam.frame_num, delta_scale)
-    sc = pc.scaling_activation(sc)
-    rt = pc.rotation_activation(rt)
-    op = pc.opacity_activation(op)
+    if sc.is_cuda:
+        sc, rt, op = fusedops.activations(sc, rt, op)      # exp / F.normalize / sigmoid in one launch each way
+    else:                                                   # CPU tensors only reach here from the gloo plumbing test
+        sc = pc.scaling_activation(sc); rt = pc.rotation_activation(rt); op = pc.opacity_activation(op)
     image, radii, depth = rasterizer(means3D=m3, means2D=screenspace_points, shs=sh, colors_precomp=None,
                                      opacities=op, scales=sc, rotations=rt, cov3D_precomp=None)
     return {"render": image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii,
@@ -197,16 +199,31 @@ class ViewParallelTrainer:
             # as a leaf, let the views' SH gradients accumulate in it, and split them back after the last view
             m = self.model
             shs = torch.cat((m._features_dc, m._features_rest), dim=1).detach().requires_grad_(True)
+        from . import field as _field
         for cam, gt in zip(cams, gts):
             pkg = self.render_fn(cam, self.model, self.bg, self.stage, shs) if self.shared_shs else \
                 self.render_fn(cam, self.model, self.bg, self.stage)
-            loss = (pkg["render"] - gt).abs().mean() / B
-            loss.backward()
+            _field.ACCUMULATE_INTO_GRAD = self.shared_shs     # p.grad are arena views: let the field kernels add into them
+            try:
+                if self.shared_shs:
+                    # fused L1 (utils/loss_utils.py:23-24) + its gradient, then backward from the image
+                    if total is None:
+                        total = torch.zeros(1, device=gt.device)
+                    img = pkg["render"]
+                    d_img = fusedops.l1_loss_and_grad(img, gt, 1.0 / (img.numel() * B), total)
+                    img.backward(d_img)
+                    loss = None
+                else:
+                    loss = (pkg["render"] - gt).abs().mean() / B
+                    loss.backward()
+            finally:
+                _field.ACCUMULATE_INTO_GRAD = False
             vg = pkg["viewspace_points"].grad
             if vg is not None:
                 self.viewspace_grad += vg
             torch.maximum(self.max_radii, pkg["radii"], out=self.max_radii)
-            total = loss.detach() if total is None else total + loss.detach()
+            if loss is not None:
+                total = loss.detach() if total is None else total + loss.detach()
         if shs is not None and shs.grad is not None:
             self.model._features_dc.grad += shs.grad[:, :1]
             self.model._features_rest.grad += shs.grad[:, 1:]
@@ -215,4 +232,4 @@ class ViewParallelTrainer:
             dist.all_reduce(self.arena, op=dist.ReduceOp.SUM, group=self.pg)
             dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=self.pg)
         self.model.optimizer.step()
-        return total
+        return total.reshape(()) if total is not None else total

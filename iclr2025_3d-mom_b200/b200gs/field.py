@@ -169,6 +169,21 @@ class _HexPlaneFn(torch.autograd.Function):
         return (d_pts, None, None, None, None, *grads)
 
 
+# When True (set by b200gs.engine.ViewParallelTrainer around its views), the backward kernels accumulate the
+# weight / plane gradients straight into the parameters' existing `.grad` buffers (the kernels add atomically
+# anyway) and autograd gets None for them: per view this saves a zero-fill plus an accumulation pass for each of
+# the 26 field parameters. Off by default, so under the reference's own scripts autograd sees ordinary gradients.
+ACCUMULATE_INTO_GRAD = False
+
+
+def _grad_target(param):
+    g = param.grad
+    if ACCUMULATE_INTO_GRAD and g is not None and g.dtype == torch.float32 and g.shape == param.shape \
+            and g.stride() == param.stride() and g.device == param.device:
+        return g
+    return None
+
+
 class _DeformFn(torch.autograd.Function):
     """(pts, scales, rot) = field(xyz, scales, rot, t, scene_flow, frame_num, delta_scale).
 
@@ -210,6 +225,7 @@ class _DeformFn(torch.autograd.Function):
         ctx.save_for_backward(xyz, tt if tt is not None else torch.empty(0), aabb, feat, saved,
                               *[w if w is not None else torch.empty(0) for w in weights], *planes)
         ctx.meta = (levels, res, heads, ts, tt is not None)
+        ctx.params = (weights, planes)          # the Parameter objects themselves (for _grad_target)
         return pts_o, scales_o, rot_o
 
     @staticmethod
@@ -236,7 +252,10 @@ class _DeformFn(torch.autograd.Function):
         P = int(xyz.shape[0])
         stream = current_stream()
         mw = _DeformFn._weights_struct(weights, heads, 32 * levels)
-        gws = [torch.zeros_like(w) if w.numel() else None for w in weights]
+        pw, pp = ctx.params
+        direct_w = [_grad_target(q) if q is not None else None for q in pw]
+        direct_p = [_grad_target(q) for q in pp]
+        gws = [(dw if dw is not None else torch.zeros_like(w)) if w.numel() else None for w, dw in zip(weights, direct_w)]
         mg = _MlpGrads()
         mg.w1 = gws[0].data_ptr(); mg.b1 = gws[1].data_ptr()
         for h in range(3):
@@ -248,7 +267,7 @@ class _DeformFn(torch.autograd.Function):
         check(L.b200gs_deform_mlp_backward(ctypes.byref(mw), ctypes.byref(mg), P, feat.data_ptr(), saved.data_ptr(),
                                            cp(d_pts) if heads[0] else None, cp(d_scales) if heads[1] else None,
                                            cp(d_rot) if heads[2] else None, d_feat.data_ptr(), stream), "deform_mlp_backward")
-        gplanes = [torch.zeros_like(p, memory_format=torch.preserve_format) for p in planes]
+        gplanes = [dp if dp is not None else torch.zeros_like(p, memory_format=torch.preserve_format) for p, dp in zip(planes, direct_p)]
         d_xyz_grid = torch.empty_like(xyz)
         d = _hex_desc(aabb, planes, levels, res, gplanes)
         check(L.b200gs_hexplane_backward(ctypes.byref(d), P, xyz.data_ptr(), _optr(ctx.order),
@@ -256,12 +275,13 @@ class _DeformFn(torch.autograd.Function):
                                          stream), "hexplane_backward")
         # pts = xyz*1 + ..., scales = scales*1 + ds, rot = rot + dr: identity paths
         d_xyz = d_xyz_grid + d_pts if d_pts is not None else d_xyz_grid
-        gw_out = [g if (g is not None) else None for g in gws]
+        gw_out = [None if dw is not None else g for g, dw in zip(gws, direct_w)]      # accumulated in place -> nothing for autograd
         for h in range(3):
             if not heads[h]:
                 for i in range(2 + 4 * h, 6 + 4 * h):
                     gw_out[i] = None
-        return (d_xyz, d_scales, d_rot, None, None, None, None, None, None, None, None, *gw_out, *gplanes)
+        gp_out = [None if dp is not None else g for g, dp in zip(gplanes, direct_p)]
+        return (d_xyz, d_scales, d_rot, None, None, None, None, None, None, None, None, *gw_out, *gp_out)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1,0 +1,70 @@
+"""Fused elementwise pieces of the training loop (csrc/elementwise.cu) for b200gs.engine.
+
+The reference spells these with stock PyTorch ops inside code that runs unchanged on top of the
+drop-ins (gaussian_renderer/__init__.py:130-132 activations; utils/loss_utils.py:23-24 L1), so they
+stay PyTorch there. Our own trainer (`engine.render` / `ViewParallelTrainer`) calls these instead:
+one launch each way for exp / normalize / sigmoid, one launch for the loss and its gradient.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, current_stream
+
+_P = ctypes.c_void_p
+_lib.register("b200gs_activations_forward", ctypes.c_int, [ctypes.c_longlong, _P, _P, _P, _P, _P, _P, _P])
+_lib.register("b200gs_activations_backward", ctypes.c_int, [ctypes.c_longlong] + [_P] * 10)
+_lib.register("b200gs_l1_loss_fwd_bwd", ctypes.c_int, [ctypes.c_longlong, _P, _P, ctypes.c_float, _P, _P, _P])
+
+
+def _req(t, shape_tail):
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise RuntimeError("fused activations need float32 CUDA tensors (there is no CPU path)")
+    if t.dim() != 2 or t.shape[1] != shape_tail:
+        raise RuntimeError(f"expected a [P,{shape_tail}] tensor, got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+class _Activations(torch.autograd.Function):
+    """(exp(scales), F.normalize(rotations), sigmoid(opacity)) — scene/gaussian_model.py:37-47."""
+
+    @staticmethod
+    def forward(ctx, scales, rotations, opacity):
+        s, r, o = _req(scales, 3), _req(rotations, 4), _req(opacity, 1)
+        P = int(s.shape[0])
+        so, ro, oo = torch.empty_like(s), torch.empty_like(r), torch.empty_like(o)
+        check(_lib.lib().b200gs_activations_forward(P, s.data_ptr(), r.data_ptr(), o.data_ptr(), so.data_ptr(), ro.data_ptr(),
+                                                    oo.data_ptr(), current_stream()), "activations_forward")
+        ctx.save_for_backward(so, r, oo)
+        return so, ro, oo
+
+    @staticmethod
+    def backward(ctx, gs, gr, go):
+        so, r, oo = ctx.saved_tensors
+        P = int(so.shape[0])
+        need = ctx.needs_input_grad
+        ds = torch.empty_like(so) if need[0] else None
+        dr = torch.empty_like(r) if need[1] else None
+        do = torch.empty_like(oo) if need[2] else None
+        p = lambda t: t.contiguous().data_ptr() if t is not None else None
+        check(_lib.lib().b200gs_activations_backward(P, so.data_ptr(), r.data_ptr(), oo.data_ptr(), p(gs), p(gr), p(go),
+                                                     p(ds), p(dr), p(do), current_stream()), "activations_backward")
+        return ds, dr, do
+
+
+def activations(scales, rotations, opacity):
+    return _Activations.apply(scales, rotations, opacity)
+
+
+def l1_loss_and_grad(render, target, scale, loss_accum):
+    """loss_accum[0] += scale * sum|render - target|; returns d(loss)/d(render) (= scale * sign)."""
+    if not (render.is_cuda and target.is_cuda and render.dtype == torch.float32 and target.dtype == torch.float32):
+        raise RuntimeError("l1_loss_and_grad needs float32 CUDA tensors (there is no CPU path)")
+    if render.shape != target.shape:
+        raise RuntimeError("render / target shape mismatch")
+    r, t = render.detach().contiguous(), target.contiguous()
+    d = torch.empty_like(r)
+    check(_lib.lib().b200gs_l1_loss_fwd_bwd(r.numel(), r.data_ptr(), t.data_ptr(), float(scale), loss_accum.data_ptr(), d.data_ptr(),
+                                            current_stream()), "l1_loss")
+    return d

@@ -200,6 +200,22 @@ int b200gs_deform_mlp_backward(const b200gs_mlp_weights* w /* host */, const b20
                                long long P, const float* features, const float* saved, const float* d_pts,
                                const float* d_scales, const float* d_rot, float* d_features, b200gs_stream_t stream);
 
+/* ---- fused elementwise pieces of the training loop ------------------------------------------------
+ * activations: scales = exp(s), rotations = F.normalize(r) (x / max(||x||, 1e-12)), opacity = sigmoid(o)
+ * (gaussian_renderer/__init__.py:130-132; scene/gaussian_model.py:37-47). [P,3] / [P,4] / [P,1] FP32.
+ * The backward takes the forward's OUTPUTS for exp / sigmoid and the raw quaternion; null upstream gradients
+ * count as zero, null outputs are skipped. */
+int b200gs_activations_forward(long long P, const float* scales_raw, const float* rot_raw, const float* opacity_raw,
+                               float* scales_out, float* rot_out, float* opacity_out, b200gs_stream_t stream);
+int b200gs_activations_backward(long long P, const float* scales_out, const float* rot_raw, const float* opacity_out,
+                                const float* d_scales_out, const float* d_rot_out, const float* d_opacity_out,
+                                float* d_scales_raw, float* d_rot_raw, float* d_opacity_raw, b200gs_stream_t stream);
+/* L1 loss of utils/loss_utils.py:23-24 with its gradient in one pass: loss_accum[0] += scale * sum |render - target|,
+ * d_render[i] = scale * sign(render[i] - target[i]) (d_render may be null). scale = 1 / (n * batch) gives the
+ * per-view share of train_4DGS.py:205-210's batch-mean L1. loss_accum is a device float the caller zeroes. */
+int b200gs_l1_loss_fwd_bwd(long long n, const float* render, const float* target, float scale, float* loss_accum, float* d_render,
+                           b200gs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,54 @@
+"""GPU parity of the fused elementwise kernels against the PyTorch ops the reference uses:
+exp / F.normalize / sigmoid (gaussian_renderer/__init__.py:130-132) forward + backward, and
+l1_loss (utils/loss_utils.py:23-24) with its gradient. Tolerance: 2e-6 relative (same FP32 formulas,
+different instruction order); the loss sum is accumulated in a different order (1e-5)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+@pytest.mark.parametrize("P", [1, 257, 100003])
+def test_activations_forward_backward(P):
+    from b200gs import fusedops
+    g = torch.Generator().manual_seed(P)
+    s = (torch.randn(P, 3, generator=g) * 0.6 - 5).cuda()
+    r = torch.randn(P, 4, generator=g).cuda()
+    o = (torch.randn(P, 1, generator=g) * 1.5).cuda()
+    if P > 2:
+        r[1] = 0.0                       # zero quaternion: the eps clamp of F.normalize is active
+    a = [t.clone().requires_grad_(True) for t in (s, r, o)]
+    b = [t.clone().requires_grad_(True) for t in (s, r, o)]
+    so, ro, oo = fusedops.activations(*a)
+    rs, rr, ropa = torch.exp(b[0]), torch.nn.functional.normalize(b[1]), torch.sigmoid(b[2])
+    assert _rel(so, rs) < 2e-6 and _rel(ro, rr) < 2e-6 and _rel(oo, ropa) < 2e-6
+    ws, wr, wo = torch.randn(P, 3, generator=g).cuda(), torch.randn(P, 4, generator=g).cuda(), torch.randn(P, 1, generator=g).cuda()
+    ((so * ws).sum() + (ro * wr).sum() + (oo * wo).sum()).backward()
+    ((rs * ws).sum() + (rr * wr).sum() + (ropa * wo).sum()).backward()
+    live = torch.ones(P, dtype=torch.bool, device="cuda")
+    if P > 2:
+        live[1] = False                  # d normalize at exactly 0 is 1e12 * g in both; compare separately
+        assert torch.allclose(a[1].grad[1], b[1].grad[1], rtol=1e-5)
+    for x, y in zip(a, b):
+        assert _rel(x.grad[live], y.grad[live]) < 2e-6
+
+
+@pytest.mark.parametrize("shape", [(3, 720, 1280), (3, 5, 7)])
+def test_l1_loss_and_grad(shape):
+    from b200gs import fusedops
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand(*shape, generator=g).cuda().requires_grad_(True)
+    gt = torch.rand(*shape, generator=g).cuda()
+    with torch.no_grad():
+        gt.view(-1)[:3] = img.view(-1)[:3]          # exact ties: sign(0) = 0
+    B = 8
+    acc = torch.zeros(1, device="cuda")
+    d = fusedops.l1_loss_and_grad(img, gt, 1.0 / (img.numel() * B), acc)
+    ref = (img - gt).abs().mean() / B
+    ref.backward()
+    assert abs(acc.item() - ref.item()) < 1e-5 * ref.item()
+    assert torch.equal(d, img.grad)
