@@ -93,6 +93,15 @@ class ClockSampler:
                 "samples": len(self.rows), "reasons": sorted(reasons)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+NCU_TRAFFIC = {"hexplane_bwd_kernel": 351.5e6, "deform_mlp_bwd_tc5_kernel": 1563.8e6, "deform_mlp_fwd_tc5v2_kernel": 1320.4e6}
+ROOFLINE_NOTES = {
+    "hexplane_bwd_kernel": "algorithmic HBM bytes only (xyz, order, d_feature in; d_xyz, plane gradients out); the 12.3 KB/point of "
+                           "plane texel gathers + vector REDs are served by L1/L2 (planes are 11.6 MB), which is what bounds this kernel",
+    "hexplane_fwd_kernel": "plane texel gathers (6.1 KB/point) are L1/L2 traffic, not HBM",
+}
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -348,20 +357,28 @@ def _main():
             return float(t[0])
         return ms
 
-    # Adam launch timing (the dominant HBM-bound kernel) is taken inside the timed steps
-    adam_ms, adam_launches = [], 0
+    # Per-entry-point device timing (CUDA events on the launching stream) is taken INSIDE the timed steps:
+    # our arm through b200gs._lib.CallTimer, the reference arm for its optimiser step only.
+    adam_ms = []
     opt_step = model.optimizer.step
-
-    def timed_opt_step(*a, **k):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); r = opt_step(*a, **k); e1.record()
-        adam_ms.append((e0, e1))
-        return r
-    model.optimizer.step = timed_opt_step
+    timer = None
+    if impl == "b200":
+        from b200gs import _lib as _b200lib
+        timer = _b200lib.CallTimer()
+        timer.__enter__()
+    else:
+        def timed_opt_step(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = opt_step(*a, **k); e1.record()
+            adam_ms.append((e0, e1))
+            return r
+        model.optimizer.step = timed_opt_step
 
     for _ in range(max(args.warmup, 3)):
         trainer.step(cams, gts_dev, global_batch=n_global)
     adam_ms.clear()
+    if timer:
+        timer.reset()
     barrier()
     with ClockSampler(local) as clk:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -371,7 +388,12 @@ def _main():
         e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
-        adam_t = sum(a.elapsed_time(b) for a, b in adam_ms) / max(len(adam_ms), 1)
+        calls = timer.summary() if timer else {}
+        if timer:
+            timer.__exit__()
+            adam_t = calls.get("b200gs_adam_multi", {}).get("ms_avg", 0.0)
+        else:
+            adam_t = sum(a.elapsed_time(b) for a, b in adam_ms) / max(len(adam_ms), 1)
         # end to end: ground truth in pinned host memory, copied per view inside the timed region; loss read back
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -385,7 +407,8 @@ def _main():
         barrier()
         ms_e2e = max_over_ranks(f0.elapsed_time(f1))
         wall_e2e = time.perf_counter() - t_wall
-    model.optimizer.step = opt_step
+    if not timer:
+        model.optimizer.step = opt_step
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
@@ -399,13 +422,37 @@ def _main():
     n_params = sum(p.numel() for p in trainer.trainable)
     adam_bytes = 28.0 * n_params                                   # p, m, v read+written, g read
     adam_gbs = adam_bytes / (adam_t * 1e-3) / 1e9 if adam_t > 0 else None
+    hbm = pk.get("hbm_gbs")
+    P_, F_ = args.points, 64
+    plane_params = sum(p.numel() for n, p in model.named_parameters() if ".grids." in n)
+    # algorithmic HBM bytes per launch: what each kernel must move when every
+    # re-used operand (planes, weights) stays on chip
+    model_bytes = {
+        "b200gs_adam_multi": ("adam_multi_kernel", adam_bytes),
+        "b200gs_hexplane_forward": ("hexplane_fwd_kernel", P_ * (12 + 4 + 4 * F_)),
+        "b200gs_hexplane_backward": ("hexplane_bwd_kernel", P_ * (12 + 4 + 4 * F_ + 12) + 4 * plane_params),
+        "b200gs_deform_mlp_forward": ("deform_mlp_fwd_tc5v2_kernel", P_ * (4 * F_ + 52 + 4 * 4 * 64 + 40)),
+        "b200gs_deform_mlp_backward": ("deform_mlp_bwd_tc5_kernel", P_ * (4 * 4 * 64 + 4 * F_ + 40 + 4 * F_)),
+        "b200gs_activations_forward": ("activations_fwd_kernel", P_ * 64),
+        "b200gs_activations_backward": ("activations_bwd_kernel", P_ * 96),
+        "b200gs_l1_loss_fwd_bwd": ("l1_fwd_bwd_kernel", 12 * 3 * args.width * args.height),
+    }
+    kernels = []
+    for name, c in sorted(calls.items(), key=lambda kv: -kv[1]["ms_total"]):
+        row = {"entry": name, "calls": c["calls"], "ms_avg": round(c["ms_avg"], 4), "share_of_step": round(c["ms_total"] / ms, 4)}
+        if name in model_bytes and c["ms_avg"] > 0:
+            kname, nbytes = model_bytes[name]
+            gbs = nbytes / (c["ms_avg"] * 1e-3) / 1e9
+            row.update({"kernel": kname, "bound": "hbm", "algorithmic_bytes_per_launch": nbytes, "achieved_gbs": round(gbs, 1),
+                        "frac_of_measured_hbm_peak": round(gbs / hbm, 4)})
+        kernels.append(row)
+    single = [k for k in kernels if "kernel" in k]
+    dom = single[0] if single else None
     tensors = len(trainer.trainable)
     launches_per_step = None
     if impl == "b200":
-        # kernels of libb200gs per view: hexplane_fwd, mlp_fwd, preprocess_fwd, depth sort (hist, scan, 4 passes), emit,
-        # tile sort (hist, scan, 2 passes), tile_ranges, composite_fwd | composite_bwd, preprocess_bwd, mlp_bwd, hexplane_bwd
-        per_view = 2 + 1 + 6 + 1 + 4 + 1 + 1 + 4
-        launches_per_step = V * per_view + (tensors + 55) // 56
+        # kernels of libb200gs launched in the timed region, counted per entry point by CallTimer (KERNELS table)
+        launches_per_step = sum(c["kernels"] for c in calls.values()) / args.steps
     res = {
         "metric": "train_iters_per_s", "value": value, "unit": "view-iters/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -420,12 +467,20 @@ def _main():
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e * 1e3 / args.steps,
                 "last_loss": last},
         "clocks": clk.summary(),
-        "roofline": {"kernel": "adam_multi_kernel" if impl == "b200" else "torch foreach Adam", "bound": "hbm", "achieved": adam_gbs,
-                     "peak": pk.get("hbm_gbs"), "unit": "GB/s", "frac": (adam_gbs / pk["hbm_gbs"]) if adam_gbs else None,
-                     "traffic": None, "peak_source": pk_kind + " (MEASURED_PEAKS.json hbm_gbs)" if pk_kind == "measured" else "fallback 6650",
-                     "algorithmic_bytes_per_launch": adam_bytes, "ms_per_launch": adam_t, "params": n_params},
-        "gpu_launches": (launches_per_step * args.steps) if launches_per_step else 0,
+        "gpu_launches": int(round(launches_per_step * args.steps)) if launches_per_step else 0,
     }
+    peak_src = pk_kind + " (MEASURED_PEAKS.json hbm_gbs)" if pk_kind == "measured" else "fallback 6650"
+    if impl == "b200" and dom is not None:
+        # the dominant kernel of the step by device time (largest share among the single-kernel entry points)
+        res["roofline"] = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+                           "frac": dom["frac_of_measured_hbm_peak"], "traffic": NCU_TRAFFIC.get(dom["kernel"]), "peak_source": peak_src,
+                           "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "ms_per_launch": dom["ms_avg"],
+                           "share_of_step": dom["share_of_step"], "note": ROOFLINE_NOTES.get(dom["kernel"], "")}
+        res["kernels"] = kernels
+    else:
+        res["roofline"] = {"kernel": "torch foreach Adam", "bound": "hbm", "achieved": adam_gbs, "peak": hbm, "unit": "GB/s",
+                           "frac": (adam_gbs / hbm) if adam_gbs else None, "traffic": None, "peak_source": peak_src,
+                           "algorithmic_bytes_per_launch": adam_bytes, "ms_per_launch": adam_t, "params": n_params}
     if impl != "b200":
         res["impl"] = "reference"
         res["reference_stack"] = "reference CUDA rasterizer (oracle/_ref, unmodified) + PyTorch port of HexPlane/deformation + torch.optim.Adam, on GPU"

@@ -96,3 +96,59 @@ def ptr(t):
 def current_stream():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+class CallTimer:
+    """Times every libb200gs entry point that launches kernels with CUDA events on torch's current stream
+    (the stream every kernel of the library is launched on). bench.py keeps it active over the timed region
+    to get each kernel family's average duration and launch count; nothing else uses it."""
+    # kernels launched per call (for the launch count): see csrc/api.cu and the per-file launchers
+    KERNELS = {"b200gs_rast_forward_stage1": 7, "b200gs_rast_forward_stage2": 7, "b200gs_rast_backward": 2,
+               "b200gs_hexplane_order": 6, "b200gs_hexplane_forward": 1, "b200gs_hexplane_backward": 1,
+               "b200gs_deform_mlp_forward": 1, "b200gs_deform_mlp_backward": 1, "b200gs_adam_multi": 1,
+               "b200gs_activations_forward": 1, "b200gs_activations_backward": 1, "b200gs_l1_loss_fwd_bwd": 1,
+               "b200gs_gather_rows_multi": 1, "b200gs_dist2": 8, "b200gs_mark_visible": 1, "b200gs_sort_pairs_u32": 6}
+
+    def __init__(self):
+        self.events = {}
+        self._orig = {}
+
+    def __enter__(self):
+        import torch
+        L = lib()
+        for name in self.KERNELS:
+            if not hasattr(L, name):
+                continue
+            orig = getattr(L, name)
+            self._orig[name] = orig
+            rec = self.events.setdefault(name, [])
+
+            def wrapped(*a, _orig=orig, _rec=rec):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = _orig(*a)
+                e1.record()
+                _rec.append((e0, e1))
+                return r
+            setattr(L, name, wrapped)
+        return self
+
+    def __exit__(self, *exc):
+        L = lib()
+        for name, orig in self._orig.items():
+            setattr(L, name, orig)
+        self._orig = {}
+
+    def reset(self):
+        for v in self.events.values():
+            v.clear()
+
+    def summary(self):
+        """{entry: {"calls", "ms_total", "ms_avg", "kernels"}} — call after a device synchronize."""
+        out = {}
+        for name, ev in self.events.items():
+            if not ev:
+                continue
+            ms = [a.elapsed_time(b) for a, b in ev]
+            out[name] = {"calls": len(ms), "ms_total": sum(ms), "ms_avg": sum(ms) / len(ms), "kernels": self.KERNELS[name] * len(ms)}
+        return out
