@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--views-per-gpu", type=int, default=8)
     ap.add_argument("--scale-mu", type=float, default=0.010, help="S-coarse 0.010 / S-fine 0.004 (SURVEY.md 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--render-frames", type=int, default=30, help="frames per GPU for the render-FPS side measurement (0 = skip)")
     ap.add_argument("--cpu-points", type=int, default=0, help="override the cpu_baseline sample size")
     return ap.parse_args()
 
@@ -138,7 +139,9 @@ def make_b200_trainer(args, raw, device, world, rank):
     model.training_setup()
     pg = None
     bg = torch.zeros(3, device=device)
-    return model, engine.ViewParallelTrainer(model, bg, stage="fine", process_group=pg, world_size=world, rank=rank)
+    h = engine.default_hyper()
+    return model, engine.ViewParallelTrainer(model, bg, stage="fine", process_group=pg, world_size=world, rank=rank,
+                                             regulation=(h.time_smoothness_weight, h.l1_time_planes, h.plane_tv_weight))
 
 
 # ---- reference arm -------------------------------------------------------------------------------
@@ -246,8 +249,77 @@ def make_reference_trainer(args, raw, device, world, rank):
         color, radii, depth = RefRaster.apply(pts, sp, sh, torch.sigmoid(op), torch.exp(sc), torch.nn.functional.normalize(rt), cam, bg)
         return {"render": color, "viewspace_points": sp, "radii": radii, "depth": depth}
 
+    def ref_regulation():
+        """compute_regulation exactly as scene/gaussian_model.py:730-769 + scene/regulation.py:22-28 spell it (PyTorch ops)."""
+        h = engine.default_hyper()
+        grids = [[model.field[model.keys[f"deformation_net.grid.grids.{l}.{k}"]] for k in range(6)] for l in range(model.levels)]
+
+        def smooth(t):
+            hh = t.shape[2]
+            first = t[..., 1:, :] - t[..., :hh - 1, :]
+            second = first[..., 1:, :] - first[..., :hh - 2, :]
+            return torch.square(second).mean()
+        plane = sum(smooth(g[k]) for g in grids for k in (0, 1, 3))
+        tsm = sum(smooth(g[k]) for g in grids for k in (2, 4, 5))
+        l1 = sum(torch.abs(1 - g[k]).mean() for g in grids for k in (2, 4, 5))
+        return h.plane_tv_weight * plane + h.time_smoothness_weight * tsm + h.l1_time_planes * l1
+
     bg = torch.zeros(3, device=device)
-    return model, engine.ViewParallelTrainer(model, bg, stage="fine", world_size=world, rank=rank, render_fn=ref_render)
+    return model, engine.ViewParallelTrainer(model, bg, stage="fine", world_size=world, rank=rank, render_fn=ref_render,
+                                             regulation_fn=ref_regulation)
+
+
+# ---- render FPS (BASELINE.json metric, second half; config C4 style) ---------------------------------
+def render_fps(args, model, device, world, rank, impl, ref_render=None):
+    """Video rendering (render_4DGS.py:41-76): frames of an orbit with advancing time, sharded round-robin over
+    ranks, no collective. `fps` = frames rendered per second on the device (deformation + rasterizer forward),
+    `e2e_fps` adds the output path per frame: to8b + D2H into pinned host memory (our arm: GPU quantise + async
+    3 B/pixel copy through a pinned ring; reference arm: the blocking float copy + host clip/cast of render_4DGS.py:49)."""
+    import numpy as np
+    from b200gs import engine, synthetic as syn
+    out = {}
+    bg = torch.zeros(3, device=device)
+    for tag, (W, H) in (("1280x720", (args.width, args.height)), ("1920x1080", (1920, 1080))):
+        n = args.render_frames
+        cams = syn.orbit_cameras(n * world, W, H, device=device)[rank::world]
+        fn = (lambda c: engine.render(c, model, bg, stage="fine")) if impl == "b200" else (lambda c: ref_render(c, model, bg, "fine"))
+        with torch.no_grad():
+            for c in cams[:3]:
+                fn(c)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for c in cams:
+                fn(c)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if impl == "b200":
+                from b200gs import output
+                ring = output.FrameRing(H, W, depth=4, device=device)      # pinned buffers are allocated once, outside the loop
+                ring.push(fn(cams[0])["render"]); ring.pop()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if impl == "b200":
+                for c in cams:
+                    if ring.count == 4:
+                        ring.pop()
+                    ring.push(fn(c)["render"])
+                while ring.count:
+                    ring.pop()
+            else:
+                for c in cams:
+                    (255 * np.clip(fn(c)["render"].cpu().numpy(), 0, 1)).astype(np.uint8)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms, wall * 1e3], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        out[tag] = {"fps": n * world / (ms / 1e3), "e2e_fps": n * world / wall, "frames": n * world,
+                    "d2h_bytes_per_frame": 3 * W * H if impl == "b200" else 12 * W * H}
+    return out
 
 
 # ---- cpu baseline ---------------------------------------------------------------------------------
@@ -302,11 +374,20 @@ def cpu_baseline(args, raw, cam):
 # ---------------------------------------------------------------------------------------------
 def main():
     import contextlib
-    real_stdout = sys.stdout
-    with contextlib.redirect_stdout(sys.stderr):      # library chatter goes to stderr; stdout carries ONE JSON line
-        line = _main()
+    # library chatter (Python prints AND C-level writes such as NCCL's version banner) goes to stderr;
+    # the original stdout carries ONE JSON line
+    sys.stdout.flush()
+    real_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        with contextlib.redirect_stdout(sys.stderr):
+            line = _main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_fd, 1)
     if line is not None:
-        print(line, file=real_stdout, flush=True)
+        os.write(real_fd, (line + "\n").encode())
+    os.close(real_fd)
 
 
 def _main():
@@ -409,6 +490,9 @@ def _main():
         wall_e2e = time.perf_counter() - t_wall
     if not timer:
         model.optimizer.step = opt_step
+    render = None
+    if args.render_frames > 0:
+        render = render_fps(args, model, device, world, rank, impl, ref_render=None if impl == "b200" else trainer.render_fn)
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
@@ -457,7 +541,7 @@ def _main():
         "metric": "train_iters_per_s", "value": value, "unit": "view-iters/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C3 train_4DGS fine-stage iteration: HexPlane deform + raster fwd/bwd + Adam, {args.points} Gaussians, "
+        "config": {"workload": f"C3 train_4DGS fine-stage iteration: HexPlane deform + raster fwd/bwd + plane regulariser + Adam, {args.points} Gaussians, "
                                f"{args.width}x{args.height}, {args.views_per_gpu} views per GPU per optimizer step (global batch {n_global})",
                    "scene": f"seeded synthetic, scale_mu={args.scale_mu}", "views_per_gpu": args.views_per_gpu,
                    "iters_per_s_at_batch": value / n_global,
@@ -481,6 +565,10 @@ def _main():
         res["roofline"] = {"kernel": "torch foreach Adam", "bound": "hbm", "achieved": adam_gbs, "peak": hbm, "unit": "GB/s",
                            "frac": (adam_gbs / hbm) if adam_gbs else None, "traffic": None, "peak_source": peak_src,
                            "algorithmic_bytes_per_launch": adam_bytes, "ms_per_launch": adam_t, "params": n_params}
+    if render is not None:
+        res["render"] = render
+        res["config"]["render"] = (f"video rendering, {args.render_frames} frames per GPU of an orbit with advancing time, frames sharded "
+                                   "round-robin over ranks; fps = device time, e2e_fps = wall clock incl. to8b + D2H per frame")
     if impl != "b200":
         res["impl"] = "reference"
         res["reference_stack"] = "reference CUDA rasterizer (oracle/_ref, unmodified) + PyTorch port of HexPlane/deformation + torch.optim.Adam, on GPU"

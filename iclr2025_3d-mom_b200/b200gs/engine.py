@@ -145,10 +145,14 @@ class ViewParallelTrainer:
     `render_fn(cam, model, bg, stage)` defaults to this module's `render`; tests inject a CPU
     stand-in to exercise the sharding / flat-arena / collective logic over gloo."""
 
-    def __init__(self, model, bg_color, stage="fine", process_group=None, world_size=1, rank=0, render_fn=None):
+    def __init__(self, model, bg_color, stage="fine", process_group=None, world_size=1, rank=0, render_fn=None,
+                 regulation=None, regulation_fn=None):
         self.model = model
         self.bg = bg_color
         self.stage = stage
+        # (time_smoothness_weight, l1_time_planes, plane_tv_weight) of train_4DGS.py:215-218, or None to leave it out
+        self.regulation = regulation if stage == "fine" else None
+        self.regulation_fn = regulation_fn if stage == "fine" else None      # PyTorch-op variant (the reference arm of bench.py)
         self.pg = process_group
         self.world_size = world_size
         self.rank = rank
@@ -231,5 +235,13 @@ class ViewParallelTrainer:
             import torch.distributed as dist
             dist.all_reduce(self.arena, op=dist.ReduceOp.SUM, group=self.pg)
             dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=self.pg)
+        if self.regulation is not None:
+            # plane-only term, identical on every rank: added once, after the reduce
+            _field.accumulate_regulation(self.model._deformation.deformation_net.grid, *self.regulation,
+                                         loss_accum=total if (total is not None and total.numel() == 1 and total.dim() == 1) else None)
+        if self.regulation_fn is not None:
+            reg = self.regulation_fn()
+            reg.backward()
+            total = total + reg.detach()
         self.model.optimizer.step()
         return total.reshape(()) if total is not None else total

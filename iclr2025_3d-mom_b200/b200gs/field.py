@@ -86,6 +86,8 @@ _lib.register("b200gs_deform_mlp_forward", ctypes.c_int,
                _P, _P, _P, _P, _P])
 _lib.register("b200gs_deform_mlp_backward", ctypes.c_int,
               [ctypes.POINTER(_MlpWeights), ctypes.POINTER(_MlpGrads), ctypes.c_longlong, _P, _P, _P, _P, _P, _P, _P])
+_lib.register("b200gs_hexplane_regulation", ctypes.c_int,
+              [ctypes.POINTER(_HexDesc), ctypes.c_float, ctypes.c_float, ctypes.c_float, _P, _P])
 
 
 def _cl(t):
@@ -282,6 +284,51 @@ class _DeformFn(torch.autograd.Function):
                     gw_out[i] = None
         gp_out = [None if dp is not None else g for g, dp in zip(gplanes, direct_p)]
         return (d_xyz, d_scales, d_rot, None, None, None, None, None, None, None, None, *gw_out, *gp_out)
+
+
+def _regulation_launch(field, weights, loss_accum, grads):
+    planes = field._planes()
+    levels = len(field.grids)
+    d = _hex_desc(field.aabb, planes, levels, tuple(field._res), grads)
+    tw, l1w, pw = weights
+    check(_lib.lib().b200gs_hexplane_regulation(ctypes.byref(d), float(pw), float(tw), float(l1w),
+                                                loss_accum.data_ptr() if loss_accum is not None else None, current_stream()),
+          "hexplane_regulation")
+
+
+class _RegulationFn(torch.autograd.Function):
+    """compute_regulation (scene/gaussian_model.py:768-769) as one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, field, tw, l1w, pw, *planes):
+        loss = torch.zeros(1, dtype=torch.float32, device=planes[0].device)
+        _regulation_launch(field, (tw, l1w, pw), loss, None)
+        ctx.field, ctx.weights = field, (tw, l1w, pw)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        planes = ctx.field._planes()
+        grads = [torch.zeros_like(p, memory_format=torch.preserve_format) for p in planes]
+        _regulation_launch(ctx.field, ctx.weights, None, grads)
+        return (None, None, None, None, *[gr * g for gr in grads])
+
+
+def compute_regulation(field, time_smoothness_weight, l1_time_planes_weight, plane_tv_weight):
+    """Drop-in for GaussianModel.compute_regulation (scene/gaussian_model.py:768-769; same argument order) given the
+    HexPlaneField: differentiable scalar."""
+    return _RegulationFn.apply(field, time_smoothness_weight, l1_time_planes_weight, plane_tv_weight, *field._planes())
+
+
+def accumulate_regulation(field, time_smoothness_weight, l1_time_planes_weight, plane_tv_weight, loss_accum=None):
+    """Trainer fast path: add the regulariser's gradient straight into the planes' existing `.grad` buffers (and its value
+    into `loss_accum`), one launch, no autograd."""
+    grads = []
+    for p in field._planes():
+        if p.grad is None or p.grad.stride() != p.stride():
+            raise RuntimeError("accumulate_regulation needs channels-last .grad buffers on every plane")
+        grads.append(p.grad)
+    _regulation_launch(field, (time_smoothness_weight, l1_time_planes_weight, plane_tv_weight), loss_accum, grads)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -8,7 +8,8 @@ reference's compiled extensions, (2) appends import shims for third-party module
 (compat/), (3) swaps `deform_network` for the fused-kernel module where
 `GaussianModel` looks it up (scene/gaussian_model.py:21,53), (4) makes `training_setup` build the fused
 multi-tensor Adam from the very param groups the reference assembles (gaussian_model.py:197-209), and
-(5) installs the one-launch prune / cat bookkeeping (gaussian_model.py:424-482). The reference tree is
+(5) installs the one-launch prune / cat bookkeeping (gaussian_model.py:424-482) and (6) routes
+`compute_regulation` (gaussian_model.py:768-769) to the fused plane-regulariser kernel. The reference tree is
 never modified.
 """
 import os
@@ -46,6 +47,15 @@ def install(reference_root):
                 self.optimizer = FusedAdam(groups, lr=0.0, eps=1e-15)
                 return out
             setattr(gm.GaussianModel, name, wrapped)
+        orig_reg = gm.GaussianModel.compute_regulation
+
+        def compute_regulation(self, time_smoothness_weight, l1_time_planes_weight, plane_tv_weight, __orig=orig_reg):
+            from . import field
+            grid = self._deformation.deformation_net.grid
+            if isinstance(grid, field.HexPlaneField) and grid.aabb.is_cuda:
+                return field.compute_regulation(grid, time_smoothness_weight, l1_time_planes_weight, plane_tv_weight)
+            return __orig(self, time_smoothness_weight, l1_time_planes_weight, plane_tv_weight)
+        gm.GaussianModel.compute_regulation = compute_regulation
         gm.GaussianModel._b200gs_patched = True
     return gm
 

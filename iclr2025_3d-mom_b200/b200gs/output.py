@@ -1,0 +1,64 @@
+"""Render output path: quantise on the GPU, copy 3 bytes per pixel to pinned host
+memory on a side stream, hand finished frames to the writer off the critical path.
+
+The reference does `to8b = lambda x: (255*np.clip(x.cpu().numpy(),0,1)).astype(np.uint8)` per frame
+(render_4DGS.py:49, train_4DGS.py:335): a blocking 12 B/pixel D2H copy plus host-side clip/scale/cast inside the
+render loop. Here the frame is clipped, scaled and cast by `b200gs_to8b_hwc` (same truncation), and a ring of
+pinned buffers lets frame i's copy overlap frame i+1's rendering.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, current_stream
+
+_lib.register("b200gs_to8b_hwc", ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p])
+
+
+def to8b(image):
+    """[3,H,W] float32 CUDA image -> [H,W,3] uint8 CUDA tensor, (255 * clip(x, 0, 1)).astype(uint8)."""
+    if not (image.is_cuda and image.dtype == torch.float32 and image.dim() == 3 and image.shape[0] == 3):
+        raise RuntimeError("to8b needs a [3,H,W] float32 CUDA image (there is no CPU path)")
+    img = image.detach().contiguous()
+    H, W = int(img.shape[1]), int(img.shape[2])
+    out = torch.empty((H, W, 3), dtype=torch.uint8, device=img.device)
+    check(_lib.lib().b200gs_to8b_hwc(H, W, img.data_ptr(), out.data_ptr(), current_stream()), "to8b_hwc")
+    return out
+
+
+class FrameRing:
+    """Pinned-host ring for finished frames. `push(image)` quantises on the current stream and starts an async
+    D2H copy on a side stream; `pop()` returns the oldest frame as a numpy array once its copy has landed."""
+
+    def __init__(self, H, W, depth=4, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.host = [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.head = 0          # next slot to fill
+        self.count = 0
+        self.bytes_per_frame = H * W * 3
+
+    def push(self, image):
+        if self.count == len(self.host):
+            raise RuntimeError("FrameRing full: pop() a frame first")
+        q = to8b(image)
+        ready = torch.cuda.Event()
+        ready.record()
+        slot = self.head
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(ready)
+            self.host[slot].copy_(q, non_blocking=True)
+            q.record_stream(self.copy_stream)
+            self.done[slot].record(self.copy_stream)
+        self.head = (self.head + 1) % len(self.host)
+        self.count += 1
+
+    def pop(self):
+        if self.count == 0:
+            raise RuntimeError("FrameRing empty")
+        slot = (self.head - self.count) % len(self.host)
+        self.done[slot].synchronize()
+        self.count -= 1
+        return self.host[slot].numpy()

@@ -90,6 +90,22 @@ __global__ void __launch_bounds__(256) l1_fwd_bwd_kernel(long long n, const floa
     }
 }
 
+// to8b of render_4DGS.py:49 / train_4DGS.py:335 on the device: out[y][x][c] = (uint8)(255 * clip(img[c][y][x], 0, 1))
+// (truncation, like numpy's astype), CHW float -> HWC bytes; 12 B read + 3 B written per pixel.
+__global__ void __launch_bounds__(256) to8b_hwc_kernel(int H, int W, const float* __restrict__ img, unsigned char* __restrict__ out)
+{
+    const long long n = (long long)H * W;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        unsigned char v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float x = fminf(fmaxf(__ldg(img + c * n + i), 0.f), 1.f);
+            v[c] = (unsigned char)(255.f * x);
+        }
+        out[3 * i] = v[0]; out[3 * i + 1] = v[1]; out[3 * i + 2] = v[2];
+    }
+}
+
 }  // namespace
 }  // namespace b200gs
 
@@ -127,6 +143,16 @@ int b200gs_l1_loss_fwd_bwd(long long n, const float* render, const float* target
     if (blocks < 1) blocks = 1;
     l1_fwd_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, render, target, scale, loss_accum, d_render);
     return check_launch("l1_loss");
+}
+
+int b200gs_to8b_hwc(int H, int W, const float* image_chw, unsigned char* out_hwc, b200gs_stream_t stream)
+{
+    if (H <= 0 || W <= 0) return 0;
+    if (!image_chw || !out_hwc) { set_error("to8b_hwc: null pointer"); return -1; }
+    long long blocks = ((long long)H * W + 255) / 256;
+    if (blocks > (long long)NUM_SMS * 8) blocks = (long long)NUM_SMS * 8;
+    to8b_hwc_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(H, W, image_chw, out_hwc);
+    return check_launch("to8b_hwc");
 }
 
 }  // extern "C"

@@ -265,6 +265,70 @@ hexplane_cellkey_kernel(long long P, const float* __restrict__ pts, const float*
     ids[i] = (unsigned int)i;
 }
 
+
+// ---- plane regulariser (scene/gaussian_model.py:730-769 compute_regulation; scene/regulation.py:22-28) ----------
+// per level:  w_plane * sum_{k in 0,1,3} S(G_k) + w_time * sum_{k in 2,4,5} S(G_k) + w_l1 * sum_{k in 2,4,5} mean|1 - G_k|
+// S(G) = mean over [C, H-2, W] of (G[y+2] - 2 G[y+1] + G[y])^2  (second difference along the plane's HEIGHT).
+// One thread owns one (x, 4-channel) column of a channels-last plane and walks it top to bottom with the three
+// live second differences in registers: value and gradient in one pass, 8 B/parameter (+4 when the L1 term reads it
+// anyway).  dS/dG[j] = (2/N) (d[j] - 2 d[j-1] + d[j-2]),  d[i] defined for 0 <= i <= H-3.
+__global__ void __launch_bounds__(128)
+hexplane_regulation_kernel(const __grid_constant__ b200gs_hexplane_desc d, float w_plane, float w_time, float w_l1,
+                           float* __restrict__ loss)
+{
+    const int l = blockIdx.y / 6, k = blockIdx.y % 6;
+    constexpr int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
+    const int W = d.res[l][pa[k]], H = d.res[l][pb[k]];
+    const bool is_time = pb[k] == 3;
+    const float w_s = is_time ? w_time : w_plane;
+    const float* __restrict__ G = d.plane[l][k];
+    float* __restrict__ gG = d.grad_plane[l][k];
+    const int col = blockIdx.x * 128 + threadIdx.x;            // (x, channel quad)
+    float acc = 0.f;
+    if (col < W * 8) {
+        const size_t stride = (size_t)W * 8;                   // float4 units per row
+        const float4* g4 = reinterpret_cast<const float4*>(G) + col;
+        float4* o4 = gG ? reinterpret_cast<float4*>(gG) + col : nullptr;
+        const float cs = H > 2 ? w_s * 2.f / ((float)HP_C * (float)(H - 2) * (float)W) : 0.f;     // 2 w / N
+        const float cl = is_time ? w_l1 / ((float)HP_C * (float)H * (float)W) : 0.f;
+        float sq = 0.f, l1 = 0.f;
+        float4 t0 = H > 0 ? __ldg(g4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 t1 = H > 1 ? __ldg(g4 + stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 dm1 = make_float4(0.f, 0.f, 0.f, 0.f), dm2 = dm1;            // d[j-1], d[j-2]
+        for (int j = 0; j < H; ++j) {
+            const float4 t2 = j + 2 < H ? __ldg(g4 + (size_t)(j + 2) * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 dj = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j + 2 < H) {
+                dj = make_float4(t2.x - 2.f * t1.x + t0.x, t2.y - 2.f * t1.y + t0.y, t2.z - 2.f * t1.z + t0.z, t2.w - 2.f * t1.w + t0.w);
+                sq += dj.x * dj.x + dj.y * dj.y + dj.z * dj.z + dj.w * dj.w;
+            }
+            float4 g = make_float4(cs * (dj.x - 2.f * dm1.x + dm2.x), cs * (dj.y - 2.f * dm1.y + dm2.y),
+                                   cs * (dj.z - 2.f * dm1.z + dm2.z), cs * (dj.w - 2.f * dm1.w + dm2.w));
+            if (is_time) {                                     // d/dG mean|1 - G| = -sign(1 - G) / M
+                const float e[4] = {1.f - t0.x, 1.f - t0.y, 1.f - t0.z, 1.f - t0.w};
+                l1 += fabsf(e[0]) + fabsf(e[1]) + fabsf(e[2]) + fabsf(e[3]);
+                g.x -= e[0] > 0.f ? cl : (e[0] < 0.f ? -cl : 0.f); g.y -= e[1] > 0.f ? cl : (e[1] < 0.f ? -cl : 0.f);
+                g.z -= e[2] > 0.f ? cl : (e[2] < 0.f ? -cl : 0.f); g.w -= e[3] > 0.f ? cl : (e[3] < 0.f ? -cl : 0.f);
+            }
+            if (o4) {
+                float4* o = o4 + (size_t)j * stride;
+                const float4 prev = *o;
+                *o = make_float4(prev.x + g.x, prev.y + g.y, prev.z + g.z, prev.w + g.w);
+            }
+            dm2 = dm1; dm1 = dj; t0 = t1; t1 = t2;
+        }
+        acc = 0.5f * cs * sq + cl * l1;                        // w * mean(d^2) = (cs / 2) * sum d^2
+    }
+    if (loss) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        __shared__ float part[4];
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(loss, part[0] + part[1] + part[2] + part[3]);
+    }
+}
+
 int validate(const b200gs_hexplane_desc* d)
 {
     if (!d) { set_error("hexplane: null descriptor"); return -1; }
@@ -334,6 +398,19 @@ int b200gs_hexplane_backward(const b200gs_hexplane_desc* desc, long long P, cons
     if (P <= 0) return 0;
     hexplane_bwd_kernel<<<grid_for(P), 256, 0, (cudaStream_t)stream>>>(*desc, P, pts, order, times, time_scalar, d_features, d_pts);
     return check_launch("hexplane_backward");
+}
+
+int b200gs_hexplane_regulation(const b200gs_hexplane_desc* desc, float plane_tv_weight, float time_smoothness_weight,
+                               float l1_time_planes_weight, float* loss_accum, b200gs_stream_t stream)
+{
+    if (validate(desc)) return -1;
+    int wmax = 1;
+    for (int l = 0; l < desc->levels; ++l)
+        for (int a = 0; a < 3; ++a) wmax = desc->res[l][a] > wmax ? desc->res[l][a] : wmax;
+    dim3 grid((unsigned)((wmax * 8 + 127) / 128), (unsigned)(desc->levels * 6));
+    hexplane_regulation_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*desc, plane_tv_weight, time_smoothness_weight,
+                                                                        l1_time_planes_weight, loss_accum);
+    return check_launch("hexplane_regulation");
 }
 
 }  // extern "C"

@@ -200,6 +200,15 @@ int b200gs_deform_mlp_backward(const b200gs_mlp_weights* w /* host */, const b20
                                long long P, const float* features, const float* saved, const float* d_pts,
                                const float* d_scales, const float* d_rot, float* d_features, b200gs_stream_t stream);
 
+/* HexPlane regulariser, value and gradient in one pass (scene/gaussian_model.py:730-769 compute_regulation;
+ * scene/regulation.py:22-28 compute_plane_smoothness): per level
+ *   plane_tv_weight * sum_{k in 0,1,3} S(G_k) + time_smoothness_weight * sum_{k in 2,4,5} S(G_k)
+ *   + l1_time_planes_weight * sum_{k in 2,4,5} mean |1 - G_k|,   S = mean squared second difference along a plane's height.
+ * The value is ADDED to loss_accum[0] (device float, may be null); the gradient is ADDED into desc->grad_plane
+ * (entries may be null). desc->aabb is not used. */
+int b200gs_hexplane_regulation(const b200gs_hexplane_desc* desc, float plane_tv_weight, float time_smoothness_weight,
+                               float l1_time_planes_weight, float* loss_accum, b200gs_stream_t stream);
+
 /* ---- fused elementwise pieces of the training loop ------------------------------------------------
  * activations: scales = exp(s), rotations = F.normalize(r) (x / max(||x||, 1e-12)), opacity = sigmoid(o)
  * (gaussian_renderer/__init__.py:130-132; scene/gaussian_model.py:37-47). [P,3] / [P,4] / [P,1] FP32.
@@ -215,6 +224,10 @@ int b200gs_activations_backward(long long P, const float* scales_out, const floa
  * per-view share of train_4DGS.py:205-210's batch-mean L1. loss_accum is a device float the caller zeroes. */
 int b200gs_l1_loss_fwd_bwd(long long n, const float* render, const float* target, float scale, float* loss_accum, float* d_render,
                            b200gs_stream_t stream);
+
+/* to8b of render_4DGS.py:49 / train_4DGS.py:335 on the device: out_hwc[y][x][c] = (uint8)(255 * clip(image_chw[c][y][x], 0, 1)),
+ * truncating like numpy's astype; [3,H,W] FP32 -> [H,W,3] bytes (the frame leaves the GPU as 3 B/pixel). */
+int b200gs_to8b_hwc(int H, int W, const float* image_chw, unsigned char* out_hwc, b200gs_stream_t stream);
 
 #ifdef __cplusplus
 }

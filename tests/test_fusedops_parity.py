@@ -52,3 +52,22 @@ def test_l1_loss_and_grad(shape):
     ref.backward()
     assert abs(acc.item() - ref.item()) < 1e-5 * ref.item()
     assert torch.equal(d, img.grad)
+
+
+def test_to8b_and_frame_ring():
+    import numpy as np
+    from b200gs import output
+    g = torch.Generator().manual_seed(11)
+    frames = [(torch.rand(3, 67, 129, generator=g) * 1.4 - 0.2).cuda() for _ in range(6)]
+    to8b = lambda x: (255 * np.clip(x.cpu().numpy(), 0, 1)).astype(np.uint8)          # render_4DGS.py:49
+    for f in frames[:2]:
+        assert np.array_equal(output.to8b(f).cpu().numpy(), to8b(f).transpose(1, 2, 0))
+    ring = output.FrameRing(67, 129, depth=3)
+    got = []
+    for i, f in enumerate(frames):
+        if ring.count == 3:
+            got.append(ring.pop().copy())
+        ring.push(f)
+    while ring.count:
+        got.append(ring.pop().copy())
+    assert len(got) == 6 and all(np.array_equal(a, to8b(f).transpose(1, 2, 0)) for a, f in zip(got, frames))
