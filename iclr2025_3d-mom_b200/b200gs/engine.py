@@ -116,7 +116,9 @@ def render(cam, pc, bg_color, scaling_modifier=1.0, stage="fine", delta_scale=1,
     if stage == "coarse":
         m3, sc, rt, op, sh = means3D, scales, rotations, opacity, shs
     else:
-        time = torch.full((means3D.shape[0], 1), float(cam.time), device=means3D.device)
+        # the reference repeats the camera's timestamp into a [P,1] tensor (gaussian_renderer/__init__.py:56); our field
+        # takes the scalar itself (CUDA path only), which also tells its backward that the whole view shares one time
+        time = float(cam.time) if means3D.is_cuda else torch.full((means3D.shape[0], 1), float(cam.time), device=means3D.device)
         m3, sc, rt, op, sh = pc._deformation(means3D, scales, rotations, opacity, shs, time, pc.get_flow,
                                              cam.frame_num, delta_scale)
     if sc.is_cuda:
@@ -204,6 +206,9 @@ class ViewParallelTrainer:
             m = self.model
             shs = torch.cat((m._features_dc, m._features_rest), dim=1).detach().requires_grad_(True)
         from . import field as _field
+        share_spatial = self.shared_shs and self.stage == "fine" and len(cams) > 1 and self.model._xyz.is_cuda
+        if share_spatial:
+            _field.begin_shared_step(self.model._deformation, self.model._xyz)
         for cam, gt in zip(cams, gts):
             pkg = self.render_fn(cam, self.model, self.bg, self.stage, shs) if self.shared_shs else \
                 self.render_fn(cam, self.model, self.bg, self.stage)
@@ -228,6 +233,8 @@ class ViewParallelTrainer:
             torch.maximum(self.max_radii, pkg["radii"], out=self.max_radii)
             if loss is not None:
                 total = loss.detach() if total is None else total + loss.detach()
+        if share_spatial:
+            _field.finish_shared_step()
         if shs is not None and shs.grad is not None:
             self.model._features_dc.grad += shs.grad[:, :1]
             self.model._features_rest.grad += shs.grad[:, 1:]

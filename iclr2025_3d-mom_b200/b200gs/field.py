@@ -50,6 +50,23 @@ _lib.register("b200gs_hexplane_forward", ctypes.c_int,
               [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, _P, ctypes.c_float, _P, _P])
 _lib.register("b200gs_hexplane_backward", ctypes.c_int,
               [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, _P, ctypes.c_float, _P, _P, _P])
+_lib.register("b200gs_hexplane_forward_masked", ctypes.c_int,
+              [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, _P, ctypes.c_float, ctypes.c_int, _P, _P, _P])
+_lib.register("b200gs_hexplane_backward_masked", ctypes.c_int,
+              [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, _P, ctypes.c_float, ctypes.c_int, _P, _P, _P, _P, _P, ctypes.c_size_t, _P])
+_lib.register("b200gs_hexplane_time_row_scratch_bytes", ctypes.c_size_t, [ctypes.POINTER(_HexDesc), ctypes.c_int])
+_ROW_SCRATCH = {}
+TIME_ROW_REPLICAS = 64
+
+
+def _time_row_scratch(d, device):
+    """Scratch for the uniform-timestamp time-plane reduction (b200gs_hexplane_backward_masked), cached per device."""
+    n = _lib.lib().b200gs_hexplane_time_row_scratch_bytes(ctypes.byref(d), TIME_ROW_REPLICAS)
+    t = _ROW_SCRATCH.get(device)
+    if t is None or t.numel() < n:
+        t = torch.empty((n,), dtype=torch.uint8, device=device)
+        _ROW_SCRATCH[device] = t
+    return t, n
 _lib.register("b200gs_hexplane_order_scratch_bytes", ctypes.c_size_t, [ctypes.c_longlong])
 _lib.register("b200gs_hexplane_order", ctypes.c_int, [ctypes.c_longlong, _P, _P, _P, _P, ctypes.c_size_t, _P])
 
@@ -186,6 +203,70 @@ def _grad_target(param):
     return None
 
 
+# ---- spatial planes shared by the views of one optimiser step -------------------------------------
+# The Gaussians' xyz do not change between the views of a batch, so the product of the three SPATIAL planes
+# (xy, xz, yz) is the same for every view: b200gs.engine.ViewParallelTrainer evaluates it once per step
+# (begin_shared_step), each view then samples only the three TIME planes and multiplies, each view's backward
+# accumulates the spatial product's upstream gradient, and ONE spatial backward per step (finish_shared_step)
+# scatters it. Same mathematics as six planes per view (the product is re-associated), ~half the gathers / REDs.
+MASK_SPATIAL, MASK_TIME, MASK_ALL = 0x0B, 0x34, 0x3F
+_SHARED = None
+
+
+def begin_shared_step(net, xyz_param):
+    """net: deform_network; xyz_param: the leaf the views will query (its .grad receives the spatial xyz gradient)."""
+    global _SHARED
+    grid = net.deformation_net.grid
+    planes = grid._planes()
+    levels, res = len(grid.grids), tuple(grid._res)
+    xyz = xyz_param.detach().contiguous()
+    _check_cuda_f32(xyz, grid.aabb, *planes)
+    P = int(xyz.shape[0])
+    S = torch.empty((P, 32 * levels), dtype=torch.float32, device=xyz.device)
+    d = _hex_desc(grid.aabb, planes, levels, res)
+    order = _cell_order(xyz, grid.aabb)
+    check(_lib.lib().b200gs_hexplane_forward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(order), None, 0.0, MASK_SPATIAL, None,
+                                                    S.data_ptr(), current_stream()), "hexplane_forward(spatial)")
+    _SHARED = {"key": (xyz.data_ptr(), xyz_param._version, P), "S": S, "A": torch.zeros_like(S), "xyz_param": xyz_param, "grid": grid,
+               "order": order, "used": False}
+
+
+def finish_shared_step():
+    """The deferred spatial backward: plane gradients into the planes' .grad, xyz gradient into xyz_param.grad."""
+    global _SHARED
+    sh, _SHARED = _SHARED, None
+    if sh is None or not sh["used"]:
+        return
+    grid, xyz_param = sh["grid"], sh["xyz_param"]
+    planes = grid._planes()
+    grads = []
+    for k, p in enumerate(planes):
+        if (k % 6) in (0, 1, 3):
+            if p.grad is None or p.grad.stride() != p.stride():
+                raise RuntimeError("finish_shared_step needs channels-last .grad buffers on the spatial planes")
+            grads.append(p.grad)
+        else:
+            grads.append(None)
+    xyz = xyz_param.detach().contiguous()
+    P = int(xyz.shape[0])
+    d = _hex_desc(grid.aabb, planes, len(grid.grids), tuple(grid._res), grads)
+    d_xyz = torch.empty_like(xyz)
+    check(_lib.lib().b200gs_hexplane_backward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(sh["order"]), None, 0.0, MASK_SPATIAL,
+                                                     None, None, sh["A"].data_ptr(), d_xyz.data_ptr(), None, 0, current_stream()),
+          "hexplane_backward(spatial)")
+    if xyz_param.grad is None:
+        xyz_param.grad = d_xyz
+    else:
+        xyz_param.grad += d_xyz
+
+
+def _shared_for(xyz, P):
+    sh = _SHARED
+    if sh is not None and sh["key"] == (xyz.data_ptr(), xyz._version, P):
+        return sh
+    return None
+
+
 class _DeformFn(torch.autograd.Function):
     """(pts, scales, rot) = field(xyz, scales, rot, t, scene_flow, frame_num, delta_scale).
 
@@ -209,9 +290,17 @@ class _DeformFn(torch.autograd.Function):
         d = _hex_desc(aabb, planes, levels, res)
         order = _cell_order(xyz, aabb)
         ctx.order = order
-        check(L.b200gs_hexplane_forward(ctypes.byref(d), P, xyz.data_ptr(), _optr(order),
-                                        tt.data_ptr() if tt is not None else None, ts, feat.data_ptr(), stream),
-              "hexplane_forward")
+        sh = _shared_for(xyz, P)
+        ctx.shared = sh
+        if sh is not None:        # spatial product from begin_shared_step; only the time planes are sampled per view
+            sh["used"] = True
+            check(L.b200gs_hexplane_forward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(order),
+                                                   tt.data_ptr() if tt is not None else None, ts, MASK_TIME, sh["S"].data_ptr(),
+                                                   feat.data_ptr(), stream), "hexplane_forward(time)")
+        else:
+            check(L.b200gs_hexplane_forward(ctypes.byref(d), P, xyz.data_ptr(), _optr(order),
+                                            tt.data_ptr() if tt is not None else None, ts, feat.data_ptr(), stream),
+                  "hexplane_forward")
         mw = _DeformFn._weights_struct(weights, heads, 32 * levels)
         saved = torch.empty((L.b200gs_deform_mlp_saved_floats(P),), dtype=torch.float32, device=dev)
         pts_o = torch.empty_like(xyz); scales_o = torch.empty_like(scales); rot_o = torch.empty_like(rot)
@@ -272,9 +361,21 @@ class _DeformFn(torch.autograd.Function):
         gplanes = [dp if dp is not None else torch.zeros_like(p, memory_format=torch.preserve_format) for p, dp in zip(planes, direct_p)]
         d_xyz_grid = torch.empty_like(xyz)
         d = _hex_desc(aabb, planes, levels, res, gplanes)
-        check(L.b200gs_hexplane_backward(ctypes.byref(d), P, xyz.data_ptr(), _optr(ctx.order),
-                                         tt.data_ptr() if has_t else None, ts, d_feat.data_ptr(), d_xyz_grid.data_ptr(),
-                                         stream), "hexplane_backward")
+        sh = ctx.shared
+        if sh is not None or not has_t:
+            # shared step: time planes now, the spatial planes' share is accumulated for finish_shared_step.
+            # One timestamp for the whole launch (scalar time): the time planes' gradient goes through replicated 1-D rows.
+            scratch, nbytes = _time_row_scratch(d, xyz.device) if not has_t else (None, 0)
+            check(L.b200gs_hexplane_backward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(ctx.order),
+                                                    tt.data_ptr() if has_t else None, ts, MASK_TIME if sh is not None else MASK_ALL,
+                                                    sh["S"].data_ptr() if sh is not None else None,
+                                                    sh["A"].data_ptr() if sh is not None else None, d_feat.data_ptr(),
+                                                    d_xyz_grid.data_ptr(), scratch.data_ptr() if scratch is not None else None, nbytes,
+                                                    stream), "hexplane_backward(time)")
+        else:
+            check(L.b200gs_hexplane_backward(ctypes.byref(d), P, xyz.data_ptr(), _optr(ctx.order),
+                                             tt.data_ptr() if has_t else None, ts, d_feat.data_ptr(), d_xyz_grid.data_ptr(),
+                                             stream), "hexplane_backward")
         # pts = xyz*1 + ..., scales = scales*1 + ds, rot = rot + dr: identity paths
         d_xyz = d_xyz_grid + d_pts if d_pts is not None else d_xyz_grid
         gw_out = [None if dw is not None else g for g, dw in zip(gws, direct_w)]      # accumulated in place -> nothing for autograd
@@ -482,7 +583,9 @@ class Deformation(nn.Module):
             frame_num = 0.0
         if delta_scale is None:
             delta_scale = 0.0
-        pts, scales, rotations = _DeformFn.apply(xyz, scales_emb[:, :3], rotations_emb[:, :4], time_emb[:, :1], scene_flow,
+        # time_emb: the reference's [P,1] tensor (gaussian_renderer/__init__.py:56), or one Python float for the whole call
+        t_arg = time_emb[:, :1] if torch.is_tensor(time_emb) else float(time_emb)
+        pts, scales, rotations = _DeformFn.apply(xyz, scales_emb[:, :3], rotations_emb[:, :4], t_arg, scene_flow,
                                                  frame_num, delta_scale, self.grid.aabb, len(self.grid.grids),
                                                  tuple(self.grid._res), heads, *weights, *self.grid._planes())
         opacity = opacity_emb[:, :1]

@@ -128,98 +128,162 @@ __device__ __forceinline__ float4 mul4(const float4 a, const float4 b)
 __global__ void __launch_bounds__(256)
 hexplane_fwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, long long P, const float* __restrict__ pts,
                     const unsigned int* __restrict__ order, const float* __restrict__ times, float time_scalar,
-                    float* __restrict__ feat)
+                    int mask, const float* __restrict__ factor, float* __restrict__ feat)
 {
     const int lane = threadIdx.x & 31, slot = lane >> 3, cg = lane & 7;
-    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int F = d.levels * HP_C;
-    for (long long base = warp0 * 4; base < P; base += nwarps * 4) {
+    // blocked assignment: a CTA walks ONE contiguous run of the (cell-sorted) order, so the texels of a small 3-D
+    // region stay in its SM's L1 from one iteration to the next (a grid-stride walk re-fetched them from L2)
+    const long long ppi = (long long)(blockDim.x >> 5) * 4;                      // points per CTA iteration
+    const long long chunk = ((P + gridDim.x - 1) / gridDim.x + ppi - 1) / ppi * ppi;
+    const long long begin = (long long)blockIdx.x * chunk, end = begin + chunk < P ? begin + chunk : P;
+    for (long long base = begin + (long long)(threadIdx.x >> 5) * 4; base < end; base += ppi) {
         const long long i = base + slot;
-        if (i >= P) continue;
+        if (i >= end) continue;
         const size_t g = order ? (size_t)__ldg(order + i) : (size_t)i;
         float c[4], scale[3];
         normalized_coords(pts, times, time_scalar, d.aabb, g, c, scale);
         for (int l = 0; l < d.levels; ++l) {
             Bilinear b;
-            float4 f = make_float4(1.f, 1.f, 1.f, 1.f);
-            f = mul4(f, sample_plane<0>(d, l, c, cg, b));
-            f = mul4(f, sample_plane<1>(d, l, c, cg, b));
-            f = mul4(f, sample_plane<2>(d, l, c, cg, b));
-            f = mul4(f, sample_plane<3>(d, l, c, cg, b));
-            f = mul4(f, sample_plane<4>(d, l, c, cg, b));
-            f = mul4(f, sample_plane<5>(d, l, c, cg, b));
+            // feature = factor * prod_{k in mask} plane_k; mask = all six planes and no factor is the reference's
+            // left-to-right product (hexplane.py:87-96)
+            float4 f = factor ? __ldg(reinterpret_cast<const float4*>(factor + g * F + l * HP_C + cg * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+            if (mask & 1) f = mul4(f, sample_plane<0>(d, l, c, cg, b));
+            if (mask & 2) f = mul4(f, sample_plane<1>(d, l, c, cg, b));
+            if (mask & 4) f = mul4(f, sample_plane<2>(d, l, c, cg, b));
+            if (mask & 8) f = mul4(f, sample_plane<3>(d, l, c, cg, b));
+            if (mask & 16) f = mul4(f, sample_plane<4>(d, l, c, cg, b));
+            if (mask & 32) f = mul4(f, sample_plane<5>(d, l, c, cg, b));
             *reinterpret_cast<float4*>(feat + g * F + l * HP_C + cg * 4) = f;
         }
     }
 }
 
-// Backward for one plane: plane-gradient scatter (128-bit vector reductions) and this lane's share of
-// the coordinate gradient (ATen grid_sampler_2d_backward).
+// Backward, pass A: sample one plane ONCE and keep, per lane (4 channels), the value and its derivatives with respect
+// to the two pixel coordinates -- v, dv/dix, dv/diy -- plus the clamped pixel coordinates.  Pass B (after the product
+// rule has turned d_feature into the plane's upstream gradient gv) rebuilds offsets and weights from (ix, iy) alone,
+// scatters gv into the four texels with 128-bit vector reductions and finishes the coordinate gradient as two dot
+// products.  Compared with re-sampling the plane in pass B this halves the texel gathers (6.1 KB instead of 12.3 KB
+// per point) and drops the second bilinear set-up.
+struct PlaneSample { float4 v, dx, dy; float ix, iy; };
+
 template <int K>
-__device__ __forceinline__ void plane_backward(const b200gs_hexplane_desc& d, int l, const float c[4], int cg,
-                                               const float4 gv, float gc[3])
+__device__ __forceinline__ void sample_plane_full(const b200gs_hexplane_desc& d, int l, const float c[4], int cg, PlaneSample& s)
 {
-    const Bilinear b = bilinear_setup(c[Pair<K>::a], c[Pair<K>::b], d.res[l][Pair<K>::a], d.res[l][Pair<K>::b]);
+    const int W = d.res[l][Pair<K>::a], H = d.res[l][Pair<K>::b];
+    const Bilinear b = bilinear_setup(c[Pair<K>::a], c[Pair<K>::b], W, H);
     const float* plane = d.plane[l][K];
-    float* gp = d.grad_plane[l][K];
     const float4 nw = ld4(plane, b.o_nw, cg), ne = ld4(plane, b.o_ne, cg), sw = ld4(plane, b.o_sw, cg), se = ld4(plane, b.o_se, cg);
-    if (gp != nullptr && (gv.x != 0.f || gv.y != 0.f || gv.z != 0.f || gv.w != 0.f)) {
-        if (b.o_nw >= 0) red_add_v4(gp + (size_t)b.o_nw * HP_C + cg * 4, gv.x * b.w_nw, gv.y * b.w_nw, gv.z * b.w_nw, gv.w * b.w_nw);
-        if (b.o_ne >= 0) red_add_v4(gp + (size_t)b.o_ne * HP_C + cg * 4, gv.x * b.w_ne, gv.y * b.w_ne, gv.z * b.w_ne, gv.w * b.w_ne);
-        if (b.o_sw >= 0) red_add_v4(gp + (size_t)b.o_sw * HP_C + cg * 4, gv.x * b.w_sw, gv.y * b.w_sw, gv.z * b.w_sw, gv.w * b.w_sw);
-        if (b.o_se >= 0) red_add_v4(gp + (size_t)b.o_se * HP_C + cg * 4, gv.x * b.w_se, gv.y * b.w_se, gv.z * b.w_se, gv.w * b.w_se);
-    }
+    s.v = interp4(nw, ne, sw, se, b);
     const float fx = (float)b.ix_nw, fy = (float)b.iy_nw;
     const float wx1 = (fx + 1.f) - b.ix, wx0 = b.ix - fx, wy1 = (fy + 1.f) - b.iy, wy0 = b.iy - fy;
-    auto one = [&](float vnw, float vne, float vsw, float vse, float g, float& gix, float& giy) {
-        gix += (-vnw * wy1 + vne * wy1 - vsw * wy0 + vse * wy0) * g;
-        giy += (-vnw * wx1 - vne * wx0 + vsw * wx1 + vse * wx0) * g;
-    };
-    float gix = 0.f, giy = 0.f;
-    one(nw.x, ne.x, sw.x, se.x, gv.x, gix, giy);
-    one(nw.y, ne.y, sw.y, se.y, gv.y, gix, giy);
-    one(nw.z, ne.z, sw.z, se.z, gv.z, gix, giy);
-    one(nw.w, ne.w, sw.w, se.w, gv.w, gix, giy);
-    if (Pair<K>::a < 3) gc[Pair<K>::a] += b.gx_mult * gix;
-    if (Pair<K>::b < 3) gc[Pair<K>::b] += b.gy_mult * giy;
+    s.dx = make_float4((ne.x - nw.x) * wy1 + (se.x - sw.x) * wy0, (ne.y - nw.y) * wy1 + (se.y - sw.y) * wy0,
+                       (ne.z - nw.z) * wy1 + (se.z - sw.z) * wy0, (ne.w - nw.w) * wy1 + (se.w - sw.w) * wy0);
+    if (Pair<K>::b < 3)
+        s.dy = make_float4((sw.x - nw.x) * wx1 + (se.x - ne.x) * wx0, (sw.y - nw.y) * wx1 + (se.y - ne.y) * wx0,
+                           (sw.z - nw.z) * wx1 + (se.z - ne.z) * wx0, (sw.w - nw.w) * wx1 + (se.w - ne.w) * wx0);
+    s.ix = b.ix; s.iy = b.iy;
 }
 
-__global__ void __launch_bounds__(256, 2)
+// Offset (floats) of the 1-D gradient row of time plane (a, t) of level l inside one replica of the row scratch.
+__device__ __host__ __forceinline__ size_t time_row_offset(const b200gs_hexplane_desc& d, int l, int a)
+{
+    size_t o = 0;
+    for (int ll = 0; ll < l; ++ll) o += (size_t)(d.res[ll][0] + d.res[ll][1] + d.res[ll][2]);
+    for (int aa = 0; aa < a; ++aa) o += (size_t)d.res[l][aa];
+    return o * HP_C;
+}
+__device__ __host__ __forceinline__ size_t time_row_floats(const b200gs_hexplane_desc& d) { return time_row_offset(d, d.levels, 0); }
+
+template <int K>
+__device__ __forceinline__ void plane_backward_full(const b200gs_hexplane_desc& d, int l, int cg, const PlaneSample& s,
+                                                    const float4 gv, float gc[3], float* __restrict__ rows)
+{
+    const int W = d.res[l][Pair<K>::a], H = d.res[l][Pair<K>::b];
+    float* gp = d.grad_plane[l][K];
+    const float fx = floorf(s.ix), fy = floorf(s.iy);
+    const int ixn = (int)fx, iyn = (int)fy;
+    if (Pair<K>::b == 3 && rows != nullptr) {
+        // The whole launch shares one timestamp, so every point hits the same two rows of this plane: 4 M reductions onto
+        // a few hundred 128-byte lines serialise in L2.  Reduce along x only, into this CTA's replica of a 1-D row
+        // (weights wx1 / wx0); hexplane_time_rows_flush then adds wy1 / wy0 times the replica sum to the two plane rows.
+        if (gp != nullptr && (gv.x != 0.f || gv.y != 0.f || gv.z != 0.f || gv.w != 0.f)) {
+            const float wx1 = (fx + 1.f) - s.ix, wx0 = s.ix - fx;
+            float* base = rows + time_row_offset(d, l, Pair<K>::a) + (size_t)ixn * HP_C + cg * 4;
+            red_add_v4(base, gv.x * wx1, gv.y * wx1, gv.z * wx1, gv.w * wx1);
+            if (ixn + 1 < W) red_add_v4(base + HP_C, gv.x * wx0, gv.y * wx0, gv.z * wx0, gv.w * wx0);
+        }
+    } else
+    if (gp != nullptr && (gv.x != 0.f || gv.y != 0.f || gv.z != 0.f || gv.w != 0.f)) {
+        const float wx1 = (fx + 1.f) - s.ix, wx0 = s.ix - fx, wy1 = (fy + 1.f) - s.iy, wy0 = s.iy - fy;
+        const float w_nw = wx1 * wy1, w_ne = wx0 * wy1, w_sw = wx1 * wy0, w_se = wx0 * wy0;
+        const bool x1 = ixn + 1 < W, y1 = iyn + 1 < H;            // (ixn, iyn) itself is always inside: the coordinates are clamped
+        float* base = gp + ((size_t)iyn * W + ixn) * HP_C + cg * 4;
+        red_add_v4(base, gv.x * w_nw, gv.y * w_nw, gv.z * w_nw, gv.w * w_nw);
+        if (x1) red_add_v4(base + HP_C, gv.x * w_ne, gv.y * w_ne, gv.z * w_ne, gv.w * w_ne);
+        if (y1) red_add_v4(base + (size_t)W * HP_C, gv.x * w_sw, gv.y * w_sw, gv.z * w_sw, gv.w * w_sw);
+        if (x1 && y1) red_add_v4(base + (size_t)(W + 1) * HP_C, gv.x * w_se, gv.y * w_se, gv.z * w_se, gv.w * w_se);
+    }
+    // clip_coordinates_set_grad: the coordinate gradient vanishes where the border clamp is active
+    if (Pair<K>::a < 3) {
+        const float mult = (s.ix <= 0.f || s.ix >= (float)(W - 1)) ? 0.f : (float)(W - 1) / 2;
+        gc[Pair<K>::a] += mult * (gv.x * s.dx.x + gv.y * s.dx.y + gv.z * s.dx.z + gv.w * s.dx.w);
+    }
+    if (Pair<K>::b < 3) {
+        const float mult = (s.iy <= 0.f || s.iy >= (float)(H - 1)) ? 0.f : (float)(H - 1) / 2;
+        gc[Pair<K>::b] += mult * (gv.x * s.dy.x + gv.y * s.dy.y + gv.z * s.dy.z + gv.w * s.dy.w);
+    }
+}
+
+__global__ void __launch_bounds__(128, 3)
 hexplane_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, long long P, const float* __restrict__ pts,
                     const unsigned int* __restrict__ order, const float* __restrict__ times, float time_scalar,
-                    const float* __restrict__ dfeat, float* __restrict__ dpts /* [P,3], written */)
+                    int mask, const float* __restrict__ factor, float* __restrict__ dfactor /* [P,F], accumulated, or null */,
+                    const float* __restrict__ dfeat, float* __restrict__ dpts /* [P,3], written */,
+                    float* __restrict__ time_rows /* [replicas][time_row_floats], or null */, int replicas)
 {
+    float* rows = time_rows ? time_rows + (size_t)(blockIdx.x % replicas) * time_row_floats(d) : nullptr;
     const int lane = threadIdx.x & 31, slot = lane >> 3, cg = lane & 7;
-    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int F = d.levels * HP_C;
-    for (long long base = warp0 * 4; base < P; base += nwarps * 4) {
+    const long long ppi = (long long)(blockDim.x >> 5) * 4;                      // blocked assignment, see the forward
+    const long long chunk = ((P + gridDim.x - 1) / gridDim.x + ppi - 1) / ppi * ppi;
+    const long long begin = (long long)blockIdx.x * chunk, end = begin + chunk < P ? begin + chunk : P;
+    for (long long base = begin + (long long)(threadIdx.x >> 5) * 4; base < end; base += ppi) {
         const long long i = base + slot;
-        const bool valid = i < P;
+        const bool valid = i < end;
         const size_t g = valid ? (order ? (size_t)__ldg(order + i) : (size_t)i) : 0;
         float c[4], scale[3];
         normalized_coords(pts, times, time_scalar, d.aabb, g, c, scale);
         float gc[3] = {0.f, 0.f, 0.f};
         if (valid) {
             for (int l = 0; l < d.levels; ++l) {
-                Bilinear b;
-                float4 v[6];
-                v[0] = sample_plane<0>(d, l, c, cg, b); v[1] = sample_plane<1>(d, l, c, cg, b);
-                v[2] = sample_plane<2>(d, l, c, cg, b); v[3] = sample_plane<3>(d, l, c, cg, b);
-                v[4] = sample_plane<4>(d, l, c, cg, b); v[5] = sample_plane<5>(d, l, c, cg, b);
-                const float4 go = __ldg(reinterpret_cast<const float4*>(dfeat + g * F + l * HP_C + cg * 4));
-                float4 pre[6], suf[6];
-                pre[0] = make_float4(1.f, 1.f, 1.f, 1.f);
-#pragma unroll
-                for (int k = 1; k < 6; ++k) pre[k] = make_float4(pre[k - 1].x * v[k - 1].x, pre[k - 1].y * v[k - 1].y, pre[k - 1].z * v[k - 1].z, pre[k - 1].w * v[k - 1].w);
-                suf[5] = make_float4(1.f, 1.f, 1.f, 1.f);
-#pragma unroll
-                for (int k = 4; k >= 0; --k) suf[k] = make_float4(suf[k + 1].x * v[k + 1].x, suf[k + 1].y * v[k + 1].y, suf[k + 1].z * v[k + 1].z, suf[k + 1].w * v[k + 1].w);
-                auto gvk = [&](int k) { return make_float4(go.x * pre[k].x * suf[k].x, go.y * pre[k].y * suf[k].y, go.z * pre[k].z * suf[k].z, go.w * pre[k].w * suf[k].w); };
-                plane_backward<0>(d, l, c, cg, gvk(0), gc); plane_backward<1>(d, l, c, cg, gvk(1), gc);
-                plane_backward<2>(d, l, c, cg, gvk(2), gc); plane_backward<3>(d, l, c, cg, gvk(3), gc);
-                plane_backward<4>(d, l, c, cg, gvk(4), gc); plane_backward<5>(d, l, c, cg, gvk(5), gc);
+                const float4 gout = __ldg(reinterpret_cast<const float4*>(dfeat + g * F + l * HP_C + cg * 4));
+                auto mul = [](const float4 a, const float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); };
+                // planes outside `mask` count as the constant 1 (their factor arrives through `factor` instead)
+                const float4 ones = make_float4(1.f, 1.f, 1.f, 1.f);
+                PlaneSample s0, s1, s2, s3, s4, s5;
+                s0.v = s1.v = s2.v = s3.v = s4.v = s5.v = ones;
+                if (mask & 1) sample_plane_full<0>(d, l, c, cg, s0);
+                if (mask & 2) sample_plane_full<1>(d, l, c, cg, s1);
+                if (mask & 4) sample_plane_full<2>(d, l, c, cg, s2);
+                if (mask & 8) sample_plane_full<3>(d, l, c, cg, s3);
+                if (mask & 16) sample_plane_full<4>(d, l, c, cg, s4);
+                if (mask & 32) sample_plane_full<5>(d, l, c, cg, s5);
+                const float4 go = factor ? mul(gout, __ldg(reinterpret_cast<const float4*>(factor + g * F + l * HP_C + cg * 4))) : gout;
+                // prefix / suffix products of the six factors (the forward multiplies left to right)
+                const float4 p1 = s0.v, p2 = mul(p1, s1.v), p3 = mul(p2, s2.v), p4 = mul(p3, s3.v), p5 = mul(p4, s4.v);
+                const float4 q4 = s5.v, q3 = mul(q4, s4.v), q2 = mul(q3, s3.v), q1 = mul(q2, s2.v), q0 = mul(q1, s1.v);
+                if (mask & 1) plane_backward_full<0>(d, l, cg, s0, mul(go, q0), gc, rows);
+                if (mask & 2) plane_backward_full<1>(d, l, cg, s1, mul(go, mul(p1, q1)), gc, rows);
+                if (mask & 4) plane_backward_full<2>(d, l, cg, s2, mul(go, mul(p2, q2)), gc, rows);
+                if (mask & 8) plane_backward_full<3>(d, l, cg, s3, mul(go, mul(p3, q3)), gc, rows);
+                if (mask & 16) plane_backward_full<4>(d, l, cg, s4, mul(go, mul(p4, q4)), gc, rows);
+                if (mask & 32) plane_backward_full<5>(d, l, cg, s5, mul(go, p5), gc, rows);
+                if (dfactor) {                       // d factor += d feature * prod_{k in mask} plane_k
+                    float4* da = reinterpret_cast<float4*>(dfactor + g * F + l * HP_C + cg * 4);
+                    const float4 prod = mul(p5, s5.v), old = *da;
+                    *da = make_float4(old.x + gout.x * prod.x, old.y + gout.y * prod.y, old.z + gout.z * prod.z, old.w + gout.w * prod.w);
+                }
             }
         }
         if (dpts != nullptr) {
@@ -234,6 +298,36 @@ hexplane_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, long long P,
             if (valid && cg < 3) dpts[3 * g + cg] = cg == 0 ? gc[0] : (cg == 1 ? gc[1] : gc[2]);
         }
     }
+}
+
+// Adds the replica-summed 1-D rows to the two time rows of every time plane: G[t0][x] += wy1 * r[x], G[t1][x] += wy0 * r[x].
+__global__ void __launch_bounds__(256)
+hexplane_time_rows_flush_kernel(const __grid_constant__ b200gs_hexplane_desc d, float time_scalar, const float* __restrict__ rows, int replicas)
+{
+    const size_t total = time_row_floats(d);
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    int l = 0, a = 0;
+    size_t rem = i / HP_C;                                   // texel index over all (level, axis) rows
+    for (;; ) {
+        const size_t n = (size_t)d.res[l][a];
+        if (rem < n) break;
+        rem -= n;
+        if (++a == 3) { a = 0; ++l; }
+    }
+    const int K = a == 0 ? 2 : (a == 1 ? 4 : 5), ch = (int)(i % HP_C), x = (int)rem;
+    float* gp = d.grad_plane[l][K];
+    if (gp == nullptr) return;
+    float sum = 0.f;
+    for (int r = 0; r < replicas; ++r) sum += rows[(size_t)r * total + i];
+    const int W = d.res[l][a], H = d.res[l][3];
+    float mult;
+    const float iy = unnormalize_clip(time_scalar, H, mult);
+    const float fy = floorf(iy);
+    const int iyn = (int)fy;
+    const float wy1 = (fy + 1.f) - iy, wy0 = iy - fy;
+    gp[((size_t)iyn * W + x) * HP_C + ch] += sum * wy1;
+    if (iyn + 1 < H) gp[((size_t)(iyn + 1) * W + x) * HP_C + ch] += sum * wy0;
 }
 
 // ---- cell order: a permutation of the points sorted by an 8-bit-per-axis Morton code of their
@@ -381,23 +475,63 @@ int b200gs_hexplane_order(long long P, const float* pts, const float* aabb, unsi
     return check_launch("hexplane_order");
 }
 
-int b200gs_hexplane_forward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
-                            const float* times, float time_scalar, float* features, b200gs_stream_t stream)
+int b200gs_hexplane_forward_masked(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
+                                   const float* times, float time_scalar, int plane_mask, const float* factor, float* features,
+                                   b200gs_stream_t stream)
 {
     if (validate(desc)) return -1;
     if (P <= 0) return 0;
-    hexplane_fwd_kernel<<<grid_for(P), 256, 0, (cudaStream_t)stream>>>(*desc, P, pts, order, times, time_scalar, features);
+    hexplane_fwd_kernel<<<grid_for(P), 256, 0, (cudaStream_t)stream>>>(*desc, P, pts, order, times, time_scalar, plane_mask & 63, factor, features);
     return check_launch("hexplane_forward");
+}
+
+int b200gs_hexplane_forward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
+                            const float* times, float time_scalar, float* features, b200gs_stream_t stream)
+{
+    return b200gs_hexplane_forward_masked(desc, P, pts, order, times, time_scalar, 63, nullptr, features, stream);
+}
+
+int b200gs_hexplane_backward_masked(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
+                                    const float* times, float time_scalar, int plane_mask, const float* factor, float* d_factor_accum,
+                                    const float* d_features, float* d_pts, void* time_row_scratch, size_t time_row_scratch_bytes,
+                                    b200gs_stream_t stream)
+{
+    if (validate(desc)) return -1;
+    if (P <= 0) return 0;
+    // uniform-time fast path for the time planes' gradient: needs one shared timestamp (times == null) and scratch
+    float* rows = nullptr;
+    int replicas = 0;
+    if (times == nullptr && time_row_scratch != nullptr && (plane_mask & 0x34)) {
+        const size_t per = time_row_floats(*desc) * sizeof(float);
+        replicas = (int)(time_row_scratch_bytes / per);
+        if (replicas > 64) replicas = 64;
+        if (replicas >= 1) {
+            rows = (float*)time_row_scratch;
+            cudaMemsetAsync(rows, 0, per * replicas, (cudaStream_t)stream);
+        }
+    }
+    long long blocks = (P + 15) / 16;                // 4 warps x 4 point slots per block, 3 blocks resident per SM (170 registers)
+    if (blocks > (long long)NUM_SMS * 12) blocks = (long long)NUM_SMS * 12;
+    hexplane_bwd_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(*desc, P, pts, order, times, time_scalar, plane_mask & 63, factor,
+                                                                            d_factor_accum, d_features, d_pts, rows, replicas);
+    if (rows) {
+        const size_t total = time_row_floats(*desc);
+        hexplane_time_rows_flush_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*desc, time_scalar, rows, replicas);
+    }
+    return check_launch("hexplane_backward");
+}
+
+size_t b200gs_hexplane_time_row_scratch_bytes(const b200gs_hexplane_desc* desc, int replicas)
+{
+    if (!desc || desc->levels < 1 || desc->levels > HP_MAXL || replicas < 1) return 0;
+    return time_row_floats(*desc) * sizeof(float) * (size_t)replicas;
 }
 
 int b200gs_hexplane_backward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
                              const float* times, float time_scalar, const float* d_features, float* d_pts,
                              b200gs_stream_t stream)
 {
-    if (validate(desc)) return -1;
-    if (P <= 0) return 0;
-    hexplane_bwd_kernel<<<grid_for(P), 256, 0, (cudaStream_t)stream>>>(*desc, P, pts, order, times, time_scalar, d_features, d_pts);
-    return check_launch("hexplane_backward");
+    return b200gs_hexplane_backward_masked(desc, P, pts, order, times, time_scalar, 63, nullptr, nullptr, d_features, d_pts, nullptr, 0, stream);
 }
 
 int b200gs_hexplane_regulation(const b200gs_hexplane_desc* desc, float plane_tv_weight, float time_smoothness_weight,

@@ -200,6 +200,24 @@ int b200gs_deform_mlp_backward(const b200gs_mlp_weights* w /* host */, const b20
                                long long P, const float* features, const float* saved, const float* d_pts,
                                const float* d_scales, const float* d_rot, float* d_features, b200gs_stream_t stream);
 
+/* Plane-subset variants: features = factor * prod_{k in plane_mask} plane_k (bit k of plane_mask = plane k; factor may be
+ * null = 1).  With the spatial planes (0,1,3: mask 0x0B) evaluated once per optimiser step and handed back as `factor`,
+ * each view of a multi-view batch only samples the time planes (2,4,5: mask 0x34): the Gaussians' xyz do not change
+ * within a step, so the spatial product is shared by all its views.  The backward additionally ACCUMULATES
+ * d_factor_accum[P,F] += d_features * prod_{k in plane_mask} plane_k (null = skip), which is the upstream gradient of the
+ * deferred spatial pass.  mask 0x3F with null factor is exactly b200gs_hexplane_forward / _backward. */
+int b200gs_hexplane_forward_masked(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
+                                   const float* times, float time_scalar, int plane_mask, const float* factor, float* features,
+                                   b200gs_stream_t stream);
+int b200gs_hexplane_backward_masked(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
+                                    const float* times, float time_scalar, int plane_mask, const float* factor, float* d_factor_accum,
+                                    const float* d_features, float* d_pts, void* time_row_scratch, size_t time_row_scratch_bytes,
+                                    b200gs_stream_t stream);
+/* Optional scratch for the backward above when the whole launch shares ONE timestamp (times == null): the time planes'
+ * gradient is then reduced along x into up to 64 replicas of a 1-D row per plane (so the few hundred hot 128-byte lines of
+ * the two touched time rows do not serialise in L2) and added to the planes by a small follow-up kernel. null = classic path. */
+size_t b200gs_hexplane_time_row_scratch_bytes(const b200gs_hexplane_desc* desc, int replicas);
+
 /* HexPlane regulariser, value and gradient in one pass (scene/gaussian_model.py:730-769 compute_regulation;
  * scene/regulation.py:22-28 compute_plane_smoothness): per level
  *   plane_tv_weight * sum_{k in 0,1,3} S(G_k) + time_smoothness_weight * sum_{k in 2,4,5} S(G_k)
