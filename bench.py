@@ -95,10 +95,12 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {"hexplane_bwd_kernel": 351.5e6, "deform_mlp_bwd_tc5_kernel": 1563.8e6, "deform_mlp_fwd_tc5v2_kernel": 1320.4e6}
+NCU_TRAFFIC = {"hexplane_bwd_kernel": 348.4e6, "deform_mlp_bwd_tc5_kernel": 1563.8e6, "deform_mlp_fwd_tc5v2_kernel": 1320.4e6}
 ROOFLINE_NOTES = {
-    "hexplane_bwd_kernel": "algorithmic HBM bytes only (xyz, order, d_feature in; d_xyz, plane gradients out); the 12.3 KB/point of "
-                           "plane texel gathers + vector REDs are served by L1/L2 (planes are 11.6 MB), which is what bounds this kernel",
+    "hexplane_bwd_kernel": "average over the step's V time-plane passes and its one spatial pass; algorithmic HBM bytes only (xyz, order, "
+                           "d_feature, shared spatial product in; d_xyz, its gradient accumulator, plane gradients out); the 3 KB/point/pass of "
+                           "plane texel gathers + vector REDs are served by L1/L2 (planes are 11.6 MB), which is what bounds this kernel; "
+                           "traffic = ncu dram bytes of the full six-plane launch",
     "hexplane_fwd_kernel": "plane texel gathers (6.1 KB/point) are L1/L2 traffic, not HBM",
 }
 
@@ -423,6 +425,19 @@ def _main():
             return None
     gts_dev = [g.to(device, non_blocking=True) for g in gts_host]
     V = len(cams)
+    pairs_per_view = None
+    if impl == "b200":
+        # evaluated (pixel, Gaussian) pairs = sum of n_contrib, counted once, outside the timed region
+        from b200gs import engine as _eng
+        from b200gs.rasterizer import _C as _rc
+        with torch.no_grad():
+            pk0 = _eng.render(cams[0], model, torch.zeros(3, device=device), stage="fine")
+        try:
+            sv = _eng.LAST_RASTER_STATE
+            nc = _rc.export_state("n_contrib", args.points, sv[0], args.width, args.height, sv[1], sv[2], sv[3])
+            pairs_per_view = int(nc.view(torch.int32).to(torch.int64).sum())
+        except Exception:
+            pairs_per_view = None
 
     def barrier():
         if world > 1:
@@ -515,6 +530,10 @@ def _main():
         "b200gs_adam_multi": ("adam_multi_kernel", adam_bytes),
         "b200gs_hexplane_forward": ("hexplane_fwd_kernel", P_ * (12 + 4 + 4 * F_)),
         "b200gs_hexplane_backward": ("hexplane_bwd_kernel", P_ * (12 + 4 + 4 * F_ + 12) + 4 * plane_params),
+        # shared-spatial step: V time-plane passes (factor S in, d(S) accumulated) + one spatial pass per optimiser step
+        "b200gs_hexplane_forward_masked": ("hexplane_fwd_kernel", (V * P_ * (12 + 4 + 4 * F_ + 4 * F_) + P_ * (12 + 4 + 4 * F_)) / (V + 1)),
+        "b200gs_hexplane_backward_masked": ("hexplane_bwd_kernel", (V * P_ * (12 + 4 + 4 * F_ + 4 * F_ + 8 * F_ + 12)
+                                                                     + P_ * (12 + 4 + 4 * F_ + 12) + 4 * plane_params) / (V + 1)),
         "b200gs_deform_mlp_forward": ("deform_mlp_fwd_tc5v2_kernel", P_ * (4 * F_ + 52 + 4 * 4 * 64 + 40)),
         "b200gs_deform_mlp_backward": ("deform_mlp_bwd_tc5_kernel", P_ * (4 * 4 * 64 + 4 * F_ + 40 + 4 * F_)),
         "b200gs_activations_forward": ("activations_fwd_kernel", P_ * 64),
@@ -530,7 +549,15 @@ def _main():
             row.update({"kernel": kname, "bound": "hbm", "algorithmic_bytes_per_launch": nbytes, "achieved_gbs": round(gbs, 1),
                         "frac_of_measured_hbm_peak": round(gbs / hbm, 4)})
         kernels.append(row)
-    single = [k for k in kernels if "kernel" in k]
+    if pairs_per_view:
+        # compositing is FP32-issue bound: SURVEY.md 8d cost model (reference SASS) = 85 FP32 lane-instructions per evaluated
+        # pair in the backward; peak = 148 SMs x 128 lanes x 1.965 GHz. The entry also contains preprocess_bwd (HBM-bound, ~15 %).
+        for row in kernels:
+            if row["entry"] == "b200gs_rast_backward":
+                rate = pairs_per_view * 85 / (row["ms_avg"] * 1e-3)
+                row.update({"kernel": "composite_bwd_kernel (+ preprocess_bwd_kernel)", "bound": "fp32-issue", "pairs_per_launch": pairs_per_view,
+                            "achieved_lane_instr_per_s": rate, "frac_of_fp32_peak_on_reference_cost_model": round(rate / (148 * 128 * 1.965e9), 4)})
+    single = [k for k in kernels if "frac_of_measured_hbm_peak" in k]
     dom = single[0] if single else None
     tensors = len(trainer.trainable)
     launches_per_step = None

@@ -99,6 +99,9 @@ class GaussianState(nn.Module):
         return self.optimizer
 
 
+LAST_RASTER_STATE = None      # (R, geomBuffer, binningBuffer, imgBuffer) of the last no-grad render (bench.py counts pairs from it)
+
+
 def render(cam, pc, bg_color, scaling_modifier=1.0, stage="fine", delta_scale=1, debug=False, shs=None):
     """gaussian_renderer/__init__.py:22-178 for a b200gs.synthetic.SynthCamera-like `cam`.
     `shs`: optional pre-concatenated [P,16,3] SH tensor standing in for `pc.get_features` (the trainer
@@ -127,6 +130,9 @@ def render(cam, pc, bg_color, scaling_modifier=1.0, stage="fine", delta_scale=1,
         sc = pc.scaling_activation(sc); rt = pc.rotation_activation(rt); op = pc.opacity_activation(op)
     image, radii, depth = rasterizer(means3D=m3, means2D=screenspace_points, shs=sh, colors_precomp=None,
                                      opacities=op, scales=sc, rotations=rt, cov3D_precomp=None)
+    if not torch.is_grad_enabled():
+        global LAST_RASTER_STATE
+        LAST_RASTER_STATE = getattr(rasterizer, "last_state", None)
     return {"render": image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii,
             "depth": depth}
 

@@ -267,5 +267,14 @@ class GaussianRasterizer(nn.Module):
             rotations = torch.Tensor([])
         if cov3D_precomp is None:
             cov3D_precomp = torch.Tensor([])
+        if not torch.is_grad_enabled():
+            # inference: keep the opaque state buffers reachable for debugging / statistics (export_state)
+            args = (raster_settings.bg, means3D, colors_precomp, opacities, scales, rotations, raster_settings.scale_modifier,
+                    cov3D_precomp, raster_settings.viewmatrix, raster_settings.projmatrix, raster_settings.tanfovx,
+                    raster_settings.tanfovy, raster_settings.image_height, raster_settings.image_width, shs,
+                    raster_settings.sh_degree, raster_settings.campos, raster_settings.prefiltered, raster_settings.debug)
+            R, color, depth, radii, geom, binning, img = _C.rasterize_gaussians(*args)
+            self.last_state = (R, geom, binning, img)
+            return color, radii, depth
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
                                    cov3D_precomp, raster_settings)
