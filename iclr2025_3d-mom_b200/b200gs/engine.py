@@ -173,7 +173,9 @@ class ViewParallelTrainer:
         # over NVLink/NVSwitch) reduces everything. Parameters outside it keep grad None and the
         # optimiser skips them, as torch does in the reference.
         self.trainable = [p for n, p in model.named_parameters() if p.requires_grad and _receives_grad(n, stage)]
-        n = sum(p.numel() for p in self.trainable) + 3 * P
+        # every slice starts on a 256-byte boundary: the kernels use 128-bit loads / vector reductions on them
+        al = lambda x: (x + 63) // 64 * 64
+        n = sum(al(p.numel()) for p in self.trainable) + al(3 * P)
         self.arena = torch.zeros(n, dtype=torch.float32, device=model.get_xyz.device)
         self.views, off = [], 0
         for p in self.trainable:
@@ -184,7 +186,7 @@ class ViewParallelTrainer:
             else:
                 v = flat.view(p.shape)
             self.views.append(v)
-            off += p.numel()
+            off += al(p.numel())
         self.viewspace_grad = self.arena[off:off + 3 * P].view(P, 3)
         self.max_radii = torch.zeros(P, dtype=torch.int32, device=self.arena.device)
 
