@@ -55,6 +55,11 @@ _lib.register("b200gs_hexplane_forward_masked", ctypes.c_int,
 _lib.register("b200gs_hexplane_backward_masked", ctypes.c_int,
               [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, _P, ctypes.c_float, ctypes.c_int, _P, _P, _P, _P, _P, ctypes.c_size_t, _P])
 _lib.register("b200gs_hexplane_time_row_scratch_bytes", ctypes.c_size_t, [ctypes.POINTER(_HexDesc), ctypes.c_int])
+_lib.register("b200gs_hexplane_time_supported", ctypes.c_int, [ctypes.POINTER(_HexDesc)])
+_lib.register("b200gs_hexplane_time_forward", ctypes.c_int,
+              [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, ctypes.c_float, _P, _P, _P])
+_lib.register("b200gs_hexplane_time_backward", ctypes.c_int,
+              [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, ctypes.c_float, _P, _P, _P, _P, _P, ctypes.c_size_t, _P])
 _ROW_SCRATCH = {}
 TIME_ROW_REPLICAS = 64
 
@@ -292,7 +297,16 @@ class _DeformFn(torch.autograd.Function):
         ctx.order = order
         sh = _shared_for(xyz, P)
         ctx.shared = sh
-        if sh is not None:        # spatial product from begin_shared_step; only the time planes are sampled per view
+        ctx.time_rows = False
+        if sh is not None and tt is None and L.b200gs_hexplane_time_supported(ctypes.byref(d)):
+            # shared spatial product + one timestamp for the view: time planes served from shared memory
+            sh["used"] = True
+            ctx.time_rows = True
+            # (no cell order here: with the rows in shared memory there is no texel locality to gain, and walking the points in
+            #  storage order keeps the S / feature rows streaming)
+            check(L.b200gs_hexplane_time_forward(ctypes.byref(d), P, xyz.data_ptr(), None, ts, sh["S"].data_ptr(),
+                                                 feat.data_ptr(), stream), "hexplane_time_forward")
+        elif sh is not None:      # spatial product from begin_shared_step; only the time planes are sampled per view
             sh["used"] = True
             check(L.b200gs_hexplane_forward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(order),
                                                    tt.data_ptr() if tt is not None else None, ts, MASK_TIME, sh["S"].data_ptr(),
@@ -362,7 +376,12 @@ class _DeformFn(torch.autograd.Function):
         d_xyz_grid = torch.empty_like(xyz)
         d = _hex_desc(aabb, planes, levels, res, gplanes)
         sh = ctx.shared
-        if sh is not None or not has_t:
+        if ctx.time_rows:
+            scratch, nbytes = _time_row_scratch(d, xyz.device)
+            check(L.b200gs_hexplane_time_backward(ctypes.byref(d), P, xyz.data_ptr(), None, ts, sh["S"].data_ptr(),
+                                                  sh["A"].data_ptr(), d_feat.data_ptr(), d_xyz_grid.data_ptr(), scratch.data_ptr(),
+                                                  nbytes, stream), "hexplane_time_backward")
+        elif sh is not None or not has_t:
             # shared step: time planes now, the spatial planes' share is accumulated for finish_shared_step.
             # One timestamp for the whole launch (scalar time): the time planes' gradient goes through replicated 1-D rows.
             scratch, nbytes = _time_row_scratch(d, xyz.device) if not has_t else (None, 0)

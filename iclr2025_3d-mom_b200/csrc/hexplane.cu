@@ -330,6 +330,166 @@ hexplane_time_rows_flush_kernel(const __grid_constant__ b200gs_hexplane_desc d, 
     if (iyn + 1 < H) gp[((size_t)(iyn + 1) * W + x) * HP_C + ch] += sum * wy0;
 }
 
+
+// ---- time planes of a one-timestamp launch, served from shared memory ------------------------------------------------
+// With the spatial-plane product S shared by the views of a step (see the *_masked variants), a view only needs the
+// three time planes (x,t), (y,t), (z,t) of every level -- and the whole view has ONE t.  Each CTA therefore pre-blends
+// the two touched time rows of every time plane into a 1-D row  R[x] = wy1 G[t0][x] + wy0 G[t1][x]  in shared memory
+// (73.7 KB for the reference's 2-level / 64-128 resolution field).  Sampling becomes a 1-D lerp with no global texel
+// traffic at all; the backward accumulates the row gradient in shared memory and adds it to the two plane rows once per
+// CTA.  Per point the kernels move only xyz, S, the feature / its gradient and d(S): they are HBM-bound.
+struct TimeRowSetup { int off[HP_MAXL][3]; int total; };     // float offsets of row (level, axis) inside the row buffer
+
+__device__ __forceinline__ void time_rows_prepare(const b200gs_hexplane_desc& d, float t, float* __restrict__ R, const TimeRowSetup& ts)
+{
+    for (int l = 0; l < d.levels; ++l) {
+        float mult;
+        const int H = d.res[l][3];
+        const float iy = unnormalize_clip(t, H, mult);
+        const float fy = floorf(iy);
+        const int iyn = (int)fy;
+        const float wy1 = (fy + 1.f) - iy, wy0 = iy - fy;
+        const bool y1 = iyn + 1 < H;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int K = a == 0 ? 2 : (a == 1 ? 4 : 5), W = d.res[l][a];
+            const float* g0 = d.plane[l][K] + (size_t)iyn * W * HP_C;
+            const float* g1 = g0 + (size_t)W * HP_C;
+            // 128-bit loads, four in flight per thread: this runs before every CTA's main loop, so its latency is exposed
+#pragma unroll 4
+            for (int i = threadIdx.x; i < W * (HP_C / 4); i += blockDim.x) {
+                const float4 p0 = __ldg(reinterpret_cast<const float4*>(g0) + i);
+                const float4 p1 = y1 ? __ldg(reinterpret_cast<const float4*>(g1) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                reinterpret_cast<float4*>(R + ts.off[l][a])[i] =
+                    make_float4(__fmaf_rn(p1.x, wy0, __fmul_rn(p0.x, wy1)), __fmaf_rn(p1.y, wy0, __fmul_rn(p0.y, wy1)),
+                                __fmaf_rn(p1.z, wy0, __fmul_rn(p0.z, wy1)), __fmaf_rn(p1.w, wy0, __fmul_rn(p0.w, wy1)));
+            }
+        }
+    }
+}
+
+struct RowSample { float4 v, dv; float wx0, wx1, mult; int x0, x1; };
+
+__device__ __forceinline__ RowSample row_sample(const float* __restrict__ row, float coord, int W, int cg)
+{
+    RowSample r;
+    const float ix = unnormalize_clip(coord, W, r.mult);
+    const float fx = floorf(ix);
+    r.x0 = (int)fx;
+    r.x1 = r.x0 + 1 < W ? r.x0 + 1 : r.x0;          // out of range on the right edge: its weight is exactly 0
+    r.wx1 = (fx + 1.f) - ix; r.wx0 = ix - fx;
+    const float4 a = *reinterpret_cast<const float4*>(row + r.x0 * HP_C + cg * 4);
+    const float4 b = *reinterpret_cast<const float4*>(row + r.x1 * HP_C + cg * 4);
+    r.v = make_float4(__fmaf_rn(b.x, r.wx0, __fmul_rn(a.x, r.wx1)), __fmaf_rn(b.y, r.wx0, __fmul_rn(a.y, r.wx1)),
+                      __fmaf_rn(b.z, r.wx0, __fmul_rn(a.z, r.wx1)), __fmaf_rn(b.w, r.wx0, __fmul_rn(a.w, r.wx1)));
+    r.dv = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, b.w - a.w);
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+hexplane_time_fwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const __grid_constant__ TimeRowSetup ts, long long P,
+                         const float* __restrict__ pts, const unsigned int* __restrict__ order, float t,
+                         const float* __restrict__ factor, float* __restrict__ feat)
+{
+    extern __shared__ float R[];
+    time_rows_prepare(d, t, R, ts);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, slot = lane >> 3, cg = lane & 7;
+    const int F = d.levels * HP_C;
+    const long long ppi = (long long)(blockDim.x >> 5) * 4;
+    const long long chunk = ((P + gridDim.x - 1) / gridDim.x + ppi - 1) / ppi * ppi;
+    const long long begin = (long long)blockIdx.x * chunk, end = begin + chunk < P ? begin + chunk : P;
+    for (long long base = begin + (long long)(threadIdx.x >> 5) * 4; base < end; base += ppi) {
+        const long long i = base + slot;
+        if (i >= end) continue;
+        const size_t g = order ? (size_t)__ldg(order + i) : (size_t)i;
+        float c[4], scale[3];
+        normalized_coords(pts, nullptr, t, d.aabb, g, c, scale);
+        for (int l = 0; l < d.levels; ++l) {
+            float4 f = factor ? __ldg(reinterpret_cast<const float4*>(factor + g * F + l * HP_C + cg * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) f = mul4(f, row_sample(R + ts.off[l][a], c[a], d.res[l][a], cg).v);
+            *reinterpret_cast<float4*>(feat + g * F + l * HP_C + cg * 4) = f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hexplane_time_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const __grid_constant__ TimeRowSetup ts, long long P,
+                         const float* __restrict__ pts, const unsigned int* __restrict__ order, float t,
+                         const float* __restrict__ factor, float* __restrict__ dfactor, const float* __restrict__ dfeat,
+                         float* __restrict__ dpts, float* __restrict__ time_rows /* [replicas][ts.total], zeroed */, int replicas)
+{
+    extern __shared__ float R[];
+    float* rows = time_rows + (size_t)(blockIdx.x % replicas) * ts.total;      // row gradients: this CTA's replica
+    time_rows_prepare(d, t, R, ts);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, slot = lane >> 3, cg = lane & 7;
+    const int F = d.levels * HP_C;
+    const long long ppi = (long long)(blockDim.x >> 5) * 4;
+    const long long chunk = ((P + gridDim.x - 1) / gridDim.x + ppi - 1) / ppi * ppi;
+    const long long begin = (long long)blockIdx.x * chunk, end = begin + chunk < P ? begin + chunk : P;
+    for (long long base = begin + (long long)(threadIdx.x >> 5) * 4; base < end; base += ppi) {
+        const long long i = base + slot;
+        const bool valid = i < end;
+        const size_t g = valid ? (order ? (size_t)__ldg(order + i) : (size_t)i) : 0;
+        float c[4], scale[3];
+        normalized_coords(pts, nullptr, t, d.aabb, g, c, scale);
+        float gc[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+            for (int l = 0; l < d.levels; ++l) {
+                const float4 gout = __ldg(reinterpret_cast<const float4*>(dfeat + g * F + l * HP_C + cg * 4));
+                const float4 fac = factor ? __ldg(reinterpret_cast<const float4*>(factor + g * F + l * HP_C + cg * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                RowSample r[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) r[a] = row_sample(R + ts.off[l][a], c[a], d.res[l][a], cg);
+                const float4 go = mul4(gout, fac);
+                if (dfactor) {                       // d S += d feature * T
+                    float4* da = reinterpret_cast<float4*>(dfactor + g * F + l * HP_C + cg * 4);
+                    const float4 T = mul4(mul4(r[0].v, r[1].v), r[2].v), old = *da;
+                    *da = make_float4(old.x + gout.x * T.x, old.y + gout.y * T.y, old.z + gout.z * T.z, old.w + gout.w * T.w);
+                }
+                if (go.x != 0.f || go.y != 0.f || go.z != 0.f || go.w != 0.f) {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const float4 oth = mul4(r[(a + 1) % 3].v, r[(a + 2) % 3].v);
+                        const float4 gv = mul4(go, oth);
+                        // (shared-memory float atomics are compare-and-swap loops on this architecture; the vector reductions to
+                        //  this CTA's replica of the global row buffer are native and four channels wide)
+                        float* g0 = rows + ts.off[l][a] + r[a].x0 * HP_C + cg * 4;
+                        red_add_v4(g0, gv.x * r[a].wx1, gv.y * r[a].wx1, gv.z * r[a].wx1, gv.w * r[a].wx1);
+                        if (r[a].x1 != r[a].x0) {
+                            float* g1 = rows + ts.off[l][a] + r[a].x1 * HP_C + cg * 4;
+                            red_add_v4(g1, gv.x * r[a].wx0, gv.y * r[a].wx0, gv.z * r[a].wx0, gv.w * r[a].wx0);
+                        }
+                        gc[a] += r[a].mult * (gv.x * r[a].dv.x + gv.y * r[a].dv.y + gv.z * r[a].dv.z + gv.w * r[a].dv.w);
+                    }
+                }
+            }
+        }
+        if (dpts != nullptr) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float s = gc[a];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                gc[a] = s * scale[a];
+            }
+            if (valid && cg < 3) dpts[3 * g + cg] = cg == 0 ? gc[0] : (cg == 1 ? gc[1] : gc[2]);
+        }
+    }
+}
+
+bool time_rows_setup(const b200gs_hexplane_desc& d, TimeRowSetup& ts)
+{
+    int o = 0;
+    for (int l = 0; l < d.levels; ++l)
+        for (int a = 0; a < 3; ++a) { ts.off[l][a] = o; o += d.res[l][a] * HP_C; }
+    ts.total = o;
+    return (size_t)o * sizeof(float) <= 200 * 1024;             // the pre-blended rows must fit one CTA's shared memory
+}
+
 // ---- cell order: a permutation of the points sorted by an 8-bit-per-axis Morton code of their
 // normalised position (a pure performance hint: any permutation gives the same results).
 __device__ __forceinline__ unsigned int spread8(unsigned int x)
@@ -545,6 +705,53 @@ int b200gs_hexplane_regulation(const b200gs_hexplane_desc* desc, float plane_tv_
     hexplane_regulation_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*desc, plane_tv_weight, time_smoothness_weight,
                                                                         l1_time_planes_weight, loss_accum);
     return check_launch("hexplane_regulation");
+}
+
+int b200gs_hexplane_time_supported(const b200gs_hexplane_desc* desc)
+{
+    if (validate(desc)) return 0;
+    TimeRowSetup ts;
+    return time_rows_setup(*desc, ts) ? 1 : 0;
+}
+
+int b200gs_hexplane_time_forward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
+                                 float time_scalar, const float* factor, float* features, b200gs_stream_t stream)
+{
+    if (validate(desc)) return -1;
+    TimeRowSetup ts;
+    if (!time_rows_setup(*desc, ts)) { set_error("hexplane_time_forward: time rows do not fit shared memory"); return -1; }
+    if (P <= 0) return 0;
+    const size_t smem = (size_t)ts.total * sizeof(float);
+    cudaFuncSetAttribute(hexplane_time_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    long long blocks = (P + 31) / 32;
+    const long long cap = (long long)NUM_SMS * (smem * 3 <= 220 * 1024 ? 3 : (smem * 2 <= 220 * 1024 ? 2 : 1));
+    if (blocks > cap) blocks = cap;
+    hexplane_time_fwd_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(*desc, ts, P, pts, order, time_scalar, factor, features);
+    return check_launch("hexplane_time_forward");
+}
+
+int b200gs_hexplane_time_backward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
+                                  float time_scalar, const float* factor, float* d_factor_accum, const float* d_features,
+                                  float* d_pts, void* time_row_scratch, size_t time_row_scratch_bytes, b200gs_stream_t stream)
+{
+    if (validate(desc)) return -1;
+    TimeRowSetup ts;
+    if (!time_rows_setup(*desc, ts)) { set_error("hexplane_time_backward: time rows do not fit shared memory"); return -1; }
+    if (P <= 0) return 0;
+    const size_t per = (size_t)ts.total * sizeof(float);
+    int replicas = time_row_scratch ? (int)(time_row_scratch_bytes / per) : 0;
+    if (replicas > 64) replicas = 64;
+    if (replicas < 1) { set_error("hexplane_time_backward: scratch for at least one row replica is required"); return -1; }
+    float* rows = (float*)time_row_scratch;
+    cudaMemsetAsync(rows, 0, per * replicas, (cudaStream_t)stream);
+    cudaFuncSetAttribute(hexplane_time_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per);
+    long long blocks = (P + 31) / 32;
+    const long long cap = (long long)NUM_SMS * (per * 3 <= 220 * 1024 ? 3 : (per * 2 <= 220 * 1024 ? 2 : 1));
+    if (blocks > cap) blocks = cap;
+    hexplane_time_bwd_kernel<<<(unsigned)blocks, 256, per, (cudaStream_t)stream>>>(*desc, ts, P, pts, order, time_scalar, factor, d_factor_accum,
+                                                                                   d_features, d_pts, rows, replicas);
+    hexplane_time_rows_flush_kernel<<<(unsigned)((ts.total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*desc, time_scalar, rows, replicas);
+    return check_launch("hexplane_time_backward");
 }
 
 }  // extern "C"

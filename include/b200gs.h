@@ -218,6 +218,18 @@ int b200gs_hexplane_backward_masked(const b200gs_hexplane_desc* desc, long long 
  * the two touched time rows do not serialise in L2) and added to the planes by a small follow-up kernel. null = classic path. */
 size_t b200gs_hexplane_time_row_scratch_bytes(const b200gs_hexplane_desc* desc, int replicas);
 
+/* Time planes only (mask 0x34), ONE timestamp for the whole launch, served from shared memory: every CTA pre-blends the two
+ * touched time rows of each (x,t) / (y,t) / (z,t) plane into a 1-D row, samples become 1-D lerps without global texel traffic,
+ * and the backward reduces the row gradients into replicated 1-D rows (time_row_scratch, as for the _masked variant; required). Same contract as the
+ * _masked variants with plane_mask = 0x34 and times = null (results differ from them by FP32 re-association only).
+ * b200gs_hexplane_time_supported: 1 when the rows of this descriptor fit one CTA's shared memory (2 levels at 64 / 128). */
+int b200gs_hexplane_time_supported(const b200gs_hexplane_desc* desc);
+int b200gs_hexplane_time_forward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
+                                 float time_scalar, const float* factor, float* features, b200gs_stream_t stream);
+int b200gs_hexplane_time_backward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
+                                  float time_scalar, const float* factor, float* d_factor_accum, const float* d_features,
+                                  float* d_pts, void* time_row_scratch, size_t time_row_scratch_bytes, b200gs_stream_t stream);
+
 /* HexPlane regulariser, value and gradient in one pass (scene/gaussian_model.py:730-769 compute_regulation;
  * scene/regulation.py:22-28 compute_plane_smoothness): per level
  *   plane_tv_weight * sum_{k in 0,1,3} S(G_k) + time_smoothness_weight * sum_{k in 2,4,5} S(G_k)
