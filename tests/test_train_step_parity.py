@@ -16,7 +16,7 @@ def _rel(a, b):
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
 
-@pytest.mark.parametrize("P,W,H,views", [(20000, 208, 128, 2), (3000, 64, 48, 3)])
+@pytest.mark.parametrize("P,W,H,views", [(20000, 208, 128, 2), (3000, 64, 48, 3), (2777, 64, 48, 1)])   # odd count; single view = no shared step
 def test_training_step_matches_reference_stack(P, W, H, views):
     import bench
     import ref_harness as rh
