@@ -59,10 +59,8 @@ __device__ __forceinline__ float4 tf32x4(float4 v)
 }
 __device__ __forceinline__ void split4(const float* x, float4& hi, float4& lo)
 {
-    float h[4], l[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { h[e] = __uint_as_float(to_tf32(x[e])); l[e] = __uint_as_float(to_tf32(x[e] - h[e])); }
-    hi = make_float4(h[0], h[1], h[2], h[3]); lo = make_float4(l[0], l[1], l[2], l[3]);
+    hi = make_float4(x[0], x[1], x[2], x[3]);            // the tensor core truncates: see tf32_lo
+    lo = make_float4(tf32_lo(x[0]), tf32_lo(x[1]), tf32_lo(x[2]), tf32_lo(x[3]));
 }
 __device__ __forceinline__ void sts128(u32 addr, float4 v)
 {

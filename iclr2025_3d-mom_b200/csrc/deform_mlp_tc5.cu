@@ -330,11 +330,7 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
                     make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         }
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-            const float x = __uint_as_float(v[e]);
-            v[e] = to_tf32(x);
-            lo[e] = to_tf32(x - __uint_as_float(v[e]));
-        }
+        for (int e = 0; e < 32; ++e) lo[e] = __float_as_uint(tf32_lo(__uint_as_float(v[e])));      // hi = the raw value (hardware truncates)
     };
 
     const long long nblocks = (a.P + ROWS - 1) / ROWS;
@@ -356,7 +352,7 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
             for (int j = 0; j < 8; ++j) {
                 const float x[4] = {fr[8 * c + j].x, fr[8 * c + j].y, fr[8 * c + j].z, fr[8 * c + j].w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { hi[4 * j + e] = to_tf32(x[e]); lo[4 * j + e] = to_tf32(x[e] - __uint_as_float(hi[4 * j + e])); }
+                for (int e = 0; e < 4; ++e) { hi[4 * j + e] = __float_as_uint(x[e]); lo[4 * j + e] = __float_as_uint(tf32_lo(x[e])); }
             }
             tmem_st32(lane_addr + FH * cT + 32 * c, hi);
             tmem_st32(lane_addr + C_FE_LO + FH * cT + 32 * c, lo);

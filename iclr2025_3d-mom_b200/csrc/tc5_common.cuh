@@ -20,6 +20,11 @@ __host__ __device__ __forceinline__ size_t stash_off(long long row, int col)
 
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ u32 to_tf32(float x) { u32 r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+// Exact two-term split for tcgen05.mma.kind::tf32. The tensor core TRUNCATES an FP32 container to TF32 (it ignores the low
+// 13 mantissa bits; measured with tools/probe/umma_probe.cu), so the "hi" operand can be the raw value itself and
+// lo = x - trunc(x) is exact (13 significant bits, of which the hardware keeps 10): hi + lo reproduces x to 2^-21 relative
+// with two instructions instead of the five of a round / subtract / round split.
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 __device__ __forceinline__ void mbar_init(u64* bar, u32 count)
 {

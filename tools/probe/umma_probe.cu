@@ -80,32 +80,22 @@ int main()
     // 1. both K-major (known-good form)
     g.a_lbo = M * 16; g.a_sbo = 128; g.a_step = 2 * M * 16; g.b_lbo = N * 16; g.b_sbo = 128; g.b_step = 2 * N * 16; g.idesc = id;
     run("A K-major, B K-major", Ak, Bk, g);
-    // MN-major tf32 needs the SWIZZLE_128B_BASE32B layout type (descriptor bits 61-63 = 1): atoms of 4 k-rows x 128 B
-    // (32 MN elements); hypotheses for the swizzle: H1 byte bits [7,9) ^-> [5,7) (32-B granule ^= row), H2 word ^= chunk
-    const u64 SW = 1ull << 61;
-    for (int hyp = 0; hyp < 3; ++hyp) {
-        std::vector<float> Am(M * K, 0.f), Bm(N * K, 0.f);
-        auto off = [&](int mn, int k, int n_mn_atoms_unused, int K_) {
-            const int mn_a = mn / 32, k_a = k / 4, row = k % 4, w = mn % 32;
-            int byte = (mn_a * (K_ / 4) + k_a) * 512 + row * 128;
-            int col = w * 4;
-            if (hyp == 0) col = ((((w / 8) ^ row) * 8) + (w % 8)) * 4;
-            if (hyp == 1) col = ((w / 4) * 4 + ((w % 4) ^ ((w / 4) & 3))) * 4;
-            return (byte + col) / 4;
-        };
-        for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) Am[off(m, k, 0, K)] = A[m * K + k];
-        for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) Bm[off(n, k, 0, K)] = B[n * K + k];
-        const char* hn[3] = {"H1 granule^=row", "H2 word^=chunk", "H0 no swizzle"};
-        char name[128];
-        for (int v = 0; v < 2; ++v) {
-            // v = 0: LBO = MN-atom stride, SBO = K-atom stride (CUTLASS); v = 1: swapped
-            const u32 mn_stride = (K / 4) * 512, k_stride = 512;
-            g.a_lbo = v ? k_stride : mn_stride; g.a_sbo = v ? mn_stride : k_stride; g.a_step = 1024;
-            g.b_lbo = N * 16; g.b_sbo = 128; g.b_step = 2 * N * 16; g.idesc = id | IDESC_A_MN; g.a_flags = SW; g.b_flags = 0;
-            snprintf(name, sizeof name, "%s A MN-sw v%d, B K", hn[hyp], v); run(name, Am, Bk, g);
-            g.b_lbo = v ? k_stride : mn_stride; g.b_sbo = v ? mn_stride : k_stride; g.b_step = 1024; g.b_flags = SW;
-            g.idesc = id | IDESC_A_MN | IDESC_B_MN;
-            snprintf(name, sizeof name, "%s A MN-sw, B MN-sw v%d", hn[hyp], v); run(name, Am, Bm, g);
+    // Does the tensor core truncate or round FP32 containers to TF32? Full-precision inputs, two CPU references.
+    {
+        std::vector<float> Af(M * K), Bf(N * K), Akf(M * K), Bkf(N * K);
+        for (auto& v : Af) v = (rand() % 2000001 - 1000000) / 1000000.f * 1.2345678f;
+        for (auto& v : Bf) v = (rand() % 2000001 - 1000000) / 1000000.f * 0.7654321f;
+        auto rna = [](float x) { u32 u; memcpy(&u, &x, 4); u += 0x1000u; u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; };
+        for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) Akf[(k / 4) * (M * 4) + m * 4 + (k & 3)] = Af[m * K + k];
+        for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) Bkf[(k / 4) * (N * 4) + n * 4 + (k & 3)] = Bf[n * K + k];
+        g.a_lbo = M * 16; g.a_sbo = 128; g.a_step = 2 * M * 16; g.b_lbo = N * 16; g.b_sbo = 128; g.b_step = 2 * N * 16; g.idesc = id; g.a_flags = 0; g.b_flags = 0;
+        for (int mode = 0; mode < 2; ++mode) {
+            for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) {
+                double acc = 0;
+                for (int k = 0; k < K; ++k) acc += (double)(mode ? rna(Af[m * K + k]) : tf(Af[m * K + k])) * (mode ? rna(Bf[n * K + k]) : tf(Bf[n * K + k]));
+                Dref[m * N + n] = (float)acc;
+            }
+            run(mode ? "full-precision inputs vs ROUNDED reference" : "full-precision inputs vs TRUNCATED reference", Akf, Bkf, g);
         }
     }
     return 0;
