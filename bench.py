@@ -97,6 +97,9 @@ class ClockSampler:
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
 NCU_TRAFFIC = {"hexplane_bwd_kernel": 348.4e6, "deform_mlp_bwd_tc5_kernel": 1563.8e6, "deform_mlp_fwd_tc5v2_kernel": 1320.4e6}
 ROOFLINE_NOTES = {
+    "deform_mlp_bwd_tc5_kernel": "HBM is the binding roofline (1.58 KB/point: 1 KB activation stash + features + d_features; the tensor pipe is 15 % "
+                                 "busy), but the kernel is SIMT-issue / latency bound today: 8 warps per SM walk five barrier-separated phases per tile",
+    "deform_mlp_fwd_tc5v2_kernel": "HBM is the binding roofline (1.37 KB/point, 1 KB of it the activation stash); tensor pipe 26 % busy",
     "hexplane_bwd_kernel": "average over the step's V time-plane passes and its one spatial pass; algorithmic HBM bytes only (xyz, order, "
                            "d_feature, shared spatial product in; d_xyz, its gradient accumulator, plane gradients out); the 3 KB/point/pass of "
                            "plane texel gathers + vector REDs are served by L1/L2 (planes are 11.6 MB), which is what bounds this kernel; "
@@ -534,6 +537,9 @@ def _main():
         "b200gs_hexplane_forward_masked": ("hexplane_fwd_kernel", (V * P_ * (12 + 4 + 4 * F_ + 4 * F_) + P_ * (12 + 4 + 4 * F_)) / (V + 1)),
         "b200gs_hexplane_backward_masked": ("hexplane_bwd_kernel", (V * P_ * (12 + 4 + 4 * F_ + 4 * F_ + 8 * F_ + 12)
                                                                      + P_ * (12 + 4 + 4 * F_ + 12) + 4 * plane_params) / (V + 1)),
+        # one-timestamp views: time planes from shared memory; streams xyz, S and the feature rows (+ the d(S) accumulator)
+        "b200gs_hexplane_time_forward": ("hexplane_time_fwd_kernel", P_ * (12 + 4 * F_ + 4 * F_)),
+        "b200gs_hexplane_time_backward": ("hexplane_time_bwd_kernel", P_ * (12 + 4 * F_ + 4 * F_ + 8 * F_ + 12)),
         "b200gs_deform_mlp_forward": ("deform_mlp_fwd_tc5v2_kernel", P_ * (4 * F_ + 52 + 4 * 4 * 64 + 40)),
         "b200gs_deform_mlp_backward": ("deform_mlp_bwd_tc5_kernel", P_ * (4 * 4 * 64 + 4 * F_ + 40 + 4 * F_)),
         "b200gs_activations_forward": ("activations_fwd_kernel", P_ * 64),
