@@ -37,7 +37,7 @@ class _HexDesc(ctypes.Structure):
 class _MlpWeights(ctypes.Structure):
     _fields_ = [("feat_dim", ctypes.c_int), ("width", ctypes.c_int), ("w1", ctypes.c_void_p), ("b1", ctypes.c_void_p),
                 ("w2", ctypes.c_void_p * 3), ("b2", ctypes.c_void_p * 3), ("w3", ctypes.c_void_p * 3),
-                ("b3", ctypes.c_void_p * 3)]
+                ("b3", ctypes.c_void_p * 3), ("feat_tiled", ctypes.c_int)]
 
 
 class _MlpGrads(ctypes.Structure):
@@ -57,9 +57,9 @@ _lib.register("b200gs_hexplane_backward_masked", ctypes.c_int,
 _lib.register("b200gs_hexplane_time_row_scratch_bytes", ctypes.c_size_t, [ctypes.POINTER(_HexDesc), ctypes.c_int])
 _lib.register("b200gs_hexplane_time_supported", ctypes.c_int, [ctypes.POINTER(_HexDesc)])
 _lib.register("b200gs_hexplane_time_forward", ctypes.c_int,
-              [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, ctypes.c_float, _P, _P, _P])
+              [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, ctypes.c_float, _P, _P, ctypes.c_int, _P])
 _lib.register("b200gs_hexplane_time_backward", ctypes.c_int,
-              [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, ctypes.c_float, _P, _P, _P, _P, _P, ctypes.c_size_t, _P])
+              [ctypes.POINTER(_HexDesc), ctypes.c_longlong, _P, _P, ctypes.c_float, _P, _P, _P, _P, _P, ctypes.c_size_t, ctypes.c_int, _P])
 _ROW_SCRATCH = {}
 TIME_ROW_REPLICAS = 64
 
@@ -298,14 +298,19 @@ class _DeformFn(torch.autograd.Function):
         sh = _shared_for(xyz, P)
         ctx.shared = sh
         ctx.time_rows = False
+        ctx.feat_tiled = False
         if sh is not None and tt is None and L.b200gs_hexplane_time_supported(ctypes.byref(d)):
             # shared spatial product + one timestamp for the view: time planes served from shared memory
             sh["used"] = True
             ctx.time_rows = True
             # (no cell order here: with the rows in shared memory there is no texel locality to gain, and walking the points in
             #  storage order keeps the S / feature rows streaming)
+            # feature / d_feature rows in the stash's 4-point-group tiles: coalesced for the MLP kernels' lane-per-point access
+            ctx.feat_tiled = levels == 2
+            if ctx.feat_tiled:
+                feat = torch.empty(((P + 127) // 128 * 128, 32 * levels), dtype=torch.float32, device=dev)
             check(L.b200gs_hexplane_time_forward(ctypes.byref(d), P, xyz.data_ptr(), None, ts, sh["S"].data_ptr(),
-                                                 feat.data_ptr(), stream), "hexplane_time_forward")
+                                                 feat.data_ptr(), int(ctx.feat_tiled), stream), "hexplane_time_forward")
         elif sh is not None:      # spatial product from begin_shared_step; only the time planes are sampled per view
             sh["used"] = True
             check(L.b200gs_hexplane_forward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(order),
@@ -316,6 +321,7 @@ class _DeformFn(torch.autograd.Function):
                                             tt.data_ptr() if tt is not None else None, ts, feat.data_ptr(), stream),
                   "hexplane_forward")
         mw = _DeformFn._weights_struct(weights, heads, 32 * levels)
+        mw.feat_tiled = int(ctx.feat_tiled)
         saved = torch.empty((L.b200gs_deform_mlp_saved_floats(P),), dtype=torch.float32, device=dev)
         pts_o = torch.empty_like(xyz); scales_o = torch.empty_like(scales); rot_o = torch.empty_like(rot)
         if torch.is_tensor(frame_num):
@@ -357,6 +363,7 @@ class _DeformFn(torch.autograd.Function):
         P = int(xyz.shape[0])
         stream = current_stream()
         mw = _DeformFn._weights_struct(weights, heads, 32 * levels)
+        mw.feat_tiled = int(ctx.feat_tiled)
         pw, pp = ctx.params
         direct_w = [_grad_target(q) if q is not None else None for q in pw]
         direct_p = [_grad_target(q) for q in pp]
@@ -380,7 +387,7 @@ class _DeformFn(torch.autograd.Function):
             scratch, nbytes = _time_row_scratch(d, xyz.device)
             check(L.b200gs_hexplane_time_backward(ctypes.byref(d), P, xyz.data_ptr(), None, ts, sh["S"].data_ptr(),
                                                   sh["A"].data_ptr(), d_feat.data_ptr(), d_xyz_grid.data_ptr(), scratch.data_ptr(),
-                                                  nbytes, stream), "hexplane_time_backward")
+                                                  nbytes, int(ctx.feat_tiled), stream), "hexplane_time_backward")
         elif sh is not None or not has_t:
             # shared step: time planes now, the spatial planes' share is accumulated for finish_shared_step.
             # One timestamp for the whole launch (scalar time): the time planes' gradient goes through replicated 1-D rows.

@@ -484,6 +484,7 @@ int check_weights(const b200gs_mlp_weights* w)
     if (!w) { set_error("deform_mlp: null weights"); return -1; }
     if (w->width != MW) { set_error("deform_mlp: net_width=%d unsupported (need %d)", w->width, MW); return -1; }
     if (w->feat_dim != 64 && w->feat_dim != 128) { set_error("deform_mlp: feature dim %d unsupported (64 or 128: 2 or 4 HexPlane levels)", w->feat_dim); return -1; }
+    if (w->feat_tiled && w->feat_dim != 64) { set_error("deform_mlp: tiled features need feature dim 64"); return -1; }
     if (!w->w1 || !w->b1) { set_error("deform_mlp: feature_out weights missing"); return -1; }
     for (int h = 0; h < 3; ++h)
         if (w->w2[h] && (!w->b2[h] || !w->w3[h] || !w->b3[h])) { set_error("deform_mlp: head %d incomplete", h); return -1; }

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
             if (prev_row < a.P) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    reinterpret_cast<float4*>(a.d_feat + (size_t)prev_row * MW + 32 * cT)[j] =
+                    *reinterpret_cast<float4*>(a.d_feat + (a.w.feat_tiled ? stash_off(prev_row, 32 * cT) + 16 * j : (size_t)prev_row * MW + 32 * cT + 4 * j)) =
                         make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
             }
             prev_row = -1;
@@ -162,10 +162,12 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
     // MMA drain + shared-memory stores of the phase before.
     const bool en0 = a.w.w2[0] != nullptr, en1 = a.w.w2[1] != nullptr, en2 = a.w.w2[2] != nullptr;
     auto next_phase = [&](int ph) { return (ph < 0 && en0) ? 0 : (ph < 1 && en1) ? 1 : (ph < 2 && en2) ? 2 : 3; };
-    auto load_rows = [&](float4* x, const float* src, long long r0) {          // row-major [P][64] (features)
+    auto load_rows = [&](float4* x, const float* src, long long r0) {          // features: row-major [P][64] or stash-style tiles
+        const float* base = src + (a.w.feat_tiled ? stash_off(r0, col0) : (size_t)r0 * MW + col0);
+        const size_t step = a.w.feat_tiled ? 256 : 4 * MW;                       // rows r0 + 4 i
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            x[i] = r0 + 4 * i < a.P ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(r0 + 4 * i) * MW + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[i] = r0 + 4 * i < a.P ? __ldg(reinterpret_cast<const float4*>(base + step * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     auto load_stash = [&](float4* x, int plane, long long r0) {                  // tiled stash plane, see stash_off
         // r0 = tile * 128 + 32 pg + sub: the 8 rows r0 + 4 i are the same slot of 8 consecutive 4-point groups

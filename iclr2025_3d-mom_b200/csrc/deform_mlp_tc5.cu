@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(NT, 1) deform_mlp_fwd_tc5_kernel(const __grid_
             u32 hi[32], lo[32];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const float4 v = valid ? __ldg(reinterpret_cast<const float4*>(a.feat + (size_t)r * F + 32 * c) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 v = valid ? __ldg(reinterpret_cast<const float4*>(a.feat + (a.w.feat_tiled ? stash_off(r, 32 * c + 4 * q) : (size_t)r * F + 32 * c + 4 * q))) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { hi[4 * q + e] = to_tf32(x[e]); lo[4 * q + e] = to_tf32(x[e] - __uint_as_float(hi[4 * q + e])); }
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
         const long long r = (long long)blockIdx.x * ROWS + pT;
 #pragma unroll
         for (int j = 0; j < FH / 4; ++j)
-            fr[j] = (blockIdx.x < nblocks && r < a.P) ? __ldg(reinterpret_cast<const float4*>(a.feat + (size_t)r * F + FH * cT) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            fr[j] = (blockIdx.x < nblocks && r < a.P) ? __ldg(reinterpret_cast<const float4*>(a.feat + (a.w.feat_tiled ? stash_off(r, FH * cT) + 16 * j : (size_t)r * F + FH * cT + 4 * j))) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const long long r = blk * ROWS + pT;
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
             const bool vn = blk + gridDim.x < nblocks && rn < a.P;
 #pragma unroll
             for (int j = 0; j < FH / 4; ++j)
-                fr[j] = vn ? __ldg(reinterpret_cast<const float4*>(a.feat + (size_t)rn * F + FH * cT) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                fr[j] = vn ? __ldg(reinterpret_cast<const float4*>(a.feat + (a.w.feat_tiled ? stash_off(rn, FH * cT) + 16 * j : (size_t)rn * F + FH * cT + 4 * j))) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float in_x[3] = {0.f, 0.f, 0.f}, in_s[3] = {0.f, 0.f, 0.f}, in_r[4] = {0.f, 0.f, 0.f, 0.f}, in_f[3] = {0.f, 0.f, 0.f};
         if (valid && cT == 0) {

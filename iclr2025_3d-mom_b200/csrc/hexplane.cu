@@ -16,6 +16,7 @@
 // lane per channel, so every texel fetch is a single coalesced 128-byte line.
 #include "common.cuh"
 #include "radix_sort.cuh"
+#include "tc5_common.cuh"
 #include "../../include/b200gs.h"
 
 namespace b200gs {
@@ -389,7 +390,7 @@ __device__ __forceinline__ RowSample row_sample(const float* __restrict__ row, f
 __global__ void __launch_bounds__(256)
 hexplane_time_fwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const __grid_constant__ TimeRowSetup ts, long long P,
                          const float* __restrict__ pts, const unsigned int* __restrict__ order, float t,
-                         const float* __restrict__ factor, float* __restrict__ feat)
+                         const float* __restrict__ factor, float* __restrict__ feat, int tiled)
 {
     extern __shared__ float R[];
     time_rows_prepare(d, t, R, ts);
@@ -409,7 +410,7 @@ hexplane_time_fwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const _
             float4 f = factor ? __ldg(reinterpret_cast<const float4*>(factor + g * F + l * HP_C + cg * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
             for (int a = 0; a < 3; ++a) f = mul4(f, row_sample(R + ts.off[l][a], c[a], d.res[l][a], cg).v);
-            *reinterpret_cast<float4*>(feat + g * F + l * HP_C + cg * 4) = f;
+            *reinterpret_cast<float4*>(feat + (tiled ? tc5::stash_off((long long)g, l * HP_C + cg * 4) : g * F + l * HP_C + cg * 4)) = f;
         }
     }
 }
@@ -418,7 +419,8 @@ __global__ void __launch_bounds__(256)
 hexplane_time_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const __grid_constant__ TimeRowSetup ts, long long P,
                          const float* __restrict__ pts, const unsigned int* __restrict__ order, float t,
                          const float* __restrict__ factor, float* __restrict__ dfactor, const float* __restrict__ dfeat,
-                         float* __restrict__ dpts, float* __restrict__ time_rows /* [replicas][ts.total], zeroed */, int replicas)
+                         float* __restrict__ dpts, float* __restrict__ time_rows /* [replicas][ts.total], zeroed */, int replicas,
+                         int tiled)
 {
     extern __shared__ float R[];
     float* rows = time_rows + (size_t)(blockIdx.x % replicas) * ts.total;      // row gradients: this CTA's replica
@@ -438,7 +440,7 @@ hexplane_time_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const _
         float gc[3] = {0.f, 0.f, 0.f};
         if (valid) {
             for (int l = 0; l < d.levels; ++l) {
-                const float4 gout = __ldg(reinterpret_cast<const float4*>(dfeat + g * F + l * HP_C + cg * 4));
+                const float4 gout = __ldg(reinterpret_cast<const float4*>(dfeat + (tiled ? tc5::stash_off((long long)g, l * HP_C + cg * 4) : g * F + l * HP_C + cg * 4)));
                 const float4 fac = factor ? __ldg(reinterpret_cast<const float4*>(factor + g * F + l * HP_C + cg * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
                 RowSample r[3];
 #pragma unroll
@@ -715,9 +717,10 @@ int b200gs_hexplane_time_supported(const b200gs_hexplane_desc* desc)
 }
 
 int b200gs_hexplane_time_forward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
-                                 float time_scalar, const float* factor, float* features, b200gs_stream_t stream)
+                                 float time_scalar, const float* factor, float* features, int features_tiled, b200gs_stream_t stream)
 {
     if (validate(desc)) return -1;
+    if (features_tiled && desc->levels != 2) { set_error("hexplane_time_forward: tiled features need 2 levels (64 columns)"); return -1; }
     TimeRowSetup ts;
     if (!time_rows_setup(*desc, ts)) { set_error("hexplane_time_forward: time rows do not fit shared memory"); return -1; }
     if (P <= 0) return 0;
@@ -726,15 +729,17 @@ int b200gs_hexplane_time_forward(const b200gs_hexplane_desc* desc, long long P, 
     long long blocks = (P + 31) / 32;
     const long long cap = (long long)NUM_SMS * (smem * 3 <= 220 * 1024 ? 3 : (smem * 2 <= 220 * 1024 ? 2 : 1));
     if (blocks > cap) blocks = cap;
-    hexplane_time_fwd_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(*desc, ts, P, pts, order, time_scalar, factor, features);
+    hexplane_time_fwd_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(*desc, ts, P, pts, order, time_scalar, factor, features, features_tiled);
     return check_launch("hexplane_time_forward");
 }
 
 int b200gs_hexplane_time_backward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
                                   float time_scalar, const float* factor, float* d_factor_accum, const float* d_features,
-                                  float* d_pts, void* time_row_scratch, size_t time_row_scratch_bytes, b200gs_stream_t stream)
+                                  float* d_pts, void* time_row_scratch, size_t time_row_scratch_bytes, int d_features_tiled,
+                                  b200gs_stream_t stream)
 {
     if (validate(desc)) return -1;
+    if (d_features_tiled && desc->levels != 2) { set_error("hexplane_time_backward: tiled d_features need 2 levels (64 columns)"); return -1; }
     TimeRowSetup ts;
     if (!time_rows_setup(*desc, ts)) { set_error("hexplane_time_backward: time rows do not fit shared memory"); return -1; }
     if (P <= 0) return 0;
@@ -749,7 +754,7 @@ int b200gs_hexplane_time_backward(const b200gs_hexplane_desc* desc, long long P,
     const long long cap = (long long)NUM_SMS * (per * 3 <= 220 * 1024 ? 3 : (per * 2 <= 220 * 1024 ? 2 : 1));
     if (blocks > cap) blocks = cap;
     hexplane_time_bwd_kernel<<<(unsigned)blocks, 256, per, (cudaStream_t)stream>>>(*desc, ts, P, pts, order, time_scalar, factor, d_factor_accum,
-                                                                                   d_features, d_pts, rows, replicas);
+                                                                                   d_features, d_pts, rows, replicas, d_features_tiled);
     hexplane_time_rows_flush_kernel<<<(unsigned)((ts.total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*desc, time_scalar, rows, replicas);
     return check_launch("hexplane_time_backward");
 }

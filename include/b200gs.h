@@ -181,6 +181,9 @@ typedef struct {
     const float* w1; const float* b1;           /* feature_out.0  [64, feat_dim], [64] */
     const float* w2[3]; const float* b2[3];     /* {pos,scales,rotations}_deform.1  [64,64],[64]; null = head off (no_dx/no_ds/no_dr) */
     const float* w3[3]; const float* b3[3];     /* {pos,scales,rotations}_deform.3  [k,64],[k], k = 3,3,4 */
+    int feat_tiled;               /* 0: features / d_features are row-major [P, feat_dim]; 1 (feat_dim 64 only): both use the
+                                     4-point-group tile layout of the activation stash ([tile of 128][32 groups][16 chunks][4 points][4]),
+                                     which is what b200gs_hexplane_time_forward / _backward produce / consume with tiled = 1 */
 } b200gs_mlp_weights;
 typedef struct { float* w1; float* b1; float* w2[3]; float* b2[3]; float* w3[3]; float* b3[3]; } b200gs_mlp_grads;
 
@@ -225,10 +228,11 @@ size_t b200gs_hexplane_time_row_scratch_bytes(const b200gs_hexplane_desc* desc, 
  * b200gs_hexplane_time_supported: 1 when the rows of this descriptor fit one CTA's shared memory (2 levels at 64 / 128). */
 int b200gs_hexplane_time_supported(const b200gs_hexplane_desc* desc);
 int b200gs_hexplane_time_forward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
-                                 float time_scalar, const float* factor, float* features, b200gs_stream_t stream);
+                                 float time_scalar, const float* factor, float* features, int features_tiled, b200gs_stream_t stream);
 int b200gs_hexplane_time_backward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
                                   float time_scalar, const float* factor, float* d_factor_accum, const float* d_features,
-                                  float* d_pts, void* time_row_scratch, size_t time_row_scratch_bytes, b200gs_stream_t stream);
+                                  float* d_pts, void* time_row_scratch, size_t time_row_scratch_bytes, int d_features_tiled,
+                                  b200gs_stream_t stream);
 
 /* HexPlane regulariser, value and gradient in one pass (scene/gaussian_model.py:730-769 compute_regulation;
  * scene/regulation.py:22-28 compute_plane_smoothness): per level

@@ -52,9 +52,9 @@ def test_split_equals_six_plane(P):
         scratch, nb = F._time_row_scratch(d, xyz.device)
         if route == "smem":
             assert L.b200gs_hexplane_time_supported(ctypes.byref(d)) == 1
-            check(L.b200gs_hexplane_time_forward(ctypes.byref(d), P, xyz.data_ptr(), None, t, S.data_ptr(), f.data_ptr(), st))
+            check(L.b200gs_hexplane_time_forward(ctypes.byref(d), P, xyz.data_ptr(), None, t, S.data_ptr(), f.data_ptr(), 0, st))
             check(L.b200gs_hexplane_time_backward(ctypes.byref(d), P, xyz.data_ptr(), None, t, S.data_ptr(), A.data_ptr(), dfeat.data_ptr(),
-                                                  dx_t.data_ptr(), scratch.data_ptr(), nb, st))
+                                                  dx_t.data_ptr(), scratch.data_ptr(), nb, 0, st))
         else:
             times = tt.data_ptr() if route == "classic" else None
             check(L.b200gs_hexplane_forward_masked(ctypes.byref(d), P, xyz.data_ptr(), optr, times, t, F.MASK_TIME, S.data_ptr(), f.data_ptr(), st))

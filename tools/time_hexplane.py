@@ -49,12 +49,12 @@ print(f"bwd time  rows    {timeit(bwd(0x34, S, A, True)):8.1f} us")
 print(f"bwd time  rows noA{timeit(bwd(0x34, S, None, True)):8.1f} us")
 
 F_=F
-def tf(): check(L.b200gs_hexplane_time_forward(ctypes.byref(d), P, xyz.data_ptr(), order.data_ptr(), 0.37, S.data_ptr(), feat.data_ptr(), st))
-def tb(): check(L.b200gs_hexplane_time_backward(ctypes.byref(d), P, xyz.data_ptr(), order.data_ptr(), 0.37, S.data_ptr(), A.data_ptr(), dfeat.data_ptr(), dxyz.data_ptr(), st))
+def tf(): check(L.b200gs_hexplane_time_forward(ctypes.byref(d), P, xyz.data_ptr(), order.data_ptr(), 0.37, S.data_ptr(), feat.data_ptr(), 0, st))
+def tb(): check(L.b200gs_hexplane_time_backward(ctypes.byref(d), P, xyz.data_ptr(), order.data_ptr(), 0.37, S.data_ptr(), A.data_ptr(), dfeat.data_ptr(), dxyz.data_ptr(), scratch.data_ptr(), nb, 0, st))
 print(f"time-rows fwd     {timeit(tf):8.1f} us")
 print(f"time-rows bwd     {timeit(tb):8.1f} us")
 # agreement with the masked kernels
 f1 = torch.empty_like(feat); f2 = torch.empty_like(feat)
 check(L.b200gs_hexplane_forward_masked(ctypes.byref(d), P, xyz.data_ptr(), order.data_ptr(), None, 0.37, 0x34, S.data_ptr(), f1.data_ptr(), st))
-check(L.b200gs_hexplane_time_forward(ctypes.byref(d), P, xyz.data_ptr(), order.data_ptr(), 0.37, S.data_ptr(), f2.data_ptr(), st))
+check(L.b200gs_hexplane_time_forward(ctypes.byref(d), P, xyz.data_ptr(), order.data_ptr(), 0.37, S.data_ptr(), f2.data_ptr(), 0, st))
 print("fwd max rel diff", ((f1 - f2).abs().max() / f1.abs().max()).item())
