@@ -78,6 +78,23 @@ def main():
                         input_grads=dict(xyz=xyz.grad, scales=scales.grad, rot=rot.grad), param_grads=grads),
                    os.path.join(out_dir, f"field_{name}.pt"))
         print(name, "saved; params with grad:", len(grads))
+    # regulariser: the reference's own GaussianModel.compute_regulation (scene/gaussian_model.py:730-769) on its own planes
+    from scene.gaussian_model import GaussianModel
+    torch.manual_seed(6666)
+    net = deform_network(hyper([1, 2], [6, 5, 7, 9]))
+    with torch.no_grad():
+        for p in net.deformation_net.grid.grids.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    gm = GaussianModel.__new__(GaussianModel)              # only _deformation is touched by compute_regulation
+    gm._deformation = net
+    tw, l1w, pw = 0.01, 0.0001, 0.0001                     # arguments/dnerf/dnerf_default.py values
+    loss = gm.compute_regulation(tw, l1w, pw)
+    loss.backward()
+    planes = {n: p.detach().clone() for n, p in net.named_parameters() if ".grids." in n}
+    torch.save(dict(weights=(tw, l1w, pw), planes=planes, loss=loss.detach(),
+                    grads={n: p.grad.clone() for n, p in net.named_parameters() if ".grids." in n and p.grad is not None}),
+               os.path.join(out_dir, "regulation.pt"))
+    print("regulation saved; loss", float(loss))
 
 
 if __name__ == "__main__":

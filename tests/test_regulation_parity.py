@@ -1,7 +1,9 @@
-"""GPU parity of the fused HexPlane regulariser against the reference's formulas
-(scene/gaussian_model.py:730-769 _plane_regulation / _time_regulation / _l1_regulation,
-scene/regulation.py:22-28 compute_plane_smoothness), restated here with the same PyTorch ops.
+"""GPU parity of the fused HexPlane regulariser against the oracle restatement of the reference's formulas
+(oracle/field_torch.py::plane_regulation = scene/gaussian_model.py:730-769 + scene/regulation.py:22-28, pinned bit-exact
+against the real GaussianModel.compute_regulation by tests/golden/regulation.pt) and against that golden fixture itself.
 Value within 1e-5 relative, plane gradients within 1e-5 of each plane's largest gradient."""
+import os
+
 import types
 
 import pytest
@@ -10,18 +12,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _smooth(t):
-    h = t.shape[2]
-    first = t[..., 1:, :] - t[..., :h - 1, :]
-    second = first[..., 1:, :] - first[..., :h - 2, :]
-    return torch.square(second).mean()
-
-
 def _reference(grids, tw, l1w, pw):
-    plane = sum(_smooth(g[k]) for g in grids for k in (0, 1, 3))
-    time = sum(_smooth(g[k]) for g in grids for k in (2, 4, 5))
-    l1 = sum(torch.abs(1 - g[k]).mean() for g in grids for k in (2, 4, 5))
-    return pw * plane + tw * time + l1w * l1
+    from oracle import field_torch
+    return field_torch.plane_regulation(grids, tw, l1w, pw)
 
 
 @pytest.mark.parametrize("multires,T", [([1, 2], 50), ([1, 2, 4, 8], 25)])
@@ -50,3 +43,22 @@ def test_regulation_value_and_gradient(multires, T):
     assert abs(acc.item() - ref.item()) < 1e-5 * abs(ref.item())
     for p, b, q in zip(f._planes(), before, [q for rg in ref_grids for q in rg]):
         assert ((p.grad - b) - q.grad).abs().max().item() <= 1e-5 * q.grad.abs().max().item()
+
+
+def test_regulation_against_reference_golden():
+    """The kernel on the very planes the reference's own GaussianModel.compute_regulation was run on."""
+    from b200gs import field
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "regulation.pt"))
+    cfg = {'grid_dimensions': 2, 'input_coordinate_dim': 4, 'output_coordinate_dim': 32, 'resolution': [6, 5, 7, 9]}
+    f = field.HexPlaneField(1.6, cfg, [1, 2]).cuda()
+    with torch.no_grad():
+        for l, gp in enumerate(f.grids):
+            for k, p in enumerate(gp):
+                p.copy_(g["planes"][f"deformation_net.grid.grids.{l}.{k}"].cuda())
+    loss = field.compute_regulation(f, *g["weights"])
+    loss.backward()
+    assert abs(loss.item() - g["loss"].item()) < 1e-5 * abs(g["loss"].item())
+    for l, gp in enumerate(f.grids):
+        for k, p in enumerate(gp):
+            ref = g["grads"][f"deformation_net.grid.grids.{l}.{k}"].cuda()
+            assert (p.grad - ref).abs().max().item() <= 1e-5 * ref.abs().max().item(), (l, k)
