@@ -605,7 +605,12 @@ def _main():
     if impl != "b200":
         res["impl"] = "reference"
         res["reference_stack"] = "reference CUDA rasterizer (oracle/_ref, unmodified) + PyTorch port of HexPlane/deformation + torch.optim.Adam, on GPU"
-    if not args.no_cpu_baseline and world == 1:
+        # schema completeness: this arm is the reference's own implementation of the path, which is CUDA (it has no CPU
+        # implementation); one host thread drives it. The CPU port is what `cpu_baseline` on the product line times.
+        res["cpu_baseline"] = {"value": value, "unit": "view-iters/s", "cores": 1, "kind": "reference",
+                               "sample": "the reference's own code path for this workload (its CUDA rasterizer from oracle/_ref + its PyTorch "
+                                         "field + torch Adam) on the same GPU, full workload; host side single-threaded"}
+    if not args.no_cpu_baseline and world == 1 and impl == "b200":
         try:
             res["cpu_baseline"] = cpu_baseline(args, raw, cams[0])
         except Exception as ex:          # the checker must never take the product line down

@@ -7,6 +7,7 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" ; tail -3 gpurun_out/pytest_$TAG.log
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_b200_$TAG.json 2> gpurun_out/bench_b200_$TAG.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref rc=$?"
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke_$TAG.log
 python tools/time_raster.py > gpurun_out/time_raster_$TAG.log 2>&1
 V=2 python tools/profile_step.py > gpurun_out/kernels_$TAG.log 2>&1
 V=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv python tools/profile_step.py > gpurun_out/ncu_launch_$TAG.log 2>&1
