@@ -1,5 +1,6 @@
-// Deformation MLP (feature decoder + position / scale / rotation heads), forward and backward,
-// on the tensor cores.
+// Deformation MLP (feature decoder + position / scale / rotation heads): C-ABI entry points, and the
+// register-resident mma.sync BACKWARD that serves the 4-level (feature dim 128) configuration. The forward
+// (deform_mlp_tc5.cu) and the 2-level backward (deform_mlp_bwd_tc5.cu) run on tcgen05 / TMEM.
 //
 // Restates scene/deformation.py:55-65 (create_net), :68-85 (query_time) and :97-153
 // (forward_dynamic) for the configuration the reference trains with:
@@ -26,7 +27,6 @@ namespace b200gs {
 
 namespace {
 
-constexpr bool USE_TCGEN05_FORWARD = true;
 constexpr bool USE_TCGEN05_BACKWARD = true;     // F = 64 only; F = 128 keeps the mma.sync kernel below
 using tc5::MW;                     // net_width
 using tc5::stash_off; using tc5::stash_plane_floats;
@@ -95,127 +95,6 @@ __device__ __forceinline__ void kstep(float (*acc)[4], const float a[4], const f
         for (int q = 0; q < G; ++q) mma(acc[n0 + q], ahi, __float_as_uint(b[q].z), __float_as_uint(b[q].w));
 #pragma unroll
         for (int q = 0; q < G; ++q) mma(acc[n0 + q], ahi, __float_as_uint(b[q].x), __float_as_uint(b[q].y));
-    }
-}
-
-struct FwdArgs {
-    b200gs_mlp_weights w;
-    long long P;
-    const float* feat; const float* xyz; const float* scales; const float* rot; const float* scene_flow;
-    float frame_num, delta_scale;
-    const float* frame_num_dev;   // optional device scalar overriding frame_num (avoids a host sync)
-    float* pts_out; float* scales_out; float* rot_out;
-    float* saved;                 // [4][P][64] row-major: relu(hidden), relu(z_pos), relu(z_scale), relu(z_rot)
-};
-
-template <int F>
-__global__ void __launch_bounds__(MT, 1) deform_mlp_fwd_kernel(const __grid_constant__ FwdArgs a)
-{
-    extern __shared__ __align__(16) float4 smem4[];
-    constexpr int RS1 = F / 2 + 4, RS2 = MW / 2 + 4;
-    float4* W1q = smem4;                       // [64][RS1]
-    float4* W2q = W1q + MW * RS1;              // [3][64][RS2]
-    float4* W3q = W2q + 3 * MW * RS2;          // [3][8][RS2]   (N padded to 8)
-    float* bias = reinterpret_cast<float*>(W3q + 3 * 8 * RS2);   // b1[64] b2[3][64] b3[3][8]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-    const int kdim[3] = {3, 3, 4};
-
-    // forward: Wm[k][n] = W_torch[n][k]  ->  sk = 1, sn = K
-    stage_weight(W1q, a.w.w1, F, MW, F, MW, 1, F);
-    for (int i = tid; i < MW; i += MT) bias[i] = __ldg(a.w.b1 + i);
-    for (int h = 0; h < 3; ++h) {
-        if (!a.w.w2[h]) continue;
-        stage_weight(W2q + h * MW * RS2, a.w.w2[h], MW, MW, MW, MW, 1, MW);
-        stage_weight(W3q + h * 8 * RS2, a.w.w3[h], MW, 8, MW, kdim[h], 1, MW);
-        for (int i = tid; i < MW; i += MT) bias[MW + h * MW + i] = __ldg(a.w.b2[h] + i);
-        if (tid < 8) bias[4 * MW + h * 8 + tid] = tid < kdim[h] ? __ldg(a.w.b3[h] + tid) : 0.f;
-    }
-    __syncthreads();
-
-    const long long nblocks = (a.P + ROWS - 1) / ROWS;
-    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-        const long long r_lo = blk * ROWS + warp * 16 + g, r_hi = r_lo + 8;
-        const bool v_lo = r_lo < a.P, v_hi = r_hi < a.P;
-        // ---- hidden = feature W1^T + b1 ----
-        float hC[8][4];
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            hC[nt][0] = hC[nt][2] = bias[8 * nt + 2 * t];
-            hC[nt][1] = hC[nt][3] = bias[8 * nt + 2 * t + 1];
-        }
-#pragma unroll 2
-        for (int j = 0; j < F / 8; ++j) {
-            const float2 lo2 = v_lo ? __ldg(reinterpret_cast<const float2*>(a.feat + (size_t)r_lo * F + 8 * j + 2 * t)) : make_float2(0.f, 0.f);
-            const float2 hi2 = v_hi ? __ldg(reinterpret_cast<const float2*>(a.feat + (size_t)r_hi * F + 8 * j + 2 * t)) : make_float2(0.f, 0.f);
-            const float af[4] = {lo2.x, hi2.x, lo2.y, hi2.y};
-            kstep<8>(hC, af, W1q, RS1, j, g, t);
-        }
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) hC[nt][i] = fmaxf(hC[nt][i], 0.f);
-            if (v_lo) *reinterpret_cast<float2*>(a.saved + stash_off(r_lo, 8 * nt + 2 * t)) = make_float2(hC[nt][0], hC[nt][1]);
-            if (v_hi) *reinterpret_cast<float2*>(a.saved + stash_off(r_hi, 8 * nt + 2 * t)) = make_float2(hC[nt][2], hC[nt][3]);
-        }
-        // ---- heads ----
-#pragma unroll
-        for (int h = 0; h < 3; ++h) {
-            const int kd = kdim[h];
-            if (!a.w.w2[h]) {            // head disabled (no_dx / no_ds / no_dr): pass through
-                const float* src = h == 0 ? a.xyz : (h == 1 ? a.scales : a.rot);
-                float* dst = h == 0 ? a.pts_out : (h == 1 ? a.scales_out : a.rot_out);
-                for (int c = 2 * t; c < 2 * t + 2 && c < kd; ++c) {
-                    if (v_lo) dst[(size_t)r_lo * kd + c] = __ldg(src + (size_t)r_lo * kd + c);
-                    if (v_hi) dst[(size_t)r_hi * kd + c] = __ldg(src + (size_t)r_hi * kd + c);
-                }
-                continue;
-            }
-            float zC[8][4];
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                zC[nt][0] = zC[nt][2] = bias[MW + h * MW + 8 * nt + 2 * t];
-                zC[nt][1] = zC[nt][3] = bias[MW + h * MW + 8 * nt + 2 * t + 1];
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float af[4] = {hC[j][0], hC[j][2], hC[j][1], hC[j][3]};
-                kstep<8>(zC, af, W2q + h * MW * RS2, RS2, j, g, t);
-            }
-            float* sv = a.saved + (size_t)(1 + h) * stash_plane_floats(a.P);
-            float oC[1][4];
-            oC[0][0] = oC[0][2] = bias[4 * MW + h * 8 + 2 * t];
-            oC[0][1] = oC[0][3] = bias[4 * MW + h * 8 + 2 * t + 1];
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) zC[nt][i] = fmaxf(zC[nt][i], 0.f);
-                if (v_lo) *reinterpret_cast<float2*>(sv + stash_off(r_lo, 8 * nt + 2 * t)) = make_float2(zC[nt][0], zC[nt][1]);
-                if (v_hi) *reinterpret_cast<float2*>(sv + stash_off(r_hi, 8 * nt + 2 * t)) = make_float2(zC[nt][2], zC[nt][3]);
-                const float af[4] = {zC[nt][0], zC[nt][2], zC[nt][1], zC[nt][3]};
-                kstep<1>(oC, af, W3q + h * 8 * RS2, RS2, nt, g, t);
-            }
-            // epilogue: columns 2t, 2t+1 of rows r_lo / r_hi
-            const float fn = a.frame_num_dev ? __ldg(a.frame_num_dev) : a.frame_num;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const long long r = half ? r_hi : r_lo;
-                if (!(half ? v_hi : v_lo)) continue;
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int c = 2 * t + cc;
-                    if (c >= kd) continue;
-                    const float o = oC[0][2 * half + cc];
-                    if (h == 0) {
-                        const float flow = __fmul_rn(a.delta_scale, __fmul_rn(fn, __ldg(a.scene_flow + 3 * r + c)));
-                        a.pts_out[3 * r + c] = __fadd_rn(__fmul_rn(__ldg(a.xyz + 3 * r + c), 1.0f), __fadd_rn(o, flow));
-                    } else if (h == 1) {
-                        a.scales_out[3 * r + c] = __fadd_rn(__fmul_rn(__ldg(a.scales + 3 * r + c), 1.0f), o);
-                    } else {
-                        a.rot_out[4 * r + c] = __fadd_rn(__ldg(a.rot + 4 * r + c), o);
-                    }
-                }
-            }
-        }
     }
 }
 
@@ -468,11 +347,6 @@ __global__ void __launch_bounds__(MT, 1) deform_mlp_bwd_kernel(const __grid_cons
     }
 }
 
-size_t fwd_smem(int F)
-{
-    return (size_t)(MW * (F / 2 + 4) + 3 * MW * (MW / 2 + 4) + 3 * 8 * (MW / 2 + 4)) * sizeof(float4) +
-           (size_t)(4 * MW + 24 + 8) * sizeof(float);
-}
 size_t bwd_smem(int F)
 {
     return (size_t)(3 * MW * 4 + (F == 64 ? 3 : 1) * MW * (MW / 2 + 4) + F * (MW / 2 + 4)) * sizeof(float4) +
@@ -517,24 +391,8 @@ int b200gs_deform_mlp_forward(const b200gs_mlp_weights* w, long long P, const fl
 {
     if (check_weights(w)) return -1;
     if (P <= 0) return 0;
-    if (USE_TCGEN05_FORWARD)
-        return deform_mlp_forward_tc5(w, P, feat, xyz, scales, rot, scene_flow, frame_num, frame_num_dev, delta_scale,
-                                      pts_out, scales_out, rot_out, saved, (cudaStream_t)stream);
-    FwdArgs a;
-    a.w = *w; a.P = P; a.feat = feat; a.xyz = xyz; a.scales = scales; a.rot = rot; a.scene_flow = scene_flow;
-    a.frame_num = frame_num; a.frame_num_dev = frame_num_dev; a.delta_scale = delta_scale; a.pts_out = pts_out;
-    a.scales_out = scales_out; a.rot_out = rot_out; a.saved = saved;
-    const long long nblocks = (P + ROWS - 1) / ROWS;
-    const int grid = (int)(nblocks < NUM_SMS ? nblocks : NUM_SMS);
-    const size_t smem = fwd_smem(w->feat_dim);
-    if (w->feat_dim == 64) {
-        cudaFuncSetAttribute(deform_mlp_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        deform_mlp_fwd_kernel<64><<<grid, MT, smem, (cudaStream_t)stream>>>(a);
-    } else {
-        cudaFuncSetAttribute(deform_mlp_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        deform_mlp_fwd_kernel<128><<<grid, MT, smem, (cudaStream_t)stream>>>(a);
-    }
-    return check_launch("deform_mlp_forward");
+    return deform_mlp_forward_tc5(w, P, feat, xyz, scales, rot, scene_flow, frame_num, frame_num_dev, delta_scale,
+                                  pts_out, scales_out, rot_out, saved, (cudaStream_t)stream);
 }
 
 int b200gs_deform_mlp_backward(const b200gs_mlp_weights* w, const b200gs_mlp_grads* gw, long long P, const float* feat,

@@ -387,7 +387,7 @@ __device__ __forceinline__ RowSample row_sample(const float* __restrict__ row, f
     return r;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 hexplane_time_fwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const __grid_constant__ TimeRowSetup ts, long long P,
                          const float* __restrict__ pts, const unsigned int* __restrict__ order, float t,
                          const float* __restrict__ factor, float* __restrict__ feat, int tiled)
@@ -415,7 +415,7 @@ hexplane_time_fwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const _
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 hexplane_time_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const __grid_constant__ TimeRowSetup ts, long long P,
                          const float* __restrict__ pts, const unsigned int* __restrict__ order, float t,
                          const float* __restrict__ factor, float* __restrict__ dfactor, const float* __restrict__ dfeat,
@@ -726,10 +726,10 @@ int b200gs_hexplane_time_forward(const b200gs_hexplane_desc* desc, long long P, 
     if (P <= 0) return 0;
     const size_t smem = (size_t)ts.total * sizeof(float);
     cudaFuncSetAttribute(hexplane_time_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    long long blocks = (P + 31) / 32;
+    long long blocks = (P + 63) / 64;                // 16 warps x 4 point slots per block; the kernels are latency bound, so as many warps as fit
     const long long cap = (long long)NUM_SMS * (smem * 3 <= 220 * 1024 ? 3 : (smem * 2 <= 220 * 1024 ? 2 : 1));
     if (blocks > cap) blocks = cap;
-    hexplane_time_fwd_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(*desc, ts, P, pts, order, time_scalar, factor, features, features_tiled);
+    hexplane_time_fwd_kernel<<<(unsigned)blocks, 512, smem, (cudaStream_t)stream>>>(*desc, ts, P, pts, order, time_scalar, factor, features, features_tiled);
     return check_launch("hexplane_time_forward");
 }
 
