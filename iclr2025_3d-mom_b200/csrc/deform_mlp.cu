@@ -382,7 +382,7 @@ using namespace b200gs;
 
 extern "C" {
 
-size_t b200gs_deform_mlp_saved_floats(long long P) { return P > 0 ? 4 * stash_plane_floats(P) : 0; }
+size_t b200gs_deform_mlp_saved_floats(long long P) { return P > 0 ? tc5::stash_total_floats(P) : 0; }
 
 int b200gs_deform_mlp_forward(const b200gs_mlp_weights* w, long long P, const float* feat, const float* xyz,
                               const float* scales, const float* rot, const float* scene_flow, float frame_num,

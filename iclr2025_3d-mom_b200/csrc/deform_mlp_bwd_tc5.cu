@@ -11,10 +11,11 @@
 //     ReLU masks, dW3 and every bias gradient are plain FP32 in registers (dW3 / biases accumulate in
 //     registers over all tiles of the CTA).  Eight lanes cover one 128-byte row, so every global load
 //     and every shared-memory store below is a full line / conflict free.
-//   * dX chain on the tensor cores, SS mode:  D_RH[p][in] += (dz_hi + dz_lo)[p][out] tf32(W2_h)[out][in],
-//     D_FE = (dh_hi + dh_lo) tf32(W1).  A = DYK, un-swizzled K-major core matrices (chunk stride padded
-//     to 2064 B so the column-chunk-per-lane stores do not collide), hi and lo planes -> dY is exact,
-//     only the weights are rounded (2^-12 relative, random sign).
+//   * dX chain on the tensor cores, SS mode, full three-term split (dY_lo W_hi + dY_hi W_lo + dY_hi W_hi, FP32-level
+//     accuracy: its error would otherwise reach the per-point xyz gradients un-averaged):  D_RH[p][in] += dz[p][out]
+//     W2_h[out][in], D_FE = dh W1.  A = DYK, un-swizzled K-major core matrices (chunk stride padded to 2064 B so the
+//     column-chunk-per-lane stores do not collide), hi and lo planes; B = the transposed TF32 hi / lo weight images the
+//     forward left behind the stash, W1 resident, the current head's W2 pair streamed in with cp.async.
 //   * weight gradients on the tensor cores: D_W[out][in] += tf32(dY)^T tf32(X), contraction over the 128
 //     points of the tile, with M = 128 rows = [dY_hi ; dY_lo] (the two halves are added at the flush, so
 //     dY is exact and only X is rounded).  Both operands are MN-major; for TF32 the only MN-major shared-memory layout
@@ -22,7 +23,7 @@
 //     (32 MN elements), the 32-byte granule index XORed with the row index (probed on hardware,
 //     tools/probe/umma_probe.cu).  The accumulators D_W2[3], D_W1 stay in TMEM for the whole life of
 //     the CTA and are flushed with one atomic per element per CTA at the end.
-// Shared memory (~225 KB): W2B 48 K | W1B 16 K | DYM 64 K | XH 32 K | DYK 2 x 33 K.
+// Shared memory (~225 KB): W2 slot 32 K (hi|lo) | W1 32 K (hi|lo) | DYM 64 K | XH 32 K | DYK 2 x 33 K.
 // TMEM columns: D_RH [0,64)  D_FE [64,128)  D_W2[h] [128 + 64 h, +64)  D_W1 [320,384).
 #include "tc5_common.cuh"
 #include "../../include/b200gs.h"
@@ -43,15 +44,6 @@ struct BwdArgs {
     const float* d_pts; const float* d_scales; const float* d_rot;
     float* d_feat;
 };
-
-// B operand for D[p][n] = sum_k A[p][k] Wm[k][n] with Wm[k][n] = w[k*ld + n]: K-major [N][K], tf32 rounded
-__device__ __forceinline__ void stage_b_kmajor(float* __restrict__ dst, const float* __restrict__ w, int N, int K, int ld)
-{
-    for (int i = threadIdx.x; i < N * K; i += BT) {
-        const int k = i / N, n = i - k * N;                         // coalesced global reads along n
-        dst[(k >> 2) * (N * 4) + n * 4 + (k & 3)] = __uint_as_float(to_tf32(__ldg(w + (size_t)k * ld + n)));
-    }
-}
 
 __device__ __forceinline__ float4 tf32x4(float4 v)
 {
@@ -76,9 +68,9 @@ __device__ __forceinline__ float4 lds128(u32 addr)
 __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_constant__ BwdArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    float* W2B = reinterpret_cast<float*>(smem_raw);                 // [3][16 k-chunks][64 n][4]
-    float* W1B = W2B + 3 * MW * MW;                                  // [16][64][4]
-    unsigned char* DYM = smem_raw + (3 * MW * MW + MW * MW) * 4;      // 64 KB, MN-major swizzled  [out: 64 hi rows | 64 lo rows][p 128]
+    float* W2B = reinterpret_cast<float*>(smem_raw);                 // current head: hi [16 k-chunks][64 n][4] | lo  (32 KB)
+    float* W1B = W2B + 2 * MW * MW;                                  // hi | lo                                      (32 KB)
+    unsigned char* DYM = smem_raw + (2 * MW * MW + 2 * MW * MW) * 4;      // 64 KB, MN-major swizzled  [out: 64 hi rows | 64 lo rows][p 128]
     unsigned char* XH = DYM + 65536;                                 // 32 KB, MN-major swizzled  [in 64][p 128]
     unsigned char* DYK = XH + 32768;                                 // 2 planes x 16 chunks x 2064 B, K-major  [p 128][out 64]
     u64* bar = reinterpret_cast<u64*>(DYK + 2 * KPLANE);
@@ -92,11 +84,17 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
     const int kdim[3] = {3, 3, 4};
 
     // ---- one-time staging ----
-    for (int h = 0; h < 3; ++h) {
-        if (!a.w.w2[h]) continue;
-        stage_b_kmajor(W2B + h * MW * MW, a.w.w2[h], MW, MW, MW);     // Wm[k = out][n = in] = W2[out][in]
-    }
-    stage_b_kmajor(W1B, a.w.w1, MW, MW, MW);                           // Wm[k = out][n = feature] = W1[out][f]  (F = 64)
+    // transposed TF32 hi / lo weight images left behind the stash by the forward (tc5_common.cuh): W1 stays resident,
+    // the current head's W2 pair is streamed in per head
+    const float* images = reinterpret_cast<const float*>(a.saved) + 4 * stash_plane_floats(a.P);
+    auto copy_image_pair = [&](float* dst, int m) {                   // 32 KB = 2048 16-byte pieces, 8 per thread
+        const float4* src = reinterpret_cast<const float4*>(images + (size_t)(2 * m) * MW * MW);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cp_async16(reinterpret_cast<float4*>(dst) + tid + BT * i, src + tid + BT * i);
+        cp_async_commit();
+    };
+    copy_image_pair(W1B, 3);
+    cp_async_wait<0>();
     for (int i = tid; i < 98304 / 16; i += BT) reinterpret_cast<float4*>(DYM)[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // DYM + XH
     if (tid == 0) {
         if (smem_u32(DYM) & 1023u) __trap();                          // the swizzle below assumes 1 KB aligned tiles
@@ -241,7 +239,8 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
                 }
             }
             load_phase_rows(next_phase(h), xin, row0);          // next head's rows, or the feature rows
-            drain();                 // the previous MMA group still reads DYK / DYM / XH
+            drain();                 // the previous MMA group still reads DYK / DYM / XH and the W2 slot
+            copy_image_pair(W2B, h);
             if (!h_staged) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) sts128(sXH + mn_off + (u32)(p0 + 4 * i) * 128u, tf32x4(hrow[i]));
@@ -257,16 +256,19 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
                 sts128(sDYM + mn_off + pp * 128u, hi);
                 sts128(sDYM + 32768u + mn_off + pp * 128u, lo);
             }
+            cp_async_wait<0>();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_before();
             __syncthreads();
             if (tid == 0) {
                 tc_fence_after();
-                const u32 w2 = sW2 + h * MW * MW * 4;
-                for (int j = 0; j < 8; ++j) {          // K = 64 out features, 8 per instruction
-                    const u64 bd = smem_desc(w2 + j * 2 * (MW * 16), MW * 16, 128);
-                    mma_ss(tbase + C_RH, smem_desc(sDYK + KPLANE + j * 2 * KCH, KCH, 128), bd, id_kk, (rh_started || j > 0) ? 1u : 0u);
-                    mma_ss(tbase + C_RH, smem_desc(sDYK + j * 2 * KCH, KCH, 128), bd, id_kk, 1u);
+                for (int j = 0; j < 8; ++j) {          // K = 64 out features, 8 per instruction; lo*hi + hi*lo + hi*hi
+                    const u64 bh = smem_desc(sW2 + j * 2 * (MW * 16), MW * 16, 128);
+                    const u64 bl = smem_desc(sW2 + MW * MW * 4 + j * 2 * (MW * 16), MW * 16, 128);
+                    const u64 ah = smem_desc(sDYK + j * 2 * KCH, KCH, 128), al = smem_desc(sDYK + KPLANE + j * 2 * KCH, KCH, 128);
+                    mma_ss(tbase + C_RH, al, bh, id_kk, (rh_started || j > 0) ? 1u : 0u);
+                    mma_ss(tbase + C_RH, ah, bl, id_kk, 1u);
+                    mma_ss(tbase + C_RH, ah, bh, id_kk, 1u);
                 }
                 for (int j = 0; j < 16; ++j)           // K = 128 points, 8 per instruction (two 4-row atoms)
                     mma_ss(tbase + C_W2 + 64 * h, smem_desc(sDYM + j * 1024, 16384, 512) | DESC_SW128_32B,
@@ -326,9 +328,12 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
         if (tid == 0) {
             tc_fence_after();
             for (int j = 0; j < 8; ++j) {
-                const u64 bd = smem_desc(sW1 + j * 2 * (MW * 16), MW * 16, 128);
-                mma_ss(tbase + C_FE, smem_desc(sDYK + KPLANE + j * 2 * KCH, KCH, 128), bd, id_kk, j > 0 ? 1u : 0u);
-                mma_ss(tbase + C_FE, smem_desc(sDYK + j * 2 * KCH, KCH, 128), bd, id_kk, 1u);
+                const u64 bh = smem_desc(sW1 + j * 2 * (MW * 16), MW * 16, 128);
+                const u64 bl = smem_desc(sW1 + MW * MW * 4 + j * 2 * (MW * 16), MW * 16, 128);
+                const u64 ah = smem_desc(sDYK + j * 2 * KCH, KCH, 128), al = smem_desc(sDYK + KPLANE + j * 2 * KCH, KCH, 128);
+                mma_ss(tbase + C_FE, al, bh, id_kk, j > 0 ? 1u : 0u);
+                mma_ss(tbase + C_FE, ah, bl, id_kk, 1u);
+                mma_ss(tbase + C_FE, ah, bh, id_kk, 1u);
             }
             for (int j = 0; j < 16; ++j)
                 mma_ss(tbase + C_W1, smem_desc(sDYM + j * 1024, 16384, 512) | DESC_SW128_32B,
@@ -392,7 +397,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
     }
 }
 
-size_t bwd_smem() { return (size_t)(3 * MW * MW + MW * MW) * 4 + 98304 + 2 * KPLANE + 64; }
+size_t bwd_smem() { return (size_t)(2 * MW * MW + 2 * MW * MW) * 4 + 98304 + 2 * KPLANE + 64; }
 
 }  // namespace tc5
 

@@ -84,6 +84,12 @@ __global__ void __launch_bounds__(NT, 1) deform_mlp_fwd_tc5_kernel(const __grid_
         for (int i = tid; i < MW; i += NT) bias[MW + h * MW + i] = __ldg(a.w.b2[h] + i);
         if (tid < 16) bias[4 * MW + h * 16 + tid] = tid < kdim[h] ? __ldg(a.w.b3[h] + tid) : 0.f;
     }
+    if (F == 64 && blockIdx.x == 0) {           // transposed TF32 weight images for the tcgen05 backward (see tc5_common.cuh)
+        float* images = a.saved + 4 * stash_plane_floats(a.P);
+        for (int h = 0; h < 3; ++h)
+            if (a.w.w2[h]) write_bwd_weight_image(images, h, a.w.w2[h], NT);
+        write_bwd_weight_image(images, 3, a.w.w1, NT);
+    }
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -295,6 +301,11 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
         stage_kmajor2(W3h + h * 16 * MW, W3l + h * 16 * MW, a.w.w3[h], 16, kdim[h], MW);
         for (int i = tid; i < MW; i += NT2) bias[MW + h * MW + i] = __ldg(a.w.b2[h] + i);
         if (tid < 16) bias[4 * MW + h * 16 + tid] = tid < kdim[h] ? __ldg(a.w.b3[h] + tid) : 0.f;
+    }
+    if (F == 64 && blockIdx.x == 0) {           // transposed TF32 weight images for the tcgen05 backward (see tc5_common.cuh)
+        float* images = a.saved + 4 * stash_plane_floats(a.P);
+        for (int h = 0; h < 3; ++h) write_bwd_weight_image(images, h, a.w.w2[h], NT2);
+        write_bwd_weight_image(images, 3, a.w.w1, NT2);
     }
     if (tid == 0) {
         for (int i = 0; i < 7; ++i) mbar_init(bars + i, 1);

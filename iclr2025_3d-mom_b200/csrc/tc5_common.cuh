@@ -18,6 +18,29 @@ __host__ __device__ __forceinline__ size_t stash_off(long long row, int col)
     return (size_t)(row >> 7) * (ROWS * MW) + (size_t)((row & 127) >> 2) * 256 + (size_t)(col >> 2) * 16 + (size_t)(row & 3) * 4 + (col & 3);
 }
 
+// Behind the four stash planes the forward leaves, for the tcgen05 backward (feature dim 64), the transposed weights as
+// ready-to-copy K-major UMMA B operands [N = in][K = out] in TF32 hi / lo pairs: W2^T of the three heads, then W1^T
+// (8 images of 64 x 64 floats). The backward streams the current head's pair into shared memory with cp.async instead
+// of keeping single-precision-rounded copies of all of them resident, which is what lets its dX chain run the full
+// three-term split (a rounded weight operand left up to 2 % error on a few per-point xyz gradients at 1M points).
+constexpr size_t BWD_W_IMAGE_FLOATS = 8 * MW * MW;
+__host__ __device__ __forceinline__ size_t stash_total_floats(long long P) { return 4 * stash_plane_floats(P) + BWD_W_IMAGE_FLOATS; }
+__device__ __forceinline__ u32 to_tf32(float x);
+// image m (0..2: W2 of head m, 3: W1), plane 0 = hi, 1 = lo; w = torch [out 64][in 64] row-major
+__device__ __forceinline__ void write_bwd_weight_image(float* __restrict__ images, int m, const float* __restrict__ w, int nthreads)
+{
+    float* hi = images + (size_t)(2 * m) * MW * MW;
+    float* lo = hi + MW * MW;
+    for (int i = threadIdx.x; i < MW * MW; i += nthreads) {
+        const int k = i >> 6, n = i & 63;                      // k = out row, n = in column: B[n][k] = W[k][n]
+        const float v = __ldg(w + i);
+        const float h = __uint_as_float(to_tf32(v));
+        const int off = (k >> 2) * (MW * 4) + n * 4 + (k & 3);
+        hi[off] = h;
+        lo[off] = __uint_as_float(to_tf32(v - h));
+    }
+}
+
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ u32 to_tf32(float x) { u32 r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
 // Exact two-term split for tcgen05.mma.kind::tf32. The tensor core TRUNCATES an FP32 container to TF32 (it ignores the low

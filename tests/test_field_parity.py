@@ -51,8 +51,12 @@ def _rel(a, b):
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
 
+import os
+_FULL = [([1, 2], 50, 1000000)] if os.environ.get("B200GS_FULLSIZE") else []      # BASELINE.json C3 point count
+
+
 @pytest.mark.parametrize("multires,T,P", [([1, 2], 50, 5000), ([1, 2], 50, 64), ([1, 2], 50, 1), ([1, 2, 4, 8], 25, 3001),
-                                          ([1, 2], 50, 40003)])   # >= 16384 points: cell-ordered traversal
+                                          ([1, 2], 50, 40003)] + _FULL)   # >= 16384 points: cell-ordered traversal
 def test_deform_network_forward_backward(multires, T, P):
     net = _model(multires, T)
     levels = len(multires)
@@ -74,10 +78,27 @@ def test_deform_network_forward_backward(multires, T, P):
     ((pts * wp).sum() + (sc * ws).sum() + (rt * wr).sum()).backward()
     ((rp * wp).sum() + (rs * ws).sum() + (rr * wr).sum()).backward()
     for x, y, name in zip(a, b, ("xyz", "scales", "rot")):
-        assert _rel(x.grad, y.grad) < 1e-3, name
+        if P < 100000:
+            assert _rel(x.grad, y.grad) < 1e-3, name
+        else:
+            # At a million points a few dozen of the 256M hidden pre-activations sit within FP32 summation-order noise of 0,
+            # where two FP32 implementations' ReLU masks legitimately differ and that POINT's gradient changes by a few per
+            # cent (tools/debug_hexplane_fullsize.py: the HexPlane kernels alone agree with torch to 4e-7 at this size).
+            # Everything else must meet the bar, and the exceptions must stay that rare.
+            err = (x.grad - y.grad).abs().max(dim=1).values / y.grad.abs().max()
+            bad = err > 1e-3
+            assert bad.float().mean().item() < 2e-4, (name, int(bad.sum()))
+            assert err[~bad].max().item() < 1e-3
     params = dict(net.named_parameters())
     checked = 0
     worst = 0.0
+    if P >= 100000:          # FP64 evaluation of the same oracle: the ground truth both FP32 implementations approximate
+        dt = torch.float64
+        sd64 = {k: (v.detach().clone().to(dt) if v.dtype.is_floating_point else v.detach().clone()).contiguous().requires_grad_(v.dtype.is_floating_point)
+                for k, v in net.state_dict().items()}
+        c = [t.clone().to(dt).requires_grad_(True) for t in (xyz, scales, rot)]
+        qp, qs, qr, _, _ = oracle.deform_forward(sd64, levels, c[0], c[1], c[2], opacity.to(dt), shs.to(dt), time.to(dt), flow.to(dt), frame_num, 1)
+        ((qp * wp.to(dt)).sum() + (qs * ws.to(dt)).sum() + (qr * wr.to(dt)).sum()).backward()
     for k, v in sd.items():
         if not v.requires_grad or k.endswith("grid.aabb") or k not in params:
             continue
@@ -86,8 +107,19 @@ def test_deform_network_forward_backward(multires, T, P):
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
         assert p.grad is not None, k
-        worst = max(worst, _rel(p.grad, v.grad))
-        assert _rel(p.grad, v.grad) < 1e-3, (k, _rel(p.grad, v.grad))
+        if P < 100000:
+            worst = max(worst, _rel(p.grad, v.grad))
+            assert _rel(p.grad, v.grad) < 1e-3, (k, _rel(p.grad, v.grad))
+        else:
+            # At this size FP32 itself is not reproducible to 1e-3 of a tensor's scale: torch's own FP32 gradients differ from
+            # the same oracle evaluated in FP64 by up to 2e-3 (ReLU-mask flips + summation order; tools/debug_dw_fullsize.py).
+            # The meaningful bar is the exact (FP64) gradient: we must be as close to it as the reference's FP32 arithmetic is.
+            ref64 = sd64[k].grad
+            scale = ref64.abs().max()
+            e_ours = ((p.grad.double() - ref64).abs().max() / scale).item()
+            e_t32 = ((v.grad.double() - ref64).abs().max() / scale).item()
+            assert e_ours <= max(1e-3, 2.0 * e_t32), (k, e_ours, e_t32)
+            worst = max(worst, e_ours)
         checked += 1
     print(f"worst parameter-gradient relative error: {worst:.2e}")
     assert checked >= 2 + 12 + 6 * levels

@@ -53,8 +53,14 @@ def _scene(P, W, H, mu, device="cuda"):
     return act, cam
 
 
+import os
+# BASELINE.json's full sizes: C3 (1M, 1280x720) always; C4 / C5 (1920x1080, 5M at 3840x2160) with B200GS_FULLSIZE=1
+_FULL = [(1000000, 1280, 720, 0.010)] + ([(1000000, 1920, 1080, 0.004), (5000000, 3840, 2160, 0.004)]
+                                         if os.environ.get("B200GS_FULLSIZE") else [])
+
+
 @pytest.mark.parametrize("P,W,H,mu", [(2000, 64, 48, 0.02), (20000, 200, 120, 0.01), (200000, 512, 512, 0.004),
-                                      (200000, 512, 512, 0.010)])
+                                      (200000, 512, 512, 0.010)] + _FULL)
 def test_forward_bit_exact_and_image(P, W, H, mu):
     assert rh.have_ref(), "oracle/_ref/libref_rast.so missing (run oracle/build_ref.sh)"
     from b200gs.rasterizer import _C
@@ -95,7 +101,7 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("P,W,H,mu,depth_grad", [(20000, 200, 120, 0.01, True), (200000, 512, 512, 0.004, False),
-                                                 (200000, 512, 512, 0.010, True)])
+                                                 (200000, 512, 512, 0.010, True)] + [c + (True,) for c in _FULL])
 def test_backward_gradients(P, W, H, mu, depth_grad):
     act, cam = _scene(P, W, H, mu)
     bg = torch.tensor([0.0, 0.0, 0.0], device="cuda")
