@@ -267,7 +267,7 @@ class GaussianRasterizer(nn.Module):
             rotations = torch.Tensor([])
         if cov3D_precomp is None:
             cov3D_precomp = torch.Tensor([])
-        if not torch.is_grad_enabled():
+        if not torch.is_grad_enabled() and not raster_settings.debug:
             # inference: keep the opaque state buffers reachable for debugging / statistics (export_state)
             args = (raster_settings.bg, means3D, colors_precomp, opacities, scales, rotations, raster_settings.scale_modifier,
                     cov3D_precomp, raster_settings.viewmatrix, raster_settings.projmatrix, raster_settings.tanfovx,
