@@ -187,7 +187,9 @@ typedef struct {
 } b200gs_mlp_weights;
 typedef struct { float* w1; float* b1; float* w2[3]; float* b2[3]; float* w3[3]; float* b3[3]; } b200gs_mlp_grads;
 
-/* floats of the activation stash the forward leaves for the backward */
+/* floats of the buffer the forward leaves for the backward (opaque to the caller, who only allocates it and hands the same
+ * pointer to both calls of one view): four planes of ReLU'd activations in 4-point-group tiles, followed by the transposed
+ * TF32 hi / lo weight images the tcgen05 backward streams into shared memory */
 size_t b200gs_deform_mlp_saved_floats(long long P);
 /* pts_out = xyz + pos_head + delta_scale*(frame_num*scene_flow); scales_out = scales + scale_head;
  * rot_out = rot + rot_head (deformation.py:113-135). frame_num_dev (device float, may be null)
@@ -198,7 +200,8 @@ int b200gs_deform_mlp_forward(const b200gs_mlp_weights* w /* host */, long long 
                               float frame_num, const float* frame_num_dev, float delta_scale, float* pts_out, float* scales_out, float* rot_out,
                               float* saved, b200gs_stream_t stream);
 /* weight gradients are ACCUMULATED into gw (caller zero-fills); d_features[P, feat_dim] is written.
- * d_pts / d_scales / d_rot: upstream gradients of the three outputs (null = zero). */
+ * d_pts / d_scales / d_rot: upstream gradients of the three outputs (null = zero). `w` and `saved` must be the ones the
+ * matching b200gs_deform_mlp_forward call was given. */
 int b200gs_deform_mlp_backward(const b200gs_mlp_weights* w /* host */, const b200gs_mlp_grads* gw /* host */,
                                long long P, const float* features, const float* saved, const float* d_pts,
                                const float* d_scales, const float* d_rot, float* d_features, b200gs_stream_t stream);
