@@ -95,7 +95,8 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {"hexplane_bwd_kernel": 348.4e6, "deform_mlp_bwd_tc5_kernel": 1561.1e6, "deform_mlp_fwd_tc5v2_kernel": 1317.6e6}
+NCU_TRAFFIC = {"hexplane_bwd_kernel": 348.4e6, "deform_mlp_bwd_tc5_kernel": 1561.1e6, "deform_mlp_fwd_tc5v2_kernel": 1317.6e6,
+               "hexplane_time_fwd_kernel": 485.5e6, "hexplane_time_bwd_kernel": 1037.8e6}
 ROOFLINE_NOTES = {
     "deform_mlp_bwd_tc5_kernel": "HBM is the binding roofline (1.58 KB/point: 1 KB activation stash + features + d_features; the tensor pipe is 15 % "
                                  "busy), but the kernel is SIMT-issue / latency bound today: 8 warps per SM walk five barrier-separated phases per tile",

@@ -92,15 +92,27 @@ __device__ __forceinline__ float4 interp4(const float4 nw, const float4 ne, cons
                        interp1(nw.z, ne.z, sw.z, se.z, b), interp1(nw.w, ne.w, sw.w, se.w, b));
 }
 
+// The aabb is the same for every point: its three IEEE divisions are done once per thread, not once per point.
+struct AabbNorm { float a0[3], scale[3]; };
+__device__ __forceinline__ AabbNorm aabb_norm(const float* __restrict__ aabb)
+{
+    AabbNorm n;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float a1 = __ldg(aabb + 3 + a);
+        n.a0[a] = __ldg(aabb + a);
+        n.scale[a] = __fdiv_rn(2.0f, __fsub_rn(a1, n.a0[a]));
+    }
+    return n;
+}
 __device__ __forceinline__ void normalized_coords(const float* __restrict__ pts, const float* __restrict__ times,
-                                                  float time_scalar, const float* __restrict__ aabb, size_t g,
+                                                  float time_scalar, const AabbNorm& n, size_t g,
                                                   float c[4], float scale[3])
 {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        const float a0 = __ldg(aabb + a), a1 = __ldg(aabb + 3 + a);
-        scale[a] = __fdiv_rn(2.0f, __fsub_rn(a1, a0));
-        c[a] = __fsub_rn(__fmul_rn(__fsub_rn(__ldg(pts + 3 * g + a), a0), scale[a]), 1.0f);
+        scale[a] = n.scale[a];
+        c[a] = __fsub_rn(__fmul_rn(__fsub_rn(__ldg(pts + 3 * g + a), n.a0[a]), n.scale[a]), 1.0f);
     }
     c[3] = times ? __ldg(times + g) : time_scalar;
 }
@@ -132,6 +144,7 @@ hexplane_fwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, long long P,
                     int mask, const float* __restrict__ factor, float* __restrict__ feat)
 {
     const int lane = threadIdx.x & 31, slot = lane >> 3, cg = lane & 7;
+    const AabbNorm an = aabb_norm(d.aabb);
     const int F = d.levels * HP_C;
     // blocked assignment: a CTA walks ONE contiguous run of the (cell-sorted) order, so the texels of a small 3-D
     // region stay in its SM's L1 from one iteration to the next (a grid-stride walk re-fetched them from L2)
@@ -143,7 +156,7 @@ hexplane_fwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, long long P,
         if (i >= end) continue;
         const size_t g = order ? (size_t)__ldg(order + i) : (size_t)i;
         float c[4], scale[3];
-        normalized_coords(pts, times, time_scalar, d.aabb, g, c, scale);
+        normalized_coords(pts, times, time_scalar, an, g, c, scale);
         for (int l = 0; l < d.levels; ++l) {
             Bilinear b;
             // feature = factor * prod_{k in mask} plane_k; mask = all six planes and no factor is the reference's
@@ -245,6 +258,7 @@ hexplane_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, long long P,
 {
     float* rows = time_rows ? time_rows + (size_t)(blockIdx.x % replicas) * time_row_floats(d) : nullptr;
     const int lane = threadIdx.x & 31, slot = lane >> 3, cg = lane & 7;
+    const AabbNorm an = aabb_norm(d.aabb);
     const int F = d.levels * HP_C;
     const long long ppi = (long long)(blockDim.x >> 5) * 4;                      // blocked assignment, see the forward
     const long long chunk = ((P + gridDim.x - 1) / gridDim.x + ppi - 1) / ppi * ppi;
@@ -254,7 +268,7 @@ hexplane_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, long long P,
         const bool valid = i < end;
         const size_t g = valid ? (order ? (size_t)__ldg(order + i) : (size_t)i) : 0;
         float c[4], scale[3];
-        normalized_coords(pts, times, time_scalar, d.aabb, g, c, scale);
+        normalized_coords(pts, times, time_scalar, an, g, c, scale);
         float gc[3] = {0.f, 0.f, 0.f};
         if (valid) {
             for (int l = 0; l < d.levels; ++l) {
@@ -396,6 +410,7 @@ hexplane_time_fwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const _
     time_rows_prepare(d, t, R, ts);
     __syncthreads();
     const int lane = threadIdx.x & 31, slot = lane >> 3, cg = lane & 7;
+    const AabbNorm an = aabb_norm(d.aabb);
     const int F = d.levels * HP_C;
     const long long ppi = (long long)(blockDim.x >> 5) * 4;
     const long long chunk = ((P + gridDim.x - 1) / gridDim.x + ppi - 1) / ppi * ppi;
@@ -405,7 +420,7 @@ hexplane_time_fwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const _
         if (i >= end) continue;
         const size_t g = order ? (size_t)__ldg(order + i) : (size_t)i;
         float c[4], scale[3];
-        normalized_coords(pts, nullptr, t, d.aabb, g, c, scale);
+        normalized_coords(pts, nullptr, t, an, g, c, scale);
         for (int l = 0; l < d.levels; ++l) {
             float4 f = factor ? __ldg(reinterpret_cast<const float4*>(factor + g * F + l * HP_C + cg * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
@@ -427,6 +442,7 @@ hexplane_time_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const _
     time_rows_prepare(d, t, R, ts);
     __syncthreads();
     const int lane = threadIdx.x & 31, slot = lane >> 3, cg = lane & 7;
+    const AabbNorm an = aabb_norm(d.aabb);
     const int F = d.levels * HP_C;
     const long long ppi = (long long)(blockDim.x >> 5) * 4;
     const long long chunk = ((P + gridDim.x - 1) / gridDim.x + ppi - 1) / ppi * ppi;
@@ -436,7 +452,7 @@ hexplane_time_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const _
         const bool valid = i < end;
         const size_t g = valid ? (order ? (size_t)__ldg(order + i) : (size_t)i) : 0;
         float c[4], scale[3];
-        normalized_coords(pts, nullptr, t, d.aabb, g, c, scale);
+        normalized_coords(pts, nullptr, t, an, g, c, scale);
         float gc[3] = {0.f, 0.f, 0.f};
         if (valid) {
             for (int l = 0; l < d.levels; ++l) {
