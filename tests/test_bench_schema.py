@@ -46,7 +46,8 @@ def test_reference_line_schema():
 
 
 def test_scaling_lines_are_weak_scaling_of_the_same_workload():
-    lines = [json.load(open(f)) for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r1i_bench_b200_n*.json")))]
+    lines = [json.load(open(f)) for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r1i_bench_b200_n*.json")) +
+                                                glob.glob(os.path.join(ROOT, "profiles", "r1j_bench_b200_n1.json")))]
     if len(lines) < 2:
         pytest.skip("no scaling lines")
     assert all(l["scaling"] == "weak" and l["config"]["views_per_gpu"] == lines[0]["config"]["views_per_gpu"] for l in lines)
