@@ -411,6 +411,13 @@ def _main():
         return json.dumps({"impl": "reference", "metric": "train_iters_per_s", "value": cb["value"], "unit": "view-iters/s",
                            "n_gpus": 0, "steps": 1, "warmup": 0, "higher_is_better": True, "cpu_baseline": cb,
                            "e2e": {"value": cb["value"], "unit": "view-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    launched_world = world
+    if impl == "reference" and world > 1:
+        # the reference has no multi-GPU path: under torchrun rank 0 alone runs it, on one GPU,
+        # and prints the line; the other ranks leave without work
+        if rank != 0:
+            return None
+        world = 1
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
     torch.cuda.set_device(local)
@@ -606,6 +613,10 @@ def _main():
     if impl != "b200":
         res["impl"] = "reference"
         res["reference_stack"] = "reference CUDA rasterizer (oracle/_ref, unmodified) + PyTorch port of HexPlane/deformation + torch.optim.Adam, on GPU"
+        if launched_world > 1:
+            res["n_gpus"] = launched_world
+            res["ranks_used"] = 1
+            res["config"]["parallelism"] = f"single GPU (the reference has no multi-GPU path; launched with {launched_world} ranks, rank 0 ran)"
         # schema completeness: this arm is the reference's own implementation of the path, which is CUDA (it has no CPU
         # implementation); one host thread drives it. The CPU port is what `cpu_baseline` on the product line times.
         res["cpu_baseline"] = {"value": value, "unit": "view-iters/s", "cores": 1, "kind": "reference",
