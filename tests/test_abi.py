@@ -76,3 +76,15 @@ def test_dropin_modules_expose_reference_names():
     for name in ("rasterize_gaussians", "rasterize_gaussians_backward", "mark_visible"):
         assert hasattr(c_mod, name)
     from simple_knn._C import distCUDA2  # noqa: F401
+
+
+def test_call_timer_table_names_are_abi_entries():
+    """bench.py's per-entry-point timing wraps libb200gs functions by name: every name must be a declared, exported entry."""
+    import re
+    from b200gs import _lib
+    header = open(os.path.join(ROOT, "include", "b200gs.h")).read()
+    declared = set(re.findall(r"\b(b200gs_[a-z0-9_]+)\s*\(", header))
+    L = _lib.lib()
+    for name in _lib.CallTimer.KERNELS:
+        assert name in declared, name
+        assert hasattr(L, name), name
