@@ -567,7 +567,7 @@ def _main():
         # compositing is FP32-issue bound: SURVEY.md 8d cost model (reference SASS) = 85 FP32 lane-instructions per evaluated
         # pair in the backward; peak = 148 SMs x 128 lanes x 1.965 GHz. The entry also contains preprocess_bwd (HBM-bound, ~15 %).
         for row in kernels:
-            if row["entry"] == "b200gs_rast_backward":
+            if row["entry"] in ("b200gs_rast_backward", "b200gs_rast_backward_accumulate_sh"):
                 rate = pairs_per_view * 85 / (row["ms_avg"] * 1e-3)
                 row.update({"kernel": "composite_bwd_kernel (+ preprocess_bwd_kernel)", "bound": "fp32-issue", "pairs_per_launch": pairs_per_view,
                             "achieved_lane_instr_per_s": rate, "frac_of_fp32_peak_on_reference_cost_model": round(rate / (148 * 128 * 1.965e9), 4)})

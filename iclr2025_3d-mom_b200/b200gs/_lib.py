@@ -47,6 +47,8 @@ def _declare(L):
     L.b200gs_rast_backward.argtypes = (
         [c_int, c_int, c_int, c_longlong, c_int, c_int, P, P, P, P, P, c_float, P, P, P, P, P, c_float, c_float,
          P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P])
+    L.b200gs_rast_backward_accumulate_sh.restype = c_int
+    L.b200gs_rast_backward_accumulate_sh.argtypes = L.b200gs_rast_backward.argtypes
     L.b200gs_mark_visible.restype = c_int
     L.b200gs_mark_visible.argtypes = [c_int, P, P, P, P, P]
     L.b200gs_rast_export.restype = c_longlong
@@ -103,7 +105,7 @@ class CallTimer:
     (the stream every kernel of the library is launched on). bench.py keeps it active over the timed region
     to get each kernel family's average duration and launch count; nothing else uses it."""
     # kernels launched per call (for the launch count): see csrc/api.cu and the per-file launchers
-    KERNELS = {"b200gs_rast_forward_stage1": 7, "b200gs_rast_forward_stage2": 7, "b200gs_rast_backward": 2,
+    KERNELS = {"b200gs_rast_forward_stage1": 7, "b200gs_rast_forward_stage2": 7, "b200gs_rast_backward": 2, "b200gs_rast_backward_accumulate_sh": 2,
                "b200gs_hexplane_order": 6, "b200gs_hexplane_forward": 1, "b200gs_hexplane_forward_masked": 1, "b200gs_hexplane_backward_masked": 1, "b200gs_hexplane_time_forward": 1, "b200gs_hexplane_time_backward": 1, "b200gs_hexplane_backward": 1, "b200gs_hexplane_regulation": 1,
                "b200gs_deform_mlp_forward": 1, "b200gs_deform_mlp_backward": 1, "b200gs_adam_multi": 1,
                "b200gs_activations_forward": 1, "b200gs_activations_backward": 1, "b200gs_l1_loss_fwd_bwd": 1,

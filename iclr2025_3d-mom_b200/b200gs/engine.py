@@ -22,6 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import fusedops
+from . import rasterizer as _rast
 from .adam import FusedAdam
 from .field import deform_network
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
@@ -213,6 +214,10 @@ class ViewParallelTrainer:
             # as a leaf, let the views' SH gradients accumulate in it, and split them back after the last view
             m = self.model
             shs = torch.cat((m._features_dc, m._features_rest), dim=1).detach().requires_grad_(True)
+            if shs.is_cuda:
+                # the rasterizer backward adds every view's SH gradient straight into this buffer (no per-view allocation,
+                # no AccumulateGrad pass over 192 B per Gaussian)
+                shs.grad = torch.zeros_like(shs)
         from . import field as _field
         share_spatial = self.shared_shs and self.stage == "fine" and len(cams) > 1 and self.model._xyz.is_cuda
         if share_spatial:
@@ -221,6 +226,7 @@ class ViewParallelTrainer:
             pkg = self.render_fn(cam, self.model, self.bg, self.stage, shs) if self.shared_shs else \
                 self.render_fn(cam, self.model, self.bg, self.stage)
             _field.ACCUMULATE_INTO_GRAD = self.shared_shs     # p.grad are arena views: let the field kernels add into them
+            _rast.SH_GRAD_ACCUMULATOR = shs.grad if (shs is not None and shs.is_cuda) else None
             try:
                 if self.shared_shs:
                     # fused L1 (utils/loss_utils.py:23-24) + its gradient, then backward from the image
@@ -235,6 +241,7 @@ class ViewParallelTrainer:
                     loss.backward()
             finally:
                 _field.ACCUMULATE_INTO_GRAD = False
+                _rast.SH_GRAD_ACCUMULATOR = None
             vg = pkg["viewspace_points"].grad
             if vg is not None:
                 self.viewspace_grad += vg

@@ -16,6 +16,10 @@ from ._lib import check, current_stream, ptr
 
 NUM_CHANNELS = 3
 
+# Set by b200gs.engine.ViewParallelTrainer for the duration of a step: a [P,M,3] buffer that the backward ADDS the SH
+# gradient into (b200gs_rast_backward_accumulate_sh); autograd then gets None for `sh`. None = ordinary behaviour.
+SH_GRAD_ACCUMULATOR = None
+
 _pinned = {}
 
 
@@ -115,12 +119,15 @@ class _CModule:
         dL_dopacity = torch.empty((P, 1), **opts)
         dL_dcov3D = torch.empty((P, 6), **opts)
         has_sh = M != 0 and (colors is None or colors.numel() == 0)
-        dL_dsh = torch.empty((P, M, 3), **opts) if has_sh else torch.zeros((P, M, 3), **opts)
+        acc = SH_GRAD_ACCUMULATOR
+        use_acc = has_sh and acc is not None and acc.shape == (P, M, 3) and acc.is_contiguous() and acc.device == dev
+        dL_dsh = acc if use_acc else (torch.empty((P, M, 3), **opts) if has_sh else torch.zeros((P, M, 3), **opts))
         dL_dscales = torch.empty((P, 3), **opts)
         dL_drotations = torch.empty((P, 4), **opts)
         if P != 0:
             arena = torch.empty((P, 12), **opts)
-            check(L.b200gs_rast_backward(
+            entry = L.b200gs_rast_backward_accumulate_sh if use_acc else L.b200gs_rast_backward
+            check(entry(
                 P, int(degree), M, int(R), W, H, ptr(background), ptr(means3D), ptr(sh), ptr(colors), ptr(scales),
                 float(scale_modifier), ptr(rotations), ptr(cov3D_precomp), ptr(viewmatrix), ptr(projmatrix),
                 ptr(campos), float(tan_fovx), float(tan_fovy), ptr(radii), geomBuffer.data_ptr(),
@@ -131,7 +138,7 @@ class _CModule:
                 "rasterize_gaussians_backward")
             if debug:
                 torch.cuda.synchronize(dev)
-        return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+        return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, (None if use_acc else dL_dsh), dL_dscales, dL_drotations
 
     @staticmethod
     def mark_visible(means3D, viewmatrix, projmatrix):

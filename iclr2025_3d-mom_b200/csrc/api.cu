@@ -43,7 +43,7 @@ int rast_backward(int P, int D, int M, long long R, int W, int H, const float* b
                   const int* radii, void* geom_buf, void* bin_buf, void* img_buf, const float* dL_dpix,
                   const float* dL_dpix_depth, float* grad_arena, float* dL_dmean2D, float* dL_dcolor,
                   float* dL_dopacity, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
-                  float* dL_drot, cudaStream_t stream);
+                  float* dL_drot, int accumulate_sh, cudaStream_t stream);
 int mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                  unsigned char* present, cudaStream_t stream);
 
@@ -132,7 +132,24 @@ int b200gs_rast_backward(int P, int D, int M, long long num_rendered, int W, int
     return rast_backward(P, D, M, num_rendered, W, H, background, means3D, shs, colors_precomp, scales,
                          scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx,
                          tan_fovy, radii, geom_buf, bin_buf, img_buf, dL_dpix, dL_dpix_depth, grad_arena,
-                         dL_dmean2D, dL_dcolor, dL_dopacity, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot,
+                         dL_dmean2D, dL_dcolor, dL_dopacity, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, 0,
+                         (cudaStream_t)stream);
+}
+
+int b200gs_rast_backward_accumulate_sh(int P, int D, int M, long long num_rendered, int W, int H, const float* background,
+                                       const float* means3D, const float* shs, const float* colors_precomp,
+                                       const float* scales, float scale_modifier, const float* rotations,
+                                       const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                                       const float* campos, float tan_fovx, float tan_fovy, const int* radii, void* geom_buf,
+                                       void* bin_buf, void* img_buf, const float* dL_dpix, const float* dL_dpix_depth,
+                                       float* grad_arena, float* dL_dmean2D, float* dL_dcolor, float* dL_dopacity,
+                                       float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh_accum, float* dL_dscale, float* dL_drot,
+                                       b200gs_stream_t stream)
+{
+    return rast_backward(P, D, M, num_rendered, W, H, background, means3D, shs, colors_precomp, scales,
+                         scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx,
+                         tan_fovy, radii, geom_buf, bin_buf, img_buf, dL_dpix, dL_dpix_depth, grad_arena,
+                         dL_dmean2D, dL_dcolor, dL_dopacity, dL_dmean3D, dL_dcov3D, dL_dsh_accum, dL_dscale, dL_drot, 1,
                          (cudaStream_t)stream);
 }
 

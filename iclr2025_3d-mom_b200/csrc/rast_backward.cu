@@ -229,6 +229,7 @@ struct PreBwdArgs {
     float* dL_dmean3D;             // [P,3]
     float* dL_dcov3D;              // [P,6]
     float* dL_dsh;                 // [P,M,3] or null
+    int accumulate_sh;             // 1: dL_dsh += (rows of invisible Gaussians are left alone); 0: every row is written
     float* dL_dscale;              // [P,3]
     float* dL_drot;                // [P,4]
 };
@@ -483,7 +484,9 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PreBwd
         float* dst = a.dL_dsh + (size_t)g0 * 3 * a.M;
         const int per = 3 * a.M;
         if (!any_vis) {
-            if ((per & 3) == 0) {
+            if (a.accumulate_sh) {
+                // nothing to add
+            } else if ((per & 3) == 0) {
                 float4* d4 = reinterpret_cast<float4*>(dst);
                 for (int e = lane; e < ng * per / 4; e += 32) d4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
             } else for (int e = lane; e < ng * per; e += 32) dst[e] = 0.f;
@@ -492,10 +495,15 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PreBwd
             for (int e = lane; e < ng * per / 4; e += 32) {
                 int f = e * 4, gg = f / per, k = f - gg * per;
                 const float* s = ws + gg * stride + k;
-                d4[e] = make_float4(s[0], s[1], s[2], s[3]);
+                float4 v = make_float4(s[0], s[1], s[2], s[3]);
+                if (a.accumulate_sh) { const float4 o = d4[e]; v = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w); }
+                d4[e] = v;
             }
         } else {
-            for (int e = lane; e < ng * per; e += 32) { int gg = e / per, k = e - gg * per; dst[e] = ws[gg * stride + k]; }
+            for (int e = lane; e < ng * per; e += 32) {
+                int gg = e / per, k = e - gg * per;
+                dst[e] = (a.accumulate_sh ? dst[e] : 0.f) + ws[gg * stride + k];
+            }
         }
     }
 }
@@ -509,7 +517,7 @@ int rast_backward(int P, int D, int M, long long R, int W, int H, const float* b
                   const int* radii, void* geom_buf, void* bin_buf, void* img_buf, const float* dL_dpix,
                   const float* dL_dpix_depth, float* grad_arena, float* dL_dmean2D, float* dL_dcolor,
                   float* dL_dopacity, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale,
-                  float* dL_drot, cudaStream_t stream)
+                  float* dL_drot, int accumulate_sh, cudaStream_t stream)
 {
     if (P <= 0) return 0;
     const int grid_x = (W + TILE_X - 1) / TILE_X, grid_y = (H + TILE_Y - 1) / TILE_Y;
@@ -539,7 +547,7 @@ int rast_backward(int P, int D, int M, long long R, int W, int H, const float* b
     a.radii = radii; a.clamped = g.clamped; a.acc = grad_arena;
     a.has_colors_precomp = colors_precomp != nullptr;
     a.dL_dmean2D = dL_dmean2D; a.dL_dcolor = dL_dcolor; a.dL_dopacity = dL_dopacity; a.dL_dmean3D = dL_dmean3D;
-    a.dL_dcov3D = dL_dcov3D; a.dL_dsh = (colors_precomp || M == 0) ? nullptr : dL_dsh;
+    a.dL_dcov3D = dL_dcov3D; a.dL_dsh = (colors_precomp || M == 0) ? nullptr : dL_dsh; a.accumulate_sh = accumulate_sh;
     a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
     const size_t smem = a.dL_dsh ? (size_t)PB_WARPS * 32 * (3 * M + 1) * sizeof(float) : 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -81,6 +81,21 @@ int b200gs_rast_backward(int P, int D, int M, long long num_rendered, int W, int
                          float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
                          b200gs_stream_t stream);
 
+/* Same, but the SH gradient is ADDED to dL_dsh_accum[P,M,3] instead of written (rows of invisible Gaussians are left
+ * untouched): a trainer that renders several views per optimiser step keeps ONE gradient buffer for the step's shared SH
+ * tensor and saves the per-view [P,16,3] allocation plus a full accumulation pass over it. */
+int b200gs_rast_backward_accumulate_sh(int P, int D, int M, long long num_rendered, int W, int H,
+                                       const float* background, const float* means3D, const float* shs,
+                                       const float* colors_precomp, const float* scales, float scale_modifier,
+                                       const float* rotations, const float* cov3D_precomp,
+                                       const float* viewmatrix, const float* projmatrix, const float* campos,
+                                       float tan_fovx, float tan_fovy, const int* radii,
+                                       void* geom_buf, void* bin_buf, void* img_buf,
+                                       const float* dL_dpix, const float* dL_dpix_depth, float* grad_arena,
+                                       float* dL_dmean2D, float* dL_dcolor, float* dL_dopacity, float* dL_dmean3D,
+                                       float* dL_dcov3D, float* dL_dsh_accum, float* dL_dscale, float* dL_drot,
+                                       b200gs_stream_t stream);
+
 /* present[P] (uint8/bool) = view-space z > 0.2 (rasterizer_impl.cu:54-66, :141-153). */
 int b200gs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                         unsigned char* present, b200gs_stream_t stream);
