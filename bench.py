@@ -573,7 +573,6 @@ def _main():
                             "achieved_lane_instr_per_s": rate, "frac_of_fp32_peak_on_reference_cost_model": round(rate / (148 * 128 * 1.965e9), 4)})
     single = [k for k in kernels if "frac_of_measured_hbm_peak" in k]
     dom = single[0] if single else None
-    tensors = len(trainer.trainable)
     launches_per_step = None
     if impl == "b200":
         # kernels of libb200gs launched in the timed region, counted per entry point by CallTimer (KERNELS table)
