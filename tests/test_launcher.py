@@ -63,6 +63,18 @@ def test_launcher_patches_reference_gaussian_model():
         # the reference's render() imports cleanly on top of the drop-ins
         import gaussian_renderer
         assert callable(gaussian_renderer.render)
+        # compute_regulation is routed to the fused kernel on CUDA and falls through to the reference's own method on CPU;
+        # on CPU that method, run over OUR (channels-last) planes, agrees with the oracle restatement
+        import torch
+        from oracle import field_torch
+        assert gm.GaussianModel.compute_regulation.__name__ == "compute_regulation"
+        with torch.no_grad():
+            for p in model._deformation.deformation_net.grid.grids.parameters():
+                p.add_(torch.randn_like(p) * 0.05)
+        ours = model.compute_regulation(0.01, 0.0001, 0.0001)
+        grids = [[p for p in gp] for gp in model._deformation.deformation_net.grid.grids]
+        ref = field_torch.plane_regulation(grids, 0.01, 0.0001, 0.0001)
+        assert torch.allclose(ours, ref, rtol=1e-6, atol=0)
     finally:
         sys.path[:] = saved_path
         for m in set(sys.modules) - saved_mods:
