@@ -50,6 +50,20 @@ def default_opt():
         rotation_lr=0.001, percent_dense=0.01)
 
 
+def expon_lr(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr_delay_mult=1.0):
+    """The reference's learning-rate schedule (utils/general_utils.py:35-68, get_expon_lr_func): log-linear interpolation from
+    lr_init at step 0 to lr_final at max_steps, optionally eased in by a reverse-cosine delay. Python floats, like the
+    reference (the optimiser reads `param_group['lr']` on the host)."""
+    if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+        return 0.0
+    if lr_delay_steps > 0:
+        delay_rate = lr_delay_mult + (1 - lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0.0), 1.0))
+    else:
+        delay_rate = 1.0
+    t = min(max(step / max_steps, 0.0), 1.0)
+    return delay_rate * math.exp(math.log(lr_init) * (1 - t) + math.log(lr_final) * t)
+
+
 class GaussianState(nn.Module):
     def __init__(self, raw, sh_degree=3, hyper=None, spatial_lr_scale=1.0):
         """raw: dict from b200gs.synthetic.make_gaussians (xyz, log_scale, rot, opacity_logit, shs, scene_flow)."""
@@ -97,7 +111,21 @@ class GaussianState(nn.Module):
             {'params': [self._scaling], 'lr': opt.scaling_lr, "name": "scaling"},
             {'params': [self._rotation], 'lr': opt.rotation_lr, "name": "rotation"}]
         self.optimizer = FusedAdam(groups, lr=0.0, eps=1e-15)
+        self._lr_args = {"xyz": (opt.position_lr_init * s, opt.position_lr_final * s),
+                         "deformation": (opt.deformation_lr_init * s, opt.deformation_lr_final * s),
+                         "grid": (opt.grid_lr_init * s, opt.grid_lr_final * s)}
+        self._lr_max_steps = opt.position_lr_max_steps
         return self.optimizer
+
+    def update_learning_rate(self, iteration):
+        """scene/gaussian_model.py:284-298: per-iteration schedule of the xyz / grid / deformation groups (all three decay
+        over position_lr_max_steps; the other groups keep their constant rates)."""
+        for group in self.optimizer.param_groups:
+            name = group["name"]
+            key = "xyz" if name == "xyz" else ("grid" if "grid" in name else ("deformation" if name == "deformation" else None))
+            if key is not None:
+                lr_init, lr_final = self._lr_args[key]
+                group["lr"] = expon_lr(iteration, lr_init, lr_final, self._lr_max_steps)
 
 
 LAST_RASTER_STATE = None      # (R, geomBuffer, binningBuffer, imgBuffer) of the last no-grad render (bench.py counts pairs from it)
