@@ -25,6 +25,7 @@
 //     the CTA and are flushed with one atomic per element per CTA at the end.
 // Shared memory (~225 KB): W2 slot 32 K (hi|lo) | W1 32 K (hi|lo) | DYM 64 K | XH 32 K | DYK 2 x 33 K.
 // TMEM columns: D_RH [0,64)  D_FE [64,128)  D_W2[h] [128 + 64 h, +64)  D_W1 [320,384).
+#include <cstdlib>
 #include "tc5_common.cuh"
 #include "../../include/b200gs.h"
 
@@ -65,6 +66,15 @@ __device__ __forceinline__ float4 lds128(u32 addr)
     return v;
 }
 
+// V2 (experimental, off by default: B200GS_MLP_BWD_V2=1; same arithmetic, same operands, same TMEM map):
+//   * the two 32 KB weight slots alternate between consecutive MMA groups and the image of the NEXT group is streamed in
+//     (cp.async) while the current phase computes, so no phase waits for its weights (W1 is re-streamed per tile from L2);
+//   * MMAs are issued from a warp-uniform branch by the elected lane of warp 0 with the shared-memory descriptors formed by
+//     adding constants to two hoisted bases: ~2 SASS instructions per tcgen05.mma instead of ~15 (the single issuing
+//     thread sits on the critical path of every phase);
+//   * the TMEM-resident weight gradients leave through a padded shared-memory transpose as hi + lo sums, one coalesced
+//     128-bit RED per 4 elements (8x fewer atomics than one scalar atomic per hi / lo element, whole lines per warp).
+template <bool V2>
 __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_constant__ BwdArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -93,8 +103,10 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
         for (int i = 0; i < 8; ++i) cp_async16(reinterpret_cast<float4*>(dst) + tid + BT * i, src + tid + BT * i);
         cp_async_commit();
     };
-    copy_image_pair(W1B, 3);
-    cp_async_wait<0>();
+    if constexpr (!V2) {
+        copy_image_pair(W1B, 3);
+        cp_async_wait<0>();
+    }
     for (int i = tid; i < 98304 / 16; i += BT) reinterpret_cast<float4*>(DYM)[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // DYM + XH
     if (tid == 0) {
         if (smem_u32(DYM) & 1023u) __trap();                          // the swizzle below assumes 1 KB aligned tiles
@@ -119,10 +131,37 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
     const u32 mn_off = (u32)c * 16384u + (u32)((((q >> 1) ^ sub) << 5) | ((q & 1) << 4));
     const u32 k_off = (u32)(8 * c + q) * KCH;
     const int p0 = 32 * pg + sub;                                     // point of iteration i: p0 + 4 i
+    bool first_tile = true;
+    // V2: one MMA group (dX chain into d_col, weight gradient into w_col) issued by the elected lane of warp 0.  Called by
+    // every thread right after the block barrier, so warp 0 is converged; elect.sync picks the same lane every time, which
+    // tcgen05.commit needs (it tracks the MMAs of the executing thread).  Descriptor start addresses are 14-bit fields of
+    // (address >> 4) and shared memory ends below 256 KB, so adding (offset >> 4) to a hoisted base cannot carry out.
+    auto issue_group = [&](u32 sW, u32 d_col, bool d_accumulate, u32 w_col) {
+        if (warp == 0) {
+            if (elect_one()) {
+                tc_fence_after();
+                const u64 dB = smem_desc(sW, MW * 16, 128), dA = smem_desc(sDYK, KCH, 128);
+                const u64 dM = smem_desc(sDYM, 16384, 512) | DESC_SW128_32B, dX = smem_desc(sXH, 16384, 512) | DESC_SW128_32B;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {          // K = 64 out features, 8 per instruction; lo*hi + hi*lo + hi*hi
+                    const u64 bh = dB + (u64)((j * 2 * (MW * 16)) >> 4), bl = bh + (u64)((MW * MW * 4) >> 4);
+                    const u64 ah = dA + (u64)((j * 2 * KCH) >> 4), al = ah + (u64)(KPLANE >> 4);
+                    mma_ss(tbase + d_col, al, bh, id_kk, (d_accumulate || j > 0) ? 1u : 0u);
+                    mma_ss(tbase + d_col, ah, bl, id_kk, 1u);
+                    mma_ss(tbase + d_col, ah, bh, id_kk, 1u);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j)           // K = 128 points, 8 per instruction (two 4-row atoms)
+                    mma_ss(tbase + w_col, dM + (u64)((j * 1024) >> 4), dX + (u64)((j * 1024) >> 4), id_mn, (first_tile && j == 0) ? 0u : 1u);
+                tc_commit(bar);
+            }
+            __syncwarp();
+        }
+    };
 
     u32 phase = 0;
+    u32 ngroup = 0;                  // V2: MMA groups committed so far; group n reads the weight slot n & 1 (0 = W2B, 1 = W1B)
     bool pending = false;            // an MMA group has been committed and not yet waited for
-    bool first_tile = true;
     long long prev_row = -1;         // row (TMEM mapping) whose d_feature is still in D_FE
     float gW3[3][4][4], gB2[3][4], gB3[3][4], gB1[4];
 #pragma unroll
@@ -195,6 +234,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
         load_stash(hrow, 0, (long long)blockIdx.x * ROWS + p0);
         load_phase_rows(next_phase(-1), xin, (long long)blockIdx.x * ROWS + p0);
     }
+    if constexpr (V2) copy_image_pair(W2B, next_phase(-1));            // group 0's weights -> slot 0 (waited for before its MMAs)
     for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const long long row0 = blk * ROWS + p0;
         // ---- relu(hidden): sign mask for dh + B operand of dW2 ----
@@ -240,7 +280,8 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
             }
             load_phase_rows(next_phase(h), xin, row0);          // next head's rows, or the feature rows
             drain();                 // the previous MMA group still reads DYK / DYM / XH and the W2 slot
-            copy_image_pair(W2B, h);
+            if constexpr (!V2) copy_image_pair(W2B, h);
+            else copy_image_pair((ngroup & 1u) ? W2B : W1B, next_phase(h));   // the NEXT group's image -> the slot the drained group used
             if (!h_staged) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) sts128(sXH + mn_off + (u32)(p0 + 4 * i) * 128u, tf32x4(hrow[i]));
@@ -256,11 +297,14 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
                 sts128(sDYM + mn_off + pp * 128u, hi);
                 sts128(sDYM + 32768u + mn_off + pp * 128u, lo);
             }
-            cp_async_wait<0>();
+            if constexpr (V2) cp_async_wait<1>(); else cp_async_wait<0>();      // V2: all but the next group's image
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_before();
             __syncthreads();
-            if (tid == 0) {
+            if constexpr (V2) {
+                issue_group((ngroup & 1u) ? sW1 : sW2, C_RH, rh_started, C_W2 + 64 * h);
+                ++ngroup;
+            } else if (tid == 0) {
                 tc_fence_after();
                 for (int j = 0; j < 8; ++j) {          // K = 64 out features, 8 per instruction; lo*hi + hi*lo + hi*hi
                     const u64 bh = smem_desc(sW2 + j * 2 * (MW * 16), MW * 16, 128);
@@ -288,6 +332,10 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
             load_phase_rows(next_phase(-1), xin, (blk + gridDim.x) * ROWS + p0);
         }
         drain();
+        if constexpr (V2) {          // the next tile's first image -> the slot the drained group used (an empty group keeps the count)
+            if (blk + gridDim.x < nblocks) copy_image_pair((ngroup & 1u) ? W2B : W1B, next_phase(-1));
+            else cp_async_commit();
+        }
         {   // D_RH comes out of TMEM as (lane = point, 32 columns); bounce it through the DYK hi plane to reach the SIMT mapping
             u32 v[32];
             if (rh_started) {
@@ -322,10 +370,14 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
             sts128(sDYM + 32768u + mn_off + pp * 128u, lo);
             sts128(sXH + mn_off + pp * 128u, tf32x4(frow[i]));
         }
+        if constexpr (V2) cp_async_wait<1>();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if constexpr (V2) {
+            issue_group((ngroup & 1u) ? sW1 : sW2, C_FE, false, C_W1);
+            ++ngroup;
+        } else if (tid == 0) {
             tc_fence_after();
             for (int j = 0; j < 8; ++j) {
                 const u64 bh = smem_desc(sW1 + j * 2 * (MW * 16), MW * 16, 128);
@@ -349,7 +401,34 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
     // ---- flush ----
     if (!first_tile) {
         // TMEM-resident weight gradients: lanes 0..63 = out feature from dY_hi, lanes 64..127 the same from dY_lo
-        {
+        if constexpr (V2) {
+            // through shared memory (DYM is free: every MMA has completed), rows padded to 68 floats so that both the
+            // lane-per-row 128-bit stores and the row-contiguous 128-bit loads are conflict free; then hi + lo row pairs
+            // leave as one 128-bit RED per 4 elements, 512 contiguous bytes per warp.  CTAs start at different matrices /
+            // row blocks so that the 148 of them do not all hit the same lines at once.
+            constexpr u32 SP = 68 * 4;
+            for (int mi = 0; mi < 4; ++mi) {
+                const int m = (mi + (int)blockIdx.x) & 3;
+                if (m < 3 && !a.w.w2[m]) continue;
+                float* dst = m < 3 ? a.gw.w2[m] : a.gw.w1;
+                u32 v[32];
+                tmem_ld32(lane_addr + (m < 3 ? C_W2 + 64 * m : C_W1) + 32 * cT, v);
+                tmem_wait_ld();
+                __syncthreads();                                  // the previous matrix has been read out of the staging rows
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    sts128(sDYM + (u32)pT * SP + (u32)(32 * cT + 4 * j) * 4u,
+                           make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int idx = tid + BT * ((k + (int)(blockIdx.x >> 2)) & 3);      // 1024 float4 = 64 rows x 16
+                    const int r = idx >> 4, c4 = idx & 15;
+                    const float4 x = lds128(sDYM + (u32)r * SP + (u32)c4 * 16u), y = lds128(sDYM + (u32)(r + 64) * SP + (u32)c4 * 16u);
+                    red_add_v4(dst + r * MW + 4 * c4, x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+                }
+            }
+        } else {
             for (int m = 0; m < 4; ++m) {
                 if (m < 3 && !a.w.w2[m]) continue;
                 float* dst = m < 3 ? a.gw.w2[m] : a.gw.w1;
@@ -411,8 +490,18 @@ int deform_mlp_backward_tc5(const b200gs_mlp_weights* w, const b200gs_mlp_grads*
     const long long nblocks = (P + tc5::ROWS - 1) / tc5::ROWS;
     const int grid = (int)(nblocks < NUM_SMS ? nblocks : NUM_SMS);
     const size_t smem = tc5::bwd_smem();
-    cudaFuncSetAttribute(tc5::deform_mlp_bwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    tc5::deform_mlp_bwd_tc5_kernel<<<grid, tc5::BT, smem, stream>>>(a);
+    // experimental variant (see the kernel's header comment): opt-in until it has been measured on the GPU; needs 16-byte
+    // aligned W1 / W2 gradient rows for its 128-bit REDs
+    static const bool want_v2 = [] { const char* e = getenv("B200GS_MLP_BWD_V2"); return e && e[0] == '1'; }();
+    bool v2 = want_v2 && ((uintptr_t)gw->w1 & 15) == 0;
+    for (int h = 0; h < 3; ++h) v2 = v2 && (!w->w2[h] || ((uintptr_t)gw->w2[h] & 15) == 0);
+    if (v2) {
+        cudaFuncSetAttribute(tc5::deform_mlp_bwd_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc5::deform_mlp_bwd_tc5_kernel<true><<<grid, tc5::BT, smem, stream>>>(a);
+        return check_launch("deform_mlp_backward(tcgen05 v2)");
+    }
+    cudaFuncSetAttribute(tc5::deform_mlp_bwd_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc5::deform_mlp_bwd_tc5_kernel<false><<<grid, tc5::BT, smem, stream>>>(a);
     return check_launch("deform_mlp_backward(tcgen05)");
 }
 

@@ -14,6 +14,7 @@
 //   * the epilogue reads the accumulator with tcgen05.ld (32 lanes x 32 bit, 32 columns at a time).
 // TMEM columns: [0, 2F) feature hi|lo, re-used as relu(hidden) hi [0,64) | lo [64,128);
 //               [2F, 2F+128) relu(z) hi|lo; [2F+128, +64) accumulator; [2F+192, +16) head output.
+#include <cstdlib>
 #include "tc5_common.cuh"
 #include "../../include/b200gs.h"
 
@@ -277,7 +278,10 @@ __device__ __forceinline__ void stage_kmajor2(float* __restrict__ hi, float* __r
     }
 }
 
-template <int F>
+// ELECT (experimental, off by default: B200GS_MLP_FWD_ELECT=1): the MMAs are issued from a warp-uniform branch by the elected lane
+// of warp 0 (tc5_common.cuh elect_one) instead of `if (tid == 0)`, which makes the compiler wrap every tcgen05.mma in an
+// ELECT / BRA.U.ANY loop; same instructions, same order, same issuing thread.
+template <int F, bool ELECT>
 __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __grid_constant__ FwdArgs a)
 {
     extern __shared__ __align__(1024) float smem[];
@@ -327,6 +331,11 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
     u32 parity = 0;
 
     auto sync_then = [&]() { tmem_wait_st(); tc_fence_before(); __syncthreads(); };
+    // the thread that issues the MMAs; every call site follows a block barrier, so warp 0 is converged for elect.sync
+    auto issuer = [&]() -> bool {
+        if constexpr (ELECT) return warp == 0 && elect_one();
+        else return tid == 0;
+    };
     // epilogue of one 64-wide layer for this thread's 32 columns: bias, ReLU, stash, split; returns hi / lo in v / lo
     auto layer_epilogue = [&](u32 d_col, const float* b, float* stash_plane, long long row, bool valid, u32* v, u32* lo) {
         tmem_ld32(lane_addr + d_col + 32 * cT, v);
@@ -369,7 +378,7 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
             tmem_st32(lane_addr + C_FE_LO + FH * cT + 32 * c, lo);
         }
         sync_then();
-        if (tid == 0) {
+        if (issuer()) {
             tc_fence_after();
             issue_layer(tbase + C_D2, tbase, tbase + C_FE_LO, smem_u32(W1h), smem_u32(W1l), MW, F, idesc64);
             tc_commit(bars + 0);
@@ -399,7 +408,7 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
         tmem_st32(lane_addr + C_H_HI + 32 * cT, v);
         tmem_st32(lane_addr + C_H_LO + 32 * cT, lo);
         sync_then();
-        if (tid == 0) {
+        if (issuer()) {
             tc_fence_after();
             issue_layer(tbase + C_D2, tbase + C_H_HI, tbase + C_H_LO, smem_u32(W2h), smem_u32(W2l), MW, MW, idesc64);
             tc_commit(bars + 1);
@@ -419,7 +428,7 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
             tmem_st32(lane_addr + C_Z_HI + 32 * cT, v);
             tmem_st32(lane_addr + C_Z_LO + 32 * cT, lo);
             sync_then();
-            if (tid == 0) {
+            if (issuer()) {
                 tc_fence_after();
                 issue_layer(tbase + C_D3 + 16 * h, tbase + C_Z_HI, tbase + C_Z_LO, smem_u32(W3h + h * 16 * MW), smem_u32(W3l + h * 16 * MW), 16, MW, idesc16);
                 tc_commit(bars + 4 + h);
@@ -491,12 +500,19 @@ int deform_mlp_forward_tc5(const b200gs_mlp_weights* w, long long P, const float
     const int grid = (int)(nblocks < NUM_SMS ? nblocks : NUM_SMS);
     const size_t smem = tc5::fwd_smem(w->feat_dim);
     if (w->w2[0] && w->w2[1] && w->w2[2]) {          // all heads on (the reference's configuration): pipelined kernel
+        // experimental issue idiom (see the kernel's comment): opt-in until it has been measured on the GPU
+        static const bool elect = [] { const char* e = getenv("B200GS_MLP_FWD_ELECT"); return e && e[0] == '1'; }();
+        if (elect && w->feat_dim == 64) {
+            cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5v2_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            tc5::deform_mlp_fwd_tc5v2_kernel<64, true><<<grid, tc5::NT2, smem, stream>>>(a);
+            return check_launch("deform_mlp_forward(tcgen05 v2, elected issuer)");
+        }
         if (w->feat_dim == 64) {
-            cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5v2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            tc5::deform_mlp_fwd_tc5v2_kernel<64><<<grid, tc5::NT2, smem, stream>>>(a);
+            cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5v2_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            tc5::deform_mlp_fwd_tc5v2_kernel<64, false><<<grid, tc5::NT2, smem, stream>>>(a);
         } else {
-            cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5v2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            tc5::deform_mlp_fwd_tc5v2_kernel<128><<<grid, tc5::NT2, smem, stream>>>(a);
+            cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5v2_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            tc5::deform_mlp_fwd_tc5v2_kernel<128, false><<<grid, tc5::NT2, smem, stream>>>(a);
         }
         return check_launch("deform_mlp_forward(tcgen05 v2)");
     }

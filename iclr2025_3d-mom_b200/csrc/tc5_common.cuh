@@ -63,6 +63,15 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity)
         if (++spins > (1u << 24)) __trap();      // never hang the GPU on a protocol error
     }
 }
+// One lane of a converged warp (the same lane on every call): the issuer of tcgen05.mma / tcgen05.commit.  Used inside a
+// warp-uniform branch this compiles to plain straight-line UTCHMMA sequences, where `if (threadIdx.x == 0)` makes the
+// compiler wrap every MMA in an ELECT / BRA.U.ANY loop.
+__device__ __forceinline__ bool elect_one()
+{
+    u32 pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(u64* bar)
