@@ -35,6 +35,10 @@ def _declare(L):
     L.b200gs_last_error.restype = c_char_p
     L.b200gs_last_error.argtypes = []
     L.b200gs_version.restype = c_int
+    L.b200gs_set_option.restype = c_int
+    L.b200gs_set_option.argtypes = [c_char_p, c_int]
+    L.b200gs_get_option.restype = c_int
+    L.b200gs_get_option.argtypes = [c_char_p]
     L.b200gs_rast_buffer_sizes.restype = c_int
     L.b200gs_rast_buffer_sizes.argtypes = [c_int, c_longlong, c_int, c_int, POINTER(c_size_t)]
     L.b200gs_rast_forward_stage1.restype = c_int

@@ -1,6 +1,7 @@
 // extern "C" surface of libb200gs.so (declared in include/b200gs.h).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include "rast_state.cuh"
@@ -9,6 +10,11 @@
 namespace b200gs {
 
 static thread_local char g_err[512] = "";
+
+// Opt-in kernel variants (b200gs_set_option); the environment gives the initial values so that unmodified callers can try them.
+static int env_flag(const char* name) { const char* e = getenv(name); return e && e[0] == '1'; }
+int g_opt_mlp_bwd_v2 = env_flag("B200GS_MLP_BWD_V2");
+int g_opt_mlp_fwd_elect = env_flag("B200GS_MLP_FWD_ELECT");
 
 void set_error(const char* fmt, ...)
 {
@@ -92,6 +98,20 @@ extern "C" {
 
 const char* b200gs_last_error(void) { return g_err; }
 int b200gs_version(void) { return 100; }
+
+int b200gs_set_option(const char* name, int value)
+{
+    if (name && !strcmp(name, "mlp_bwd_v2")) { b200gs::g_opt_mlp_bwd_v2 = value; return 0; }
+    if (name && !strcmp(name, "mlp_fwd_elect")) { b200gs::g_opt_mlp_fwd_elect = value; return 0; }
+    set_error("b200gs_set_option: unknown option '%s'", name ? name : "(null)");
+    return -1;
+}
+int b200gs_get_option(const char* name)
+{
+    if (name && !strcmp(name, "mlp_bwd_v2")) return b200gs::g_opt_mlp_bwd_v2;
+    if (name && !strcmp(name, "mlp_fwd_elect")) return b200gs::g_opt_mlp_fwd_elect;
+    return -1;
+}
 
 int b200gs_rast_buffer_sizes(int P, long long R, int W, int H, size_t out_bytes[3])
 {

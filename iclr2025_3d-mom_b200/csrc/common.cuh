@@ -21,6 +21,8 @@ typedef uint64_t u64;
 // Per-thread last error text (the library keeps no other global state).
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);   // returns 0 or sets error and returns -1
+// opt-in kernel variants, see b200gs_set_option (api.cu)
+extern int g_opt_mlp_bwd_v2, g_opt_mlp_fwd_elect;
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

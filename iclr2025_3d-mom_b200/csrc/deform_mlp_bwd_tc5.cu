@@ -25,7 +25,6 @@
 //     the CTA and are flushed with one atomic per element per CTA at the end.
 // Shared memory (~225 KB): W2 slot 32 K (hi|lo) | W1 32 K (hi|lo) | DYM 64 K | XH 32 K | DYK 2 x 33 K.
 // TMEM columns: D_RH [0,64)  D_FE [64,128)  D_W2[h] [128 + 64 h, +64)  D_W1 [320,384).
-#include <cstdlib>
 #include "tc5_common.cuh"
 #include "../../include/b200gs.h"
 
@@ -66,7 +65,7 @@ __device__ __forceinline__ float4 lds128(u32 addr)
     return v;
 }
 
-// V2 (experimental, off by default: B200GS_MLP_BWD_V2=1; same arithmetic, same operands, same TMEM map):
+// V2 (experimental, off by default: b200gs_set_option("mlp_bwd_v2", 1) or B200GS_MLP_BWD_V2=1; same arithmetic, same operands, same TMEM map):
 //   * the two 32 KB weight slots alternate between consecutive MMA groups and the image of the NEXT group is streamed in
 //     (cp.async) while the current phase computes, so no phase waits for its weights (W1 is re-streamed per tile from L2);
 //   * MMAs are issued from a warp-uniform branch by the elected lane of warp 0 with the shared-memory descriptors formed by
@@ -492,8 +491,7 @@ int deform_mlp_backward_tc5(const b200gs_mlp_weights* w, const b200gs_mlp_grads*
     const size_t smem = tc5::bwd_smem();
     // experimental variant (see the kernel's header comment): opt-in until it has been measured on the GPU; needs 16-byte
     // aligned W1 / W2 gradient rows for its 128-bit REDs
-    static const bool want_v2 = [] { const char* e = getenv("B200GS_MLP_BWD_V2"); return e && e[0] == '1'; }();
-    bool v2 = want_v2 && ((uintptr_t)gw->w1 & 15) == 0;
+    bool v2 = g_opt_mlp_bwd_v2 != 0 && ((uintptr_t)gw->w1 & 15) == 0;
     for (int h = 0; h < 3; ++h) v2 = v2 && (!w->w2[h] || ((uintptr_t)gw->w2[h] & 15) == 0);
     if (v2) {
         cudaFuncSetAttribute(tc5::deform_mlp_bwd_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

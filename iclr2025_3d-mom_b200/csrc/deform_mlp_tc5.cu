@@ -14,7 +14,6 @@
 //   * the epilogue reads the accumulator with tcgen05.ld (32 lanes x 32 bit, 32 columns at a time).
 // TMEM columns: [0, 2F) feature hi|lo, re-used as relu(hidden) hi [0,64) | lo [64,128);
 //               [2F, 2F+128) relu(z) hi|lo; [2F+128, +64) accumulator; [2F+192, +16) head output.
-#include <cstdlib>
 #include "tc5_common.cuh"
 #include "../../include/b200gs.h"
 
@@ -278,7 +277,7 @@ __device__ __forceinline__ void stage_kmajor2(float* __restrict__ hi, float* __r
     }
 }
 
-// ELECT (experimental, off by default: B200GS_MLP_FWD_ELECT=1): the MMAs are issued from a warp-uniform branch by the elected lane
+// ELECT (experimental, off by default: b200gs_set_option("mlp_fwd_elect", 1) or B200GS_MLP_FWD_ELECT=1): the MMAs are issued from a warp-uniform branch by the elected lane
 // of warp 0 (tc5_common.cuh elect_one) instead of `if (tid == 0)`, which makes the compiler wrap every tcgen05.mma in an
 // ELECT / BRA.U.ANY loop; same instructions, same order, same issuing thread.
 template <int F, bool ELECT>
@@ -501,8 +500,7 @@ int deform_mlp_forward_tc5(const b200gs_mlp_weights* w, long long P, const float
     const size_t smem = tc5::fwd_smem(w->feat_dim);
     if (w->w2[0] && w->w2[1] && w->w2[2]) {          // all heads on (the reference's configuration): pipelined kernel
         // experimental issue idiom (see the kernel's comment): opt-in until it has been measured on the GPU
-        static const bool elect = [] { const char* e = getenv("B200GS_MLP_FWD_ELECT"); return e && e[0] == '1'; }();
-        if (elect && w->feat_dim == 64) {
+        if (g_opt_mlp_fwd_elect != 0 && w->feat_dim == 64) {
             cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5v2_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             tc5::deform_mlp_fwd_tc5v2_kernel<64, true><<<grid, tc5::NT2, smem, stream>>>(a);
             return check_launch("deform_mlp_forward(tcgen05 v2, elected issuer)");

@@ -29,6 +29,13 @@ typedef void* b200gs_stream_t; /* cudaStream_t */
 
 const char* b200gs_last_error(void);
 int b200gs_version(void);
+/* Opt-in kernel variants, process-wide, default 0 (initial value 1 if the environment variable B200GS_<NAME> is "1"):
+ *   "mlp_bwd_v2"     deformation-MLP backward with alternating weight slots, elected MMA issuer, coalesced gradient flush
+ *   "mlp_fwd_elect"  deformation-MLP forward with the elected MMA issuer
+ * Same arithmetic as the default kernels; they stay opt-in until measured on a B200.
+ * set: 0 on success, non-zero for an unknown name; get: the value, or -1 for an unknown name. */
+int b200gs_set_option(const char* name, int value);
+int b200gs_get_option(const char* name);
 
 /* ---------------------------------------------------------------------------------------
  * Rasterizer — replaces _C.rasterize_gaussians / rasterize_gaussians_backward / mark_visible

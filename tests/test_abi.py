@@ -88,3 +88,16 @@ def test_call_timer_table_names_are_abi_entries():
     for name in _lib.CallTimer.KERNELS:
         assert name in declared, name
         assert hasattr(L, name), name
+
+
+def test_kernel_variant_options_default_off_and_toggle():
+    """The opt-in kernel variants (include/b200gs.h: b200gs_set_option) are off unless asked for; unknown names are an error."""
+    from b200gs import _lib
+    L = _lib.lib()
+    for name in (b"mlp_bwd_v2", b"mlp_fwd_elect"):
+        env_on = os.environ.get("B200GS_" + name.decode().upper()) == "1"
+        assert L.b200gs_get_option(name) == (1 if env_on else 0)
+        assert L.b200gs_set_option(name, 1) == 0 and L.b200gs_get_option(name) == 1
+        assert L.b200gs_set_option(name, 1 if env_on else 0) == 0
+    assert L.b200gs_set_option(b"no_such_option", 1) != 0 and b"unknown option" in L.b200gs_last_error()
+    assert L.b200gs_get_option(b"no_such_option") == -1
