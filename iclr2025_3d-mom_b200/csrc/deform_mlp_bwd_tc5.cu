@@ -73,9 +73,13 @@ __device__ __forceinline__ float4 lds128(u32 addr)
 //     thread sits on the critical path of every phase);
 //   * the TMEM-resident weight gradients leave through a padded shared-memory transpose as hi + lo sums, one coalesced
 //     128-bit RED per 4 elements (8x fewer atomics than one scalar atomic per hi / lo element, whole lines per warp).
-template <bool V2>
+// VER: 0 = default; otherwise bit 0 = V2, bits 1-2 = how the upstream gradients d_out reach a phase (0: loaded at its start,
+// 1: loaded into registers one phase ahead, 2 / 3: prefetched into L1 / L2 one phase ahead), bit 3 = the previous tile's
+// d_feature rows leave TMEM in four 8-column parts, one per MMA drain, instead of one 32 KB burst at the tile boundary.
+template <int VER>
 __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_constant__ BwdArgs a)
 {
+    constexpr bool V2 = (VER & 1) != 0, DIN_AHEAD = ((VER >> 1) & 3) == 1, DIN_PREFETCH = ((VER >> 1) & 3) >= 2, SPLIT_FE = ((VER >> 3) & 1) != 0;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* W2B = reinterpret_cast<float*>(smem_raw);                 // current head: hi [16 k-chunks][64 n][4] | lo  (32 KB)
     float* W1B = W2B + 2 * MW * MW;                                  // hi | lo                                      (32 KB)
@@ -174,22 +178,42 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
 #pragma unroll
     for (int e = 0; e < 4; ++e) gB1[e] = 0.f;
 
-    auto drain = [&]() {             // wait for the committed MMA group; then D_FE of the previous tile can be stored
+    int fe_part = 0;                 // SPLIT_FE: 8-column parts of the previous tile's d_feature rows already stored
+    auto drain = [&](bool all = true) {   // wait for the committed MMA group; then D_FE of the previous tile can be stored
         if (pending) {
             mbar_wait(bar, phase); phase ^= 1; pending = false;
             tc_fence_after();
         }
         if (prev_row >= 0) {
-            u32 v[32];
-            tmem_ld32(lane_addr + C_FE + 32 * cT, v);
-            tmem_wait_ld();
-            if (prev_row < a.P) {
+            if constexpr (SPLIT_FE) {
+                // D_FE stays valid until this tile's feature-phase MMAs, so its rows can leave a quarter at a time
+                // (`all`: everything that is left -- the feature phase and the end of the kernel)
+                do {
+                    u32 v[8];
+                    tmem_ld8(lane_addr + C_FE + 32 * cT + 8 * fe_part, v);
+                    tmem_wait_ld();
+                    if (prev_row < a.P) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(a.d_feat + (a.w.feat_tiled ? stash_off(prev_row, 32 * cT) + 16 * j : (size_t)prev_row * MW + 32 * cT + 4 * j)) =
-                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        for (int j = 0; j < 2; ++j)
+                            *reinterpret_cast<float4*>(a.d_feat + (a.w.feat_tiled ? stash_off(prev_row, 32 * cT) + 16 * (2 * fe_part + j)
+                                                                                  : (size_t)prev_row * MW + 32 * cT + 4 * (2 * fe_part + j))) =
+                                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    }
+                    ++fe_part;
+                } while (all && fe_part < 4);
+                if (fe_part == 4) { prev_row = -1; fe_part = 0; }
+            } else {
+                u32 v[32];
+                tmem_ld32(lane_addr + C_FE + 32 * cT, v);
+                tmem_wait_ld();
+                if (prev_row < a.P) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(a.d_feat + (a.w.feat_tiled ? stash_off(prev_row, 32 * cT) + 16 * j : (size_t)prev_row * MW + 32 * cT + 4 * j)) =
+                            make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                }
+                prev_row = -1;
             }
-            prev_row = -1;
         }
     };
 
@@ -227,6 +251,17 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
         }
     };
 
+    // the d_out rows of one tile are one contiguous run of 128 * kd floats: one prefetch per 128-byte line, one line per thread
+    auto prefetch_phase_dout = [&](int ph, long long tile) {
+        if (ph >= 3) return;
+        const float* dsrc = ph == 0 ? a.d_pts : (ph == 1 ? a.d_scales : a.d_rot);
+        const int kd = ph == 2 ? 4 : 3;
+        if (!dsrc || tid > 4 * kd) return;                                   // 128 * kd * 4 bytes = 4 kd lines (+1: unaligned base)
+        const char* p = reinterpret_cast<const char*>(dsrc + (size_t)tile * ROWS * kd) + 128 * tid;
+        if (p >= reinterpret_cast<const char*>(dsrc + (size_t)a.P * kd)) return;
+        if constexpr (((VER >> 1) & 3) == 2) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+        else asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+    };
     const long long nblocks = (a.P + ROWS - 1) / ROWS;
     float4 hrow[8], xin[8];
     if ((long long)blockIdx.x < nblocks) {
@@ -234,6 +269,8 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
         load_phase_rows(next_phase(-1), xin, (long long)blockIdx.x * ROWS + p0);
     }
     if constexpr (V2) copy_image_pair(W2B, next_phase(-1));            // group 0's weights -> slot 0 (waited for before its MMAs)
+    float din_next[8][4];
+    if constexpr (DIN_AHEAD) load_phase_dout(next_phase(-1), din_next, (long long)blockIdx.x * ROWS + p0);
     for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const long long row0 = blk * ROWS + p0;
         // ---- relu(hidden): sign mask for dh + B operand of dW2 ----
@@ -251,7 +288,12 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
 #pragma unroll
             for (int k = 0; k < 4; ++k) w3[k] = k < kd ? __ldg(reinterpret_cast<const float4*>(a.w.w3[h] + k * MW + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
             float din[8][4];
-            load_phase_dout(h, din, row0);
+            if constexpr (DIN_AHEAD) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) din[i][k] = din_next[i][k];
+            } else load_phase_dout(h, din, row0);
             float dz[8][4];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -278,7 +320,9 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
                 }
             }
             load_phase_rows(next_phase(h), xin, row0);          // next head's rows, or the feature rows
-            drain();                 // the previous MMA group still reads DYK / DYM / XH and the W2 slot
+            if constexpr (DIN_AHEAD) load_phase_dout(next_phase(h), din_next, row0);        // (nothing for the feature phase)
+            if constexpr (DIN_PREFETCH) prefetch_phase_dout(next_phase(h), blk);
+            drain(false);            // the previous MMA group still reads DYK / DYM / XH and the W2 slot
             if constexpr (!V2) copy_image_pair(W2B, h);
             else copy_image_pair((ngroup & 1u) ? W2B : W1B, next_phase(h));   // the NEXT group's image -> the slot the drained group used
             if (!h_staged) {
@@ -329,6 +373,8 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
         if (blk + gridDim.x < nblocks) {                              // next tile: relu(hidden) rows and the first phase's inputs
             load_stash(hrow, 0, (blk + gridDim.x) * ROWS + p0);
             load_phase_rows(next_phase(-1), xin, (blk + gridDim.x) * ROWS + p0);
+            if constexpr (DIN_AHEAD) load_phase_dout(next_phase(-1), din_next, (blk + gridDim.x) * ROWS + p0);
+            if constexpr (DIN_PREFETCH) prefetch_phase_dout(next_phase(-1), blk + gridDim.x);
         }
         drain();
         if constexpr (V2) {          // the next tile's first image -> the slot the drained group used (an empty group keeps the count)
@@ -494,12 +540,22 @@ int deform_mlp_backward_tc5(const b200gs_mlp_weights* w, const b200gs_mlp_grads*
     bool v2 = g_opt_mlp_bwd_v2 != 0 && ((uintptr_t)gw->w1 & 15) == 0;
     for (int h = 0; h < 3; ++h) v2 = v2 && (!w->w2[h] || ((uintptr_t)gw->w2[h] & 15) == 0);
     if (v2) {
-        cudaFuncSetAttribute(tc5::deform_mlp_bwd_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tc5::deform_mlp_bwd_tc5_kernel<true><<<grid, tc5::BT, smem, stream>>>(a);
+        void (*kern)(tc5::BwdArgs) = tc5::deform_mlp_bwd_tc5_kernel<1>;
+        switch (g_opt_mlp_bwd_v2) {          // see the kernel's VER comment
+            case 3: kern = tc5::deform_mlp_bwd_tc5_kernel<3>; break;
+            case 5: kern = tc5::deform_mlp_bwd_tc5_kernel<5>; break;
+            case 7: kern = tc5::deform_mlp_bwd_tc5_kernel<7>; break;
+            case 9: kern = tc5::deform_mlp_bwd_tc5_kernel<9>; break;
+            case 13: kern = tc5::deform_mlp_bwd_tc5_kernel<13>; break;
+            case 15: kern = tc5::deform_mlp_bwd_tc5_kernel<15>; break;
+            default: break;
+        }
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, tc5::BT, smem, stream>>>(a);
         return check_launch("deform_mlp_backward(tcgen05 v2)");
     }
-    cudaFuncSetAttribute(tc5::deform_mlp_bwd_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    tc5::deform_mlp_bwd_tc5_kernel<false><<<grid, tc5::BT, smem, stream>>>(a);
+    cudaFuncSetAttribute(tc5::deform_mlp_bwd_tc5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc5::deform_mlp_bwd_tc5_kernel<0><<<grid, tc5::BT, smem, stream>>>(a);
     return check_launch("deform_mlp_backward(tcgen05)");
 }
 

@@ -110,6 +110,10 @@ __device__ __forceinline__ void tmem_ld16(u32 addr, u32* v)
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : R8(v, 0), R8(v, 8) : "r"(addr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(u32 addr, u32* v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : R8(v, 0) : "r"(addr) : "memory");
+}
 __device__ __forceinline__ void tmem_st32(u32 addr, const u32* v)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
