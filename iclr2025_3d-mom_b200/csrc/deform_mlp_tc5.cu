@@ -280,9 +280,12 @@ __device__ __forceinline__ void stage_kmajor2(float* __restrict__ hi, float* __r
 // ELECT (experimental, off by default: b200gs_set_option("mlp_fwd_elect", 1) or B200GS_MLP_FWD_ELECT=1): the MMAs are issued from a warp-uniform branch by the elected lane
 // of warp 0 (tc5_common.cuh elect_one) instead of `if (tid == 0)`, which makes the compiler wrap every tcgen05.mma in an
 // ELECT / BRA.U.ANY loop; same instructions, same order, same issuing thread.
-template <int F, bool ELECT>
+// MODE 0: default; 1: ELECT; 2: ELECT + the activation-stash stores of a layer are issued AFTER the next layer's MMAs have been
+// started (they are not on the MMA -> epilogue -> MMA chain, the values just stay in registers a little longer).
+template <int F, int MODE>
 __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __grid_constant__ FwdArgs a)
 {
+    constexpr bool ELECT = MODE >= 1, DEFER_STASH = MODE >= 2;
     extern __shared__ __align__(1024) float smem[];
     float* W1h = smem;                         // [F/4][64][4]
     float* W1l = W1h + MW * F;
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
         tmem_wait_ld();
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(fmaxf(__uint_as_float(v[e]) + b[32 * cT + e], 0.f));
-        if (valid) {
+        if (valid && !DEFER_STASH) {
             float* dst = stash_plane + stash_off(row, 32 * cT);          // this thread's 8 chunks are 16 floats apart
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -350,6 +353,15 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
         }
 #pragma unroll
         for (int e = 0; e < 32; ++e) lo[e] = __float_as_uint(tf32_lo(__uint_as_float(v[e])));      // hi = the raw value (hardware truncates)
+    };
+    auto deferred_stash = [&](float* stash_plane, long long row, bool valid, const u32* v) {
+        if (DEFER_STASH && valid) {
+            float* dst = stash_plane + stash_off(row, 32 * cT);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(dst + 16 * j) =
+                    make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
     };
 
     const long long nblocks = (a.P + ROWS - 1) / ROWS;
@@ -414,6 +426,7 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
             issue_layer(tbase + C_D2 + 64, tbase + C_H_HI, tbase + C_H_LO, smem_u32(W2h + MW * MW), smem_u32(W2l + MW * MW), MW, MW, idesc64);
             tc_commit(bars + 2);
         }
+        deferred_stash(a.saved, r, valid, v);
         // ---- heads ----
 #pragma unroll
         for (int h = 0; h < 3; ++h) {
@@ -436,6 +449,7 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
                     tc_commit(bars + 3);
                 }
             }
+            deferred_stash(a.saved + (size_t)(1 + h) * stash_plane_floats(a.P), r, valid, v);
         }
         // ---- outputs ----
         mbar_wait(bars + 6, parity);
@@ -501,16 +515,17 @@ int deform_mlp_forward_tc5(const b200gs_mlp_weights* w, long long P, const float
     if (w->w2[0] && w->w2[1] && w->w2[2]) {          // all heads on (the reference's configuration): pipelined kernel
         // experimental issue idiom (see the kernel's comment): opt-in until it has been measured on the GPU
         if (g_opt_mlp_fwd_elect != 0 && w->feat_dim == 64) {
-            cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5v2_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            tc5::deform_mlp_fwd_tc5v2_kernel<64, true><<<grid, tc5::NT2, smem, stream>>>(a);
+            void (*kern)(tc5::FwdArgs) = g_opt_mlp_fwd_elect >= 2 ? tc5::deform_mlp_fwd_tc5v2_kernel<64, 2> : tc5::deform_mlp_fwd_tc5v2_kernel<64, 1>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<grid, tc5::NT2, smem, stream>>>(a);
             return check_launch("deform_mlp_forward(tcgen05 v2, elected issuer)");
         }
         if (w->feat_dim == 64) {
-            cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5v2_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            tc5::deform_mlp_fwd_tc5v2_kernel<64, false><<<grid, tc5::NT2, smem, stream>>>(a);
+            cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5v2_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            tc5::deform_mlp_fwd_tc5v2_kernel<64, 0><<<grid, tc5::NT2, smem, stream>>>(a);
         } else {
-            cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5v2_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            tc5::deform_mlp_fwd_tc5v2_kernel<128, false><<<grid, tc5::NT2, smem, stream>>>(a);
+            cudaFuncSetAttribute(tc5::deform_mlp_fwd_tc5v2_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            tc5::deform_mlp_fwd_tc5v2_kernel<128, 0><<<grid, tc5::NT2, smem, stream>>>(a);
         }
         return check_launch("deform_mlp_forward(tcgen05 v2)");
     }

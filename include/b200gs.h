@@ -31,7 +31,8 @@ const char* b200gs_last_error(void);
 int b200gs_version(void);
 /* Opt-in kernel variants, process-wide, default 0 (initial value 1 if the environment variable B200GS_<NAME> is "1"):
  *   "mlp_bwd_v2"     deformation-MLP backward with alternating weight slots, elected MMA issuer, coalesced gradient flush
- *   "mlp_fwd_elect"  deformation-MLP forward with the elected MMA issuer
+ *                    (1; further bits select how d_out is prefetched and how d_features leave TMEM, deform_mlp_bwd_tc5.cu)
+ *   "mlp_fwd_elect"  deformation-MLP forward with the elected MMA issuer (1), plus deferred activation-stash stores (2)
  * Same arithmetic as the default kernels; they stay opt-in until measured on a B200.
  * set: 0 on success, non-zero for an unknown name; get: the value, or -1 for an unknown name. */
 int b200gs_set_option(const char* name, int value);

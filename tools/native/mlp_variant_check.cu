@@ -113,10 +113,14 @@ static bool run_case(long long P, int tiled, int heads, const std::vector<int>& 
     const float f0 = forward(0);
     std::vector<float> r_out[3] = {to_host(out[0], (size_t)P * 3), to_host(out[1], (size_t)P * 3), to_host(out[2], (size_t)P * 4)};
     std::vector<float> r_saved = to_host(saved, nsaved);
-    const float f1 = forward(1);
-    if (timed) printf("  forward: default %.3f ms, mlp_fwd_elect %.3f ms\n", f0, f1);
-    ok &= same_bits("pts_out", r_out[0], out[0], quiet) & same_bits("scales_out", r_out[1], out[1], quiet) & same_bits("rot_out", r_out[2], out[2], quiet);
-    ok &= same_bits("activation stash + images", r_saved, saved, quiet);
+    if (timed) printf("  forward: default %.3f ms\n", f0);
+    for (int fv = 1; fv <= 2; ++fv) {
+        const float f1 = forward(fv);
+        const bool fok = same_bits("pts_out", r_out[0], out[0], true) & same_bits("scales_out", r_out[1], out[1], true) &
+                         same_bits("rot_out", r_out[2], out[2], true) & same_bits("activation stash + images", r_saved, saved, true);
+        if (timed || !fok) printf("  forward mlp_fwd_elect = %d: %.3f ms  %s\n", fv, f1, fok ? "bit-identical to the default kernel" : "MISMATCH");
+        ok &= fok;
+    }
     r_saved.clear(); r_saved.shrink_to_fit();
     const float b0 = backward(0);
     std::vector<float> r_dfeat = to_host(dfeat, rowsP * F), r_g = to_host(gbuf, G_TOTAL);
