@@ -11,10 +11,12 @@ namespace b200gs {
 
 static thread_local char g_err[512] = "";
 
-// Opt-in kernel variants (b200gs_set_option); the environment gives the initial values so that unmodified callers can try them.
-static int env_flag(const char* name) { const char* e = getenv(name); return e && e[0] == '1'; }
-int g_opt_mlp_bwd_v2 = env_flag("B200GS_MLP_BWD_V2");
-int g_opt_mlp_fwd_elect = env_flag("B200GS_MLP_FWD_ELECT");
+// Kernel variants (b200gs_set_option): the defaults are the fastest variants that have passed tools/native/mlp_variant_check
+// on a B200 (bit-identical outputs; gradients equal up to float-atomic order); 0 selects the first-generation kernels. The
+// environment (B200GS_MLP_BWD_V2 / B200GS_MLP_FWD_ELECT = integer) overrides the initial value.
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : dflt; }
+int g_opt_mlp_bwd_v2 = env_int("B200GS_MLP_BWD_V2", 7);
+int g_opt_mlp_fwd_elect = env_int("B200GS_MLP_FWD_ELECT", 2);
 
 void set_error(const char* fmt, ...)
 {

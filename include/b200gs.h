@@ -29,12 +29,15 @@ typedef void* b200gs_stream_t; /* cudaStream_t */
 
 const char* b200gs_last_error(void);
 int b200gs_version(void);
-/* Opt-in kernel variants, process-wide, default 0 (initial value 1 if the environment variable B200GS_<NAME> is "1"):
- *   "mlp_bwd_v2"     deformation-MLP backward with alternating weight slots, elected MMA issuer, coalesced gradient flush
- *                    (1; further bits select how d_out is prefetched and how d_features leave TMEM, deform_mlp_bwd_tc5.cu)
- *   "mlp_fwd_elect"  deformation-MLP forward with the elected MMA issuer (1), plus deferred activation-stash stores (2)
- * Same arithmetic as the default kernels; they stay opt-in until measured on a B200.
- * set: 0 on success, non-zero for an unknown name; get: the value, or -1 for an unknown name. */
+/* Kernel variants, process-wide. The defaults are the fastest variants that have passed tools/native/mlp_variant_check.cu on
+ * a B200 (bit-identical outputs, gradients equal up to float-atomic order); 0 selects the first-generation kernel, the
+ * environment variable B200GS_<NAME>=<integer> overrides the initial value:
+ *   "mlp_bwd_v2"     deformation-MLP backward (default 7): bit 0 = alternating weight slots + elected MMA issuer + coalesced
+ *                    gradient flush; bits 1-2 = how d_out reaches a phase (3 = prefetched into L2 one phase ahead); bit 3 =
+ *                    d_features leave TMEM in four parts (deform_mlp_bwd_tc5.cu)
+ *   "mlp_fwd_elect"  deformation-MLP forward (default 2): 1 = elected MMA issuer, 2 = plus activation-stash stores deferred
+ *                    past the next layer's MMA issue (deform_mlp_tc5.cu)
+ * Same arithmetic in every variant. set: 0 on success, non-zero for an unknown name; get: the value, or -1 for an unknown name. */
 int b200gs_set_option(const char* name, int value);
 int b200gs_get_option(const char* name);
 

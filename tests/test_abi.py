@@ -90,14 +90,16 @@ def test_call_timer_table_names_are_abi_entries():
         assert hasattr(L, name), name
 
 
-def test_kernel_variant_options_default_off_and_toggle():
-    """The opt-in kernel variants (include/b200gs.h: b200gs_set_option) are off unless asked for; unknown names are an error."""
+def test_kernel_variant_options_defaults_and_toggle():
+    """Kernel variants (include/b200gs.h: b200gs_set_option): validated defaults unless the environment overrides them;
+    unknown names are an error."""
     from b200gs import _lib
     L = _lib.lib()
-    for name in (b"mlp_bwd_v2", b"mlp_fwd_elect"):
-        env_on = os.environ.get("B200GS_" + name.decode().upper()) == "1"
-        assert L.b200gs_get_option(name) == (1 if env_on else 0)
-        assert L.b200gs_set_option(name, 1) == 0 and L.b200gs_get_option(name) == 1
-        assert L.b200gs_set_option(name, 1 if env_on else 0) == 0
+    for name, dflt in ((b"mlp_bwd_v2", 7), (b"mlp_fwd_elect", 2)):
+        env = os.environ.get("B200GS_" + name.decode().upper())
+        want = int(env) if env is not None and env[:1].isdigit() else dflt
+        assert L.b200gs_get_option(name) == want
+        assert L.b200gs_set_option(name, 0) == 0 and L.b200gs_get_option(name) == 0
+        assert L.b200gs_set_option(name, want) == 0 and L.b200gs_get_option(name) == want
     assert L.b200gs_set_option(b"no_such_option", 1) != 0 and b"unknown option" in L.b200gs_last_error()
     assert L.b200gs_get_option(b"no_such_option") == -1

@@ -1,9 +1,8 @@
-"""GPU parity of the opt-in kernel variants (not the default path): the field / whole-step parity tests re-run in a child
-process with the variants switched on (the library reads the switches once per process):
-  B200GS_MLP_BWD_V2=1      deform_mlp_bwd_tc5_kernel<true>   (alternating weight slots, elected MMA issuer, coalesced flush)
-  B200GS_MLP_FWD_ELECT=1   deform_mlp_fwd_tc5v2_kernel<64, true> (elected MMA issuer)
-They were written without GPU access at the end of round 1, so this test only runs when B200GS_TEST_EXPERIMENTAL=1 is set;
-once it has passed on a B200 the variants can become the default and this file folds into the ordinary parity tests."""
+"""GPU parity of the NON-default deformation-MLP kernel variants (include/b200gs.h: b200gs_set_option): the field / split /
+whole-step parity tests re-run in a child process with the first-generation kernels (0 / 0) and with the minimal variants
+(1 / 1) selected through the environment.  The defaults (7 / 2) are what every other GPU test runs; they were validated
+against the first-generation kernels bit for bit by tools/native/mlp_variant_check (profiles/r1l_mlp_variant_check_b200.txt).
+Three extra pytest sessions take a few minutes, so this only runs when B200GS_TEST_EXPERIMENTAL=1 is set."""
 import os
 import subprocess
 import sys
@@ -12,8 +11,9 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-VARIANTS = {"mlp_bwd_v2": {"B200GS_MLP_BWD_V2": "1"}, "mlp_fwd_elect": {"B200GS_MLP_FWD_ELECT": "1"},
-            "both": {"B200GS_MLP_BWD_V2": "1", "B200GS_MLP_FWD_ELECT": "1"}}
+VARIANTS = {"first_generation": {"B200GS_MLP_BWD_V2": "0", "B200GS_MLP_FWD_ELECT": "0"},
+            "minimal": {"B200GS_MLP_BWD_V2": "1", "B200GS_MLP_FWD_ELECT": "1"},
+            "split_dfeature_store": {"B200GS_MLP_BWD_V2": "15", "B200GS_MLP_FWD_ELECT": "2"}}
 
 
 @pytest.mark.skipif(os.environ.get("B200GS_TEST_EXPERIMENTAL") != "1", reason="opt-in: set B200GS_TEST_EXPERIMENTAL=1")

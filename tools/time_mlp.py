@@ -1,8 +1,9 @@
 """Deformation-MLP kernels alone (C3 point count): device time per launch of b200gs_deform_mlp_forward / _backward through the
 C ABI, CUDA events on the launching stream, L2 flushed by the working set itself (1.4 / 1.6 GB per launch).  Run it once per
-variant, the library reads the switches at first use:
-    python tools/time_mlp.py
-    B200GS_MLP_BWD_V2=1 B200GS_MLP_FWD_ELECT=1 python tools/time_mlp.py"""
+variant (include/b200gs.h: b200gs_set_option; the environment gives the initial values):
+    python tools/time_mlp.py                                                  # defaults
+    B200GS_MLP_BWD_V2=0 B200GS_MLP_FWD_ELECT=0 python tools/time_mlp.py       # first-generation kernels
+(tools/native/mlp_variant_check does the same without Python and also compares the variants' results.)"""
 import os
 import sys
 
