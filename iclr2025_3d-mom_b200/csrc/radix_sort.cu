@@ -48,15 +48,16 @@ __global__ void __launch_bounds__(256) rs_scan_hist(u32* __restrict__ g_hist)
     h[threadIdx.x] = block_exclusive_scan_256(v, s_warp);
 }
 
-template <bool HAS_VALS>
+template <bool HAS_VALS, int IPT>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_onesweep_pass(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in,
                  u32* __restrict__ keys_out, u32* __restrict__ vals_out, u32 n, int shift, u32 mask,
                  const u32* __restrict__ g_base, u32* lookback, u32* ticket)
 {
     __shared__ u32 s_warp_hist[RS_WARPS][RS_RADIX];
-    __shared__ u32 s_keys[RS_TILE];
-    __shared__ u32 s_vals[HAS_VALS ? RS_TILE : 1];
+    constexpr int TILE = RS_THREADS * IPT;
+    __shared__ u32 s_keys[TILE];
+    __shared__ u32 s_vals[HAS_VALS ? TILE : 1];
     __shared__ u32 s_digit_off[RS_RADIX];
     __shared__ u32 s_scan[8];
     __shared__ u32 s_tile;
@@ -67,20 +68,20 @@ rs_onesweep_pass(const u32* __restrict__ keys_in, const u32* __restrict__ vals_i
     for (int w = 0; w < RS_WARPS; ++w) s_warp_hist[w][tid] = 0;
     __syncthreads();
     const u32 tile = s_tile;
-    const u32 base = tile * RS_TILE;
-    const u32 wbase = base + warp * (32 * RS_IPT);
+    const u32 base = tile * TILE;
+    const u32 wbase = base + warp * (32 * IPT);
 
-    u32 key[RS_IPT];
-    unsigned short rank[RS_IPT];
+    u32 key[IPT];
+    unsigned short rank[IPT];
 #pragma unroll
-    for (int i = 0; i < RS_IPT; ++i) {
+    for (int i = 0; i < IPT; ++i) {
         u32 idx = wbase + i * 32 + lane;
         key[i] = idx < n ? __ldg(keys_in + idx) : 0xFFFFFFFFu;
     }
     // Stable in-warp ranking: items are visited in index order (i-major, then lane).
     const u32 lt = lanemask_lt();
 #pragma unroll
-    for (int i = 0; i < RS_IPT; ++i) {
+    for (int i = 0; i < IPT; ++i) {
         u32 d = (key[i] >> shift) & mask;
         u32 peers = __match_any_sync(0xffffffffu, d);
         u32 before = s_warp_hist[warp][d];
@@ -121,7 +122,7 @@ rs_onesweep_pass(const u32* __restrict__ keys_in, const u32* __restrict__ vals_i
     __syncthreads();
 
 #pragma unroll
-    for (int i = 0; i < RS_IPT; ++i) {
+    for (int i = 0; i < IPT; ++i) {
         u32 d = (key[i] >> shift) & mask;
         u32 pos = s_warp_hist[warp][d] + rank[i];
         s_keys[pos] = key[i];
@@ -131,7 +132,7 @@ rs_onesweep_pass(const u32* __restrict__ keys_in, const u32* __restrict__ vals_i
         }
     }
     __syncthreads();
-    const u32 valid = min((u32)RS_TILE, n - base);
+    const u32 valid = min((u32)TILE, n - base);
     for (u32 j = tid; j < valid; j += RS_THREADS) {
         u32 k = s_keys[j];
         u32 out = s_digit_off[(k >> shift) & mask] + j;
@@ -154,7 +155,10 @@ int radix_sort_pairs(u32* keys_a, u32* vals_a, u32* keys_b, u32* vals_b, size_t 
     u32* g_hist = (u32*)temp;
     u32* tickets = g_hist + (size_t)plan.passes * RS_RADIX;
     u32* lookback = tickets + 256;
-    cudaMemsetAsync(temp, 0, plan.temp_bytes, stream);
+    const bool small = g_opt_sort_small_tiles != 0 && n <= RS_SMALL_MAX_N;
+    const size_t tiles = small ? (n + RS_TILE_SMALL - 1) / RS_TILE_SMALL : plan.tiles;
+    // clear what this call uses: digit bases, tickets, look-back state of `tiles` tiles per pass
+    cudaMemsetAsync(temp, 0, ((size_t)plan.passes * RS_RADIX + 256 + (size_t)plan.passes * tiles * RS_RADIX) * sizeof(u32), stream);
 
     DigitSpec spec;
     for (int p = 0; p < RS_MAX_PASSES; ++p) {
@@ -170,12 +174,18 @@ int radix_sort_pairs(u32* keys_a, u32* vals_a, u32* keys_b, u32* vals_b, size_t 
 
     u32 *kin = keys_a, *kout = keys_b, *vin = vals_a, *vout = vals_b;
     for (int p = 0; p < plan.passes; ++p) {
-        u32* lb = lookback + (size_t)p * plan.tiles * RS_RADIX;
-        if (vals_a)
-            rs_onesweep_pass<true><<<(unsigned)plan.tiles, RS_THREADS, 0, stream>>>(
+        u32* lb = lookback + (size_t)p * tiles * RS_RADIX;
+        if (vals_a && small)
+            rs_onesweep_pass<true, RS_IPT_SMALL><<<(unsigned)tiles, RS_THREADS, 0, stream>>>(
                 kin, vin, kout, vout, (u32)n, spec.shift[p], spec.mask[p], g_hist + p * RS_RADIX, lb, tickets + p);
+        else if (vals_a)
+            rs_onesweep_pass<true, RS_IPT><<<(unsigned)tiles, RS_THREADS, 0, stream>>>(
+                kin, vin, kout, vout, (u32)n, spec.shift[p], spec.mask[p], g_hist + p * RS_RADIX, lb, tickets + p);
+        else if (small)
+            rs_onesweep_pass<false, RS_IPT_SMALL><<<(unsigned)tiles, RS_THREADS, 0, stream>>>(
+                kin, nullptr, kout, nullptr, (u32)n, spec.shift[p], spec.mask[p], g_hist + p * RS_RADIX, lb, tickets + p);
         else
-            rs_onesweep_pass<false><<<(unsigned)plan.tiles, RS_THREADS, 0, stream>>>(
+            rs_onesweep_pass<false, RS_IPT><<<(unsigned)tiles, RS_THREADS, 0, stream>>>(
                 kin, nullptr, kout, nullptr, (u32)n, spec.shift[p], spec.mask[p], g_hist + p * RS_RADIX, lb, tickets + p);
         u32* t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;

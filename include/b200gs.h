@@ -37,6 +37,8 @@ int b200gs_version(void);
  *                    d_features leave TMEM in four parts (deform_mlp_bwd_tc5.cu)
  *   "mlp_fwd_elect"  deformation-MLP forward (default 2): 1 = elected MMA issuer, 2 = plus activation-stash stores deferred
  *                    past the next layer's MMA issue (deform_mlp_tc5.cu)
+ *   "sort_small_tiles" radix sort (default 0, not yet measured): 2048-key tiles instead of 4096 for inputs up to 4M keys
+ *                    (the depth sort of ~1M Gaussians is bound by the serial work per tile); the result is identical
  * Same arithmetic in every variant. set: 0 on success, non-zero for an unknown name; get: the value, or -1 for an unknown name. */
 int b200gs_set_option(const char* name, int value);
 int b200gs_get_option(const char* name);
