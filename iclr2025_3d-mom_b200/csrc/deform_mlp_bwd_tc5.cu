@@ -43,6 +43,7 @@ struct BwdArgs {
     const float* feat; const float* saved;
     const float* d_pts; const float* d_scales; const float* d_rot;
     float* d_feat;
+    u32 dy_sbo;                 // SINGLE_DY: byte stride between 8-point groups of the K-major view of the dY image
 };
 
 __device__ __forceinline__ float4 tf32x4(float4 v)
@@ -75,11 +76,14 @@ __device__ __forceinline__ float4 lds128(u32 addr)
 //     128-bit RED per 4 elements (8x fewer atomics than one scalar atomic per hi / lo element, whole lines per warp).
 // VER: 0 = default; otherwise bit 0 = V2, bits 1-2 = how the upstream gradients d_out reach a phase (0: loaded at its start,
 // 1: loaded into registers one phase ahead, 2 / 3: prefetched into L1 / L2 one phase ahead), bit 3 = the previous tile's
-// d_feature rows leave TMEM in four 8-column parts, one per MMA drain, instead of one 32 KB burst at the tile boundary.
+// d_feature rows leave TMEM in four 8-column parts, one per MMA drain, instead of one 32 KB burst at the tile boundary;
+// bit 4 (EXPERIMENTAL, unvalidated: see tools/probe/umma_probe2.cu) = the dX chain reads its A operand dY from the MN-major
+// SWIZZLE_128B_BASE32B image of the weight-gradient MMAs, re-described as a K-major operand (rows = points, 128-byte rows of 32
+// out-features, 8-row group stride BwdArgs::dy_sbo), so dY is stored to shared memory twice (hi, lo) instead of four times.
 template <int VER>
 __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_constant__ BwdArgs a)
 {
-    constexpr bool V2 = (VER & 1) != 0, DIN_AHEAD = ((VER >> 1) & 3) == 1, DIN_PREFETCH = ((VER >> 1) & 3) >= 2, SPLIT_FE = ((VER >> 3) & 1) != 0;
+    constexpr bool V2 = (VER & 1) != 0, DIN_AHEAD = ((VER >> 1) & 3) == 1, DIN_PREFETCH = ((VER >> 1) & 3) >= 2, SPLIT_FE = ((VER >> 3) & 1) != 0, SINGLE_DY = ((VER >> 4) & 1) != 0;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* W2B = reinterpret_cast<float*>(smem_raw);                 // current head: hi [16 k-chunks][64 n][4] | lo  (32 KB)
     float* W1B = W2B + 2 * MW * MW;                                  // hi | lo                                      (32 KB)
@@ -143,12 +147,15 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
         if (warp == 0) {
             if (elect_one()) {
                 tc_fence_after();
-                const u64 dB = smem_desc(sW, MW * 16, 128), dA = smem_desc(sDYK, KCH, 128);
+                const u64 dB = smem_desc(sW, MW * 16, 128);
+                const u64 dA = SINGLE_DY ? (smem_desc(sDYM, 16384, a.dy_sbo) | DESC_SW128_32B) : smem_desc(sDYK, KCH, 128);
                 const u64 dM = smem_desc(sDYM, 16384, 512) | DESC_SW128_32B, dX = smem_desc(sXH, 16384, 512) | DESC_SW128_32B;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {          // K = 64 out features, 8 per instruction; lo*hi + hi*lo + hi*hi
                     const u64 bh = dB + (u64)((j * 2 * (MW * 16)) >> 4), bl = bh + (u64)((MW * MW * 4) >> 4);
-                    const u64 ah = dA + (u64)((j * 2 * KCH) >> 4), al = ah + (u64)(KPLANE >> 4);
+                    // SINGLE_DY: 8 out-features = one 32-byte step inside the 128-byte row, 32 out-features per 16 KB half; lo plane +32 KB
+                    const u64 ah = dA + (SINGLE_DY ? (u64)(((j >> 2) * 16384 + (j & 3) * 32) >> 4) : (u64)((j * 2 * KCH) >> 4));
+                    const u64 al = ah + (u64)((SINGLE_DY ? 32768u : KPLANE) >> 4);
                     mma_ss(tbase + d_col, al, bh, id_kk, (d_accumulate || j > 0) ? 1u : 0u);
                     mma_ss(tbase + d_col, ah, bl, id_kk, 1u);
                     mma_ss(tbase + d_col, ah, bh, id_kk, 1u);
@@ -335,8 +342,10 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
                 const u32 pp = (u32)(p0 + 4 * i);
                 float4 hi, lo;
                 split4(dz[i], hi, lo);
-                sts128(sDYK + k_off + pp * 16u, hi);
-                sts128(sDYK + KPLANE + k_off + pp * 16u, lo);
+                if constexpr (!SINGLE_DY) {
+                    sts128(sDYK + k_off + pp * 16u, hi);
+                    sts128(sDYK + KPLANE + k_off + pp * 16u, lo);
+                }
                 sts128(sDYM + mn_off + pp * 128u, hi);
                 sts128(sDYM + 32768u + mn_off + pp * 128u, lo);
             }
@@ -409,8 +418,10 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
             }
             float4 hi, lo;
             split4(x, hi, lo);
-            sts128(sDYK + k_off + pp * 16u, hi);
-            sts128(sDYK + KPLANE + k_off + pp * 16u, lo);
+            if constexpr (!SINGLE_DY) {
+                sts128(sDYK + k_off + pp * 16u, hi);
+                sts128(sDYK + KPLANE + k_off + pp * 16u, lo);
+            }
             sts128(sDYM + mn_off + pp * 128u, hi);
             sts128(sDYM + 32768u + mn_off + pp * 128u, lo);
             sts128(sXH + mn_off + pp * 128u, tf32x4(frow[i]));
@@ -531,7 +542,7 @@ int deform_mlp_backward_tc5(const b200gs_mlp_weights* w, const b200gs_mlp_grads*
 {
     tc5::BwdArgs a;
     a.w = *w; a.gw = *gw; a.P = P; a.feat = feat; a.saved = saved; a.d_pts = d_pts; a.d_scales = d_scales; a.d_rot = d_rot;
-    a.d_feat = d_feat;
+    a.d_feat = d_feat; a.dy_sbo = 1024u;
     const long long nblocks = (P + tc5::ROWS - 1) / tc5::ROWS;
     const int grid = (int)(nblocks < NUM_SMS ? nblocks : NUM_SMS);
     const size_t smem = tc5::bwd_smem();
@@ -548,6 +559,7 @@ int deform_mlp_backward_tc5(const b200gs_mlp_weights* w, const b200gs_mlp_grads*
             case 9: kern = tc5::deform_mlp_bwd_tc5_kernel<9>; break;
             case 13: kern = tc5::deform_mlp_bwd_tc5_kernel<13>; break;
             case 15: kern = tc5::deform_mlp_bwd_tc5_kernel<15>; break;
+            case 23: case 55: kern = tc5::deform_mlp_bwd_tc5_kernel<23>; a.dy_sbo = g_opt_mlp_bwd_v2 == 55 ? 512u : 1024u; break;   // EXPERIMENTAL
             default: break;
         }
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
