@@ -499,6 +499,86 @@ hexplane_time_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const _
     }
 }
 
+// Opt-in variant ("hexplane_time_bwd" = 1 / 2, unmeasured): same arithmetic per element as the kernel above, but the level
+// count is a compile-time 2, so both levels' d_feature / factor / d_factor rows of a point group are requested before the
+// first one is used (the kernel above waits for one level's rows, works, then requests the next: two exposed memory
+// latencies per iteration -- 66 % of its stall samples are the first use of a load).  MINB = resident CTAs per SM the
+// register budget is set for (3: 85 registers, 2: 128 registers and a third fewer warps).
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
+hexplane_time_bwd2_kernel(const __grid_constant__ b200gs_hexplane_desc d, const __grid_constant__ TimeRowSetup ts, long long P,
+                          const float* __restrict__ pts, const unsigned int* __restrict__ order, float t,
+                          const float* __restrict__ factor, float* __restrict__ dfactor, const float* __restrict__ dfeat,
+                          float* __restrict__ dpts, float* __restrict__ time_rows, int replicas, int tiled)
+{
+    constexpr int L = 2, F = L * HP_C;
+    extern __shared__ float R[];
+    float* rows = time_rows + (size_t)(blockIdx.x % replicas) * ts.total;
+    time_rows_prepare(d, t, R, ts);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, slot = lane >> 3, cg = lane & 7;
+    const AabbNorm an = aabb_norm(d.aabb);
+    const long long ppi = (long long)(blockDim.x >> 5) * 4;
+    const long long chunk = ((P + gridDim.x - 1) / gridDim.x + ppi - 1) / ppi * ppi;
+    const long long begin = (long long)blockIdx.x * chunk, end = begin + chunk < P ? begin + chunk : P;
+    for (long long base = begin + (long long)(threadIdx.x >> 5) * 4; base < end; base += ppi) {
+        const long long i = base + slot;
+        const bool valid = i < end;
+        const size_t g = valid ? (order ? (size_t)__ldg(order + i) : (size_t)i) : 0;
+        float4 gout[L], fac[L], old[L];
+        if (valid) {
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                gout[l] = __ldg(reinterpret_cast<const float4*>(dfeat + (tiled ? tc5::stash_off((long long)g, l * HP_C + cg * 4) : g * F + l * HP_C + cg * 4)));
+                fac[l] = factor ? __ldg(reinterpret_cast<const float4*>(factor + g * F + l * HP_C + cg * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                old[l] = dfactor ? *reinterpret_cast<const float4*>(dfactor + g * F + l * HP_C + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        float c[4], scale[3];
+        normalized_coords(pts, nullptr, t, an, g, c, scale);
+        float gc[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                RowSample r[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) r[a] = row_sample(R + ts.off[l][a], c[a], d.res[l][a], cg);
+                const float4 go = mul4(gout[l], fac[l]);
+                if (dfactor) {                       // d S += d feature * T
+                    const float4 T = mul4(mul4(r[0].v, r[1].v), r[2].v);
+                    *reinterpret_cast<float4*>(dfactor + g * F + l * HP_C + cg * 4) =
+                        make_float4(old[l].x + gout[l].x * T.x, old[l].y + gout[l].y * T.y, old[l].z + gout[l].z * T.z, old[l].w + gout[l].w * T.w);
+                }
+                if (go.x != 0.f || go.y != 0.f || go.z != 0.f || go.w != 0.f) {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const float4 oth = mul4(r[(a + 1) % 3].v, r[(a + 2) % 3].v);
+                        const float4 gv = mul4(go, oth);
+                        float* g0 = rows + ts.off[l][a] + r[a].x0 * HP_C + cg * 4;
+                        red_add_v4(g0, gv.x * r[a].wx1, gv.y * r[a].wx1, gv.z * r[a].wx1, gv.w * r[a].wx1);
+                        if (r[a].x1 != r[a].x0) {
+                            float* g1 = rows + ts.off[l][a] + r[a].x1 * HP_C + cg * 4;
+                            red_add_v4(g1, gv.x * r[a].wx0, gv.y * r[a].wx0, gv.z * r[a].wx0, gv.w * r[a].wx0);
+                        }
+                        gc[a] += r[a].mult * (gv.x * r[a].dv.x + gv.y * r[a].dv.y + gv.z * r[a].dv.z + gv.w * r[a].dv.w);
+                    }
+                }
+            }
+        }
+        if (dpts != nullptr) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float s = gc[a];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                gc[a] = s * scale[a];
+            }
+            if (valid && cg < 3) dpts[3 * g + cg] = cg == 0 ? gc[0] : (cg == 1 ? gc[1] : gc[2]);
+        }
+    }
+}
+
 bool time_rows_setup(const b200gs_hexplane_desc& d, TimeRowSetup& ts)
 {
     int o = 0;
@@ -769,6 +849,13 @@ int b200gs_hexplane_time_backward(const b200gs_hexplane_desc* desc, long long P,
     long long blocks = (P + 31) / 32;
     const long long cap = (long long)NUM_SMS * (per * 3 <= 220 * 1024 ? 3 : (per * 2 <= 220 * 1024 ? 2 : 1));
     if (blocks > cap) blocks = cap;
+    if (g_opt_hexplane_time_bwd != 0 && desc->levels == 2) {            // opt-in variant, see hexplane_time_bwd2_kernel
+        auto kern = g_opt_hexplane_time_bwd == 2 ? hexplane_time_bwd2_kernel<2> : hexplane_time_bwd2_kernel<3>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per);
+        if (g_opt_hexplane_time_bwd == 2 && blocks > (long long)NUM_SMS * 2) blocks = (long long)NUM_SMS * 2;
+        kern<<<(unsigned)blocks, 256, per, (cudaStream_t)stream>>>(*desc, ts, P, pts, order, time_scalar, factor, d_factor_accum,
+                                                                 d_features, d_pts, rows, replicas, d_features_tiled);
+    } else
     hexplane_time_bwd_kernel<<<(unsigned)blocks, 256, per, (cudaStream_t)stream>>>(*desc, ts, P, pts, order, time_scalar, factor, d_factor_accum,
                                                                                    d_features, d_pts, rows, replicas, d_features_tiled);
     hexplane_time_rows_flush_kernel<<<(unsigned)((ts.total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*desc, time_scalar, rows, replicas);
