@@ -99,7 +99,8 @@ NCU_TRAFFIC = {"hexplane_bwd_kernel": 348.4e6, "deform_mlp_bwd_tc5_kernel": 1561
                "hexplane_time_fwd_kernel": 485.5e6, "hexplane_time_bwd_kernel": 1037.8e6}
 ROOFLINE_NOTES = {
     "deform_mlp_bwd_tc5_kernel": "HBM is the binding roofline (1.58 KB/point: 1 KB activation stash + features + d_features; the tensor pipe is 15 % "
-                                 "busy), but the kernel is SIMT-issue / latency bound today: 8 warps per SM walk five barrier-separated phases per tile",
+                                 "busy), but the kernel is SIMT / shared-memory-port bound today: per phase the gradient math runs at 0.4 IPC per scheduler (two warps each) "
+                                 "and 164 KB of operand stores go through the 128 B/clk shared-memory port (DESIGN.md section 7); traffic = ncu dram bytes of the first-generation kernel",
     "deform_mlp_fwd_tc5v2_kernel": "HBM is the binding roofline (1.37 KB/point, 1 KB of it the activation stash); tensor pipe 26 % busy",
     "hexplane_bwd_kernel": "average over the step's V time-plane passes and its one spatial pass; algorithmic HBM bytes only (xyz, order, "
                            "d_feature, shared spatial product in; d_xyz, its gradient accumulator, plane gradients out); the 3 KB/point/pass of "
@@ -605,6 +606,11 @@ def _main():
         res["roofline"] = {"kernel": "torch foreach Adam", "bound": "hbm", "achieved": adam_gbs, "peak": hbm, "unit": "GB/s",
                            "frac": (adam_gbs / hbm) if adam_gbs else None, "traffic": None, "peak_source": peak_src,
                            "algorithmic_bytes_per_launch": adam_bytes, "ms_per_launch": adam_t, "params": n_params}
+    if impl == "b200":
+        # which kernel generations ran (include/b200gs.h: b200gs_set_option; environment B200GS_* overrides)
+        from b200gs import _lib as _l
+        res["config"]["kernel_options"] = {n: int(_l.lib().b200gs_get_option(n.encode()))
+                                           for n in ("mlp_fwd_elect", "mlp_bwd_v2", "sort_small_tiles", "hexplane_time_bwd")}
     if render is not None:
         res["render"] = render
         res["config"]["render"] = (f"video rendering, {args.render_frames} frames per GPU of an orbit with advancing time, frames sharded "
