@@ -608,9 +608,12 @@ def _main():
                            "algorithmic_bytes_per_launch": adam_bytes, "ms_per_launch": adam_t, "params": n_params}
     if impl == "b200":
         # which kernel generations ran (include/b200gs.h: b200gs_set_option; environment B200GS_* overrides)
-        from b200gs import _lib as _l
-        res["config"]["kernel_options"] = {n: int(_l.lib().b200gs_get_option(n.encode()))
-                                           for n in ("mlp_fwd_elect", "mlp_bwd_v2", "sort_small_tiles", "hexplane_time_bwd")}
+        try:
+            from b200gs import _lib as _l
+            res["config"]["kernel_options"] = {n: int(_l.lib().b200gs_get_option(n.encode()))
+                                               for n in ("mlp_fwd_elect", "mlp_bwd_v2", "sort_small_tiles", "hexplane_time_bwd")}
+        except Exception as ex:              # informational only
+            res["config"]["kernel_options"] = f"unavailable: {ex}"
     if render is not None:
         res["render"] = render
         res["config"]["render"] = (f"video rendering, {args.render_frames} frames per GPU of an orbit with advancing time, frames sharded "
