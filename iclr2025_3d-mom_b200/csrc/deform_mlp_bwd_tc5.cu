@@ -80,9 +80,14 @@ __device__ __forceinline__ float4 lds128(u32 addr)
 // bit 4 (EXPERIMENTAL, unvalidated: see tools/probe/umma_probe2.cu) = the dX chain reads its A operand dY from the MN-major
 // SWIZZLE_128B_BASE32B image of the weight-gradient MMAs, re-described as a K-major operand (rows = points, 128-byte rows of 32
 // out-features, 8-row group stride BwdArgs::dy_sbo), so dY is stored to shared memory twice (hi, lo) instead of four times.
-template <int VER>
+// ABL (timing experiments only, WRONG RESULTS, option "mlp_bwd_ablate"): what the kernel costs without one of its parts --
+// 1: d_out read from constants instead of global memory, 2: no operand stores to shared memory, 4: no MMAs (and no waits for
+// them), 8: no gradient math (dz / dW3 / bias sums), 16: no d_feature stores, 32: stash / feature rows from constants.
+template <int VER, int ABL = 0>
 __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_constant__ BwdArgs a)
 {
+    constexpr bool A_NODIN = (ABL & 1) != 0, A_NOSTS = (ABL & 2) != 0, A_NOMMA = (ABL & 4) != 0, A_NOMATH = (ABL & 8) != 0,
+                   A_NODFEAT = (ABL & 16) != 0, A_NOLOAD = (ABL & 32) != 0;
     constexpr bool V2 = (VER & 1) != 0, DIN_AHEAD = ((VER >> 1) & 3) == 1, DIN_PREFETCH = ((VER >> 1) & 3) >= 2, SPLIT_FE = ((VER >> 3) & 1) != 0, SINGLE_DY = ((VER >> 4) & 1) != 0;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* W2B = reinterpret_cast<float*>(smem_raw);                 // current head: hi [16 k-chunks][64 n][4] | lo  (32 KB)
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
     // tcgen05.commit needs (it tracks the MMAs of the executing thread).  Descriptor start addresses are 14-bit fields of
     // (address >> 4) and shared memory ends below 256 KB, so adding (offset >> 4) to a hoisted base cannot carry out.
     auto issue_group = [&](u32 sW, u32 d_col, bool d_accumulate, u32 w_col) {
-        if (warp == 0) {
+        if (!A_NOMMA && warp == 0) {
             if (elect_one()) {
                 tc_fence_after();
                 const u64 dB = smem_desc(sW, MW * 16, 128);
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
                     u32 v[8];
                     tmem_ld8(lane_addr + C_FE + 32 * cT + 8 * fe_part, v);
                     tmem_wait_ld();
-                    if (prev_row < a.P) {
+                    if (!A_NODFEAT && prev_row < a.P) {
 #pragma unroll
                         for (int j = 0; j < 2; ++j)
                             *reinterpret_cast<float4*>(a.d_feat + (a.w.feat_tiled ? stash_off(prev_row, 32 * cT) + 16 * (2 * fe_part + j)
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
                 u32 v[32];
                 tmem_ld32(lane_addr + C_FE + 32 * cT, v);
                 tmem_wait_ld();
-                if (prev_row < a.P) {
+                if (!A_NODFEAT && prev_row < a.P) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<float4*>(a.d_feat + (a.w.feat_tiled ? stash_off(prev_row, 32 * cT) + 16 * j : (size_t)prev_row * MW + 32 * cT + 4 * j)) =
@@ -234,14 +239,16 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
         const size_t step = a.w.feat_tiled ? 256 : 4 * MW;                       // rows r0 + 4 i
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            x[i] = r0 + 4 * i < a.P ? __ldg(reinterpret_cast<const float4*>(base + step * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[i] = A_NOLOAD ? make_float4(0.5f, 0.25f, 0.f, 1.f) :
+                   r0 + 4 * i < a.P ? __ldg(reinterpret_cast<const float4*>(base + step * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     auto load_stash = [&](float4* x, int plane, long long r0) {                  // tiled stash plane, see stash_off
         // r0 = tile * 128 + 32 pg + sub: the 8 rows r0 + 4 i are the same slot of 8 consecutive 4-point groups
         const float* src = a.saved + (size_t)plane * stash_plane_floats(a.P) + stash_off(r0, col0);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            x[i] = r0 + 4 * i < a.P ? __ldg(reinterpret_cast<const float4*>(src + 256 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[i] = A_NOLOAD ? make_float4(0.5f, 0.25f, 0.f, 1.f) :
+                   r0 + 4 * i < a.P ? __ldg(reinterpret_cast<const float4*>(src + 256 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     auto load_phase_rows = [&](int ph, float4* x, long long r0) {
         if (ph >= 3) load_rows(x, a.feat, r0); else load_stash(x, 1 + ph, r0);
@@ -254,7 +261,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
         for (int i = 0; i < 8; ++i) {
             const long long r = r0 + 4 * i;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) d[i][k] = (r < a.P && dsrc && k < kd) ? __ldg(dsrc + (size_t)r * kd + k) : 0.f;
+            for (int k = 0; k < 4; ++k) d[i][k] = A_NODIN ? 0.25f * (float)(k + 1) : (r < a.P && dsrc && k < kd) ? __ldg(dsrc + (size_t)r * kd + k) : 0.f;
         }
     };
 
@@ -307,6 +314,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
                 const float zz[4] = {xin[i].x, xin[i].y, xin[i].z, xin[i].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
+                    if constexpr (A_NOMATH) { dz[i][e] = zz[e] + din[i][e]; continue; }
                     const float wk[4] = {e == 0 ? w3[0].x : e == 1 ? w3[0].y : e == 2 ? w3[0].z : w3[0].w,
                                          e == 0 ? w3[1].x : e == 1 ? w3[1].y : e == 2 ? w3[1].z : w3[1].w,
                                          e == 0 ? w3[2].x : e == 1 ? w3[2].y : e == 2 ? w3[2].z : w3[2].w,
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
                     for (int k = 0; k < 4; ++k)
                         if (k < kd) gW3[h][k][e] = fmaf(din[i][k], zz[e], gW3[h][k][e]);
                 }
-                if (q == 0 && c == 0) {
+                if (!A_NOMATH && q == 0 && c == 0) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) gB3[h][k] += din[i][k];
                 }
@@ -334,7 +342,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
             else copy_image_pair((ngroup & 1u) ? W2B : W1B, next_phase(h));   // the NEXT group's image -> the slot the drained group used
             if (!h_staged) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) sts128(sXH + mn_off + (u32)(p0 + 4 * i) * 128u, tf32x4(hrow[i]));
+                for (int i = 0; i < 8; ++i) if (!A_NOSTS || i == 0) sts128(sXH + mn_off + (u32)(p0 + 4 * i) * 128u, tf32x4(hrow[i]));
                 h_staged = true;
             }
 #pragma unroll
@@ -342,6 +350,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
                 const u32 pp = (u32)(p0 + 4 * i);
                 float4 hi, lo;
                 split4(dz[i], hi, lo);
+                if constexpr (A_NOSTS) { if (i > 0 || hi.x + lo.y != 12345.678f) continue; }     // keeps dz alive, stores (almost) never
                 if constexpr (!SINGLE_DY) {
                     sts128(sDYK + k_off + pp * 16u, hi);
                     sts128(sDYK + KPLANE + k_off + pp * 16u, lo);
@@ -371,7 +380,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
                            smem_desc(sXH + j * 1024, 16384, 512) | DESC_SW128_32B, id_mn, (first_tile && j == 0) ? 0u : 1u);
                 tc_commit(bar);
             }
-            pending = true;
+            pending = !A_NOMMA;
             rh_started = true;
         }
         // ---- dh = d relu(hidden) masked ; d feature = dh W1 ; dW1 += dh^T feature ----
@@ -418,6 +427,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
             }
             float4 hi, lo;
             split4(x, hi, lo);
+            if constexpr (A_NOSTS) { if (i > 0 || hi.x + lo.y + frow[i].x != 12345.678f) continue; }
             if constexpr (!SINGLE_DY) {
                 sts128(sDYK + k_off + pp * 16u, hi);
                 sts128(sDYK + KPLANE + k_off + pp * 16u, lo);
@@ -448,7 +458,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
                        smem_desc(sXH + j * 1024, 16384, 512) | DESC_SW128_32B, id_mn, (first_tile && j == 0) ? 0u : 1u);
             tc_commit(bar);
         }
-        pending = true;
+        pending = !A_NOMMA;
         prev_row = blk * ROWS + pT;
         first_tile = false;
     }
@@ -550,6 +560,22 @@ int deform_mlp_backward_tc5(const b200gs_mlp_weights* w, const b200gs_mlp_grads*
     // aligned W1 / W2 gradient rows for its 128-bit REDs
     bool v2 = g_opt_mlp_bwd_v2 != 0 && ((uintptr_t)gw->w1 & 15) == 0;
     for (int h = 0; h < 3; ++h) v2 = v2 && (!w->w2[h] || ((uintptr_t)gw->w2[h] & 15) == 0);
+    if (v2 && g_opt_mlp_bwd_ablate != 0) {           // timing experiments, wrong results (see the kernel's ABL comment)
+        void (*kern)(tc5::BwdArgs) = nullptr;
+        switch (g_opt_mlp_bwd_ablate) {
+            case 1: kern = tc5::deform_mlp_bwd_tc5_kernel<7, 1>; break;
+            case 2: kern = tc5::deform_mlp_bwd_tc5_kernel<7, 2>; break;
+            case 4: kern = tc5::deform_mlp_bwd_tc5_kernel<7, 4>; break;
+            case 8: kern = tc5::deform_mlp_bwd_tc5_kernel<7, 8>; break;
+            case 16: kern = tc5::deform_mlp_bwd_tc5_kernel<7, 16>; break;
+            case 32: kern = tc5::deform_mlp_bwd_tc5_kernel<7, 32>; break;
+            case 10: kern = tc5::deform_mlp_bwd_tc5_kernel<7, 10>; break;
+            default: set_error("deform_mlp_backward: mlp_bwd_ablate = %d is not built", g_opt_mlp_bwd_ablate); return -1;
+        }
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, tc5::BT, smem, stream>>>(a);
+        return check_launch("deform_mlp_backward(tcgen05 v2, ablation)");
+    }
     if (v2) {
         void (*kern)(tc5::BwdArgs) = tc5::deform_mlp_bwd_tc5_kernel<1>;
         switch (g_opt_mlp_bwd_v2) {          // see the kernel's VER comment

@@ -9,6 +9,7 @@
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/native/mlp_variant_check tools/native/mlp_variant_check.cu \
 //             -Iinclude -Liclr2025_3d-mom_b200/b200gs/lib -lb200gs -Xlinker -rpath -Xlinker '$ORIGIN/../../iclr2025_3d-mom_b200/b200gs/lib'
 // run:   tools/native/mlp_variant_check [P of the timed case] [comma-separated mlp_bwd_v2 values]     (exit code 0 = all passed)
+//        tools/native/mlp_variant_check 1000000 ablate      (times the backward kernel with one part removed at a time)
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -68,7 +69,6 @@ static b200gs_mlp_grads grads_in(float* buf)
 static bool run_case(long long P, int tiled, int heads, const std::vector<int>& bwd_variants, bool timed, cudaStream_t st)
 {
     printf("case P = %lld, features %s, heads %d%d%d%s\n", P, tiled ? "tiled" : "row-major", heads & 1, (heads >> 1) & 1, (heads >> 2) & 1, timed ? " (timed)" : "");
-    const bool quiet = !timed;
     b200gs_mlp_weights w; memset(&w, 0, sizeof(w));
     w.feat_dim = F; w.width = W; w.feat_tiled = tiled;
     w.w1 = dev_random((size_t)W * F, -0.2f, 0.2f); w.b1 = dev_random(W, -0.1f, 0.1f);
@@ -139,9 +139,53 @@ static bool run_case(long long P, int tiled, int heads, const std::vector<int>& 
     return ok;
 }
 
+// what the default backward kernel costs without one of its parts (option "mlp_bwd_ablate": wrong results, timing only)
+static void run_ablations(long long P, cudaStream_t st)
+{
+    printf("backward ablations at P = %lld, tiled features (results are wrong by construction; only the times mean something):\n", P);
+    b200gs_mlp_weights w; memset(&w, 0, sizeof(w));
+    w.feat_dim = F; w.width = W; w.feat_tiled = 1;
+    w.w1 = dev_random((size_t)W * F, -0.2f, 0.2f); w.b1 = dev_random(W, -0.1f, 0.1f);
+    for (int h = 0; h < 3; ++h) {
+        w.w2[h] = dev_random((size_t)W * W, -0.2f, 0.2f); w.b2[h] = dev_random(W, -0.1f, 0.1f);
+        w.w3[h] = dev_random((size_t)KD[h] * W, -0.2f, 0.2f); w.b3[h] = dev_random(KD[h], -0.1f, 0.1f);
+    }
+    const size_t rowsP = (size_t)((P + 127) / 128) * 128;
+    float* feat = dev_random(rowsP * F, 0.f, 1.f);
+    float* xyz = dev_random((size_t)P * 3, -1.5f, 1.5f), *scales = dev_random((size_t)P * 3, -6.f, -4.f), *rot = dev_random((size_t)P * 4, -1.f, 1.f);
+    float* flow = dev_random((size_t)P * 3, -1e-3f, 1e-3f);
+    const float* dout[3] = {dev_random((size_t)P * 3, -1.f, 1.f), dev_random((size_t)P * 3, -1.f, 1.f), dev_random((size_t)P * 4, -1.f, 1.f)};
+    float* out[3] = {dev_zero((size_t)P * 3), dev_zero((size_t)P * 3), dev_zero((size_t)P * 4)};
+    float* saved = dev_zero(b200gs_deform_mlp_saved_floats(P)), *dfeat = dev_zero(rowsP * F), *gbuf = dev_zero(G_TOTAL);
+    b200gs_mlp_grads g = grads_in(gbuf);
+    BK(b200gs_deform_mlp_forward(&w, P, feat, xyz, scales, rot, flow, 22.f, nullptr, 1.f, out[0], out[1], out[2], saved, st));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int abl[] = {0, 1, 2, 4, 8, 16, 32, 10};
+    const char* what[] = {"complete kernel", "d_out from constants (no global loads of d_out)", "no operand stores to shared memory", "no MMAs, no waits for them",
+                          "no gradient math (dz, dW3, bias sums)", "no d_feature stores", "stash / feature rows from constants (no global loads)",
+                          "neither operand stores nor gradient math"};
+    for (int k = 0; k < 8; ++k) {
+        BK(b200gs_set_option("mlp_bwd_ablate", abl[k]));
+        for (int rep = -1; rep < 5; ++rep) {
+            if (rep == 0) CK(cudaEventRecord(e0, st));
+            BK(b200gs_deform_mlp_backward(&w, &g, P, feat, saved, dout[0], dout[1], dout[2], dfeat, st));
+        }
+        CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        printf("  mlp_bwd_ablate = %2d: %.3f ms  %s\n", abl[k], ms / 5, what[k]);
+    }
+    BK(b200gs_set_option("mlp_bwd_ablate", 0));
+    free_all();
+}
+
 int main(int argc, char** argv)
 {
     const long long P = argc > 1 ? atoll(argv[1]) : 1000000;
+    if (argc > 2 && !strcmp(argv[2], "ablate")) {
+        cudaStream_t st; CK(cudaStreamCreate(&st));
+        run_ablations(P, st);
+        return 0;
+    }
     std::vector<int> variants;
     for (char* t = strtok(argc > 2 ? argv[2] : (char*)"", ","); t; t = strtok(nullptr, ",")) variants.push_back(atoi(t));
     if (variants.empty()) variants = {1, 3, 5, 7, 9, 13, 15};
