@@ -16,6 +16,7 @@ With the real reference tree on sys.path, train_4DGS.py / render_4DGS.py run unc
 b200gs.launcher instead.
 """
 import math
+import os
 import types
 
 import torch
@@ -183,7 +184,7 @@ class ViewParallelTrainer:
     stand-in to exercise the sharding / flat-arena / collective logic over gloo."""
 
     def __init__(self, model, bg_color, stage="fine", process_group=None, world_size=1, rank=0, render_fn=None,
-                 regulation=None, regulation_fn=None):
+                 regulation=None, regulation_fn=None, shared_shs=None, overlap_sh_reduce=None):
         self.model = model
         self.bg = bg_color
         self.stage = stage
@@ -194,20 +195,37 @@ class ViewParallelTrainer:
         self.world_size = world_size
         self.rank = rank
         # our own render() takes the per-step SH tensor; an injected render_fn keeps the 4-argument form
-        self.shared_shs = render_fn is None
+        self.shared_shs = (render_fn is None) if shared_shs is None else bool(shared_shs)
         self.render_fn = render_fn or (lambda cam, m, bg, st, shs=None: render(cam, m, bg, stage=st, shs=shs))
+        # Opt-in (B200GS_OVERLAP_SH_REDUCE=1, not yet measured): the SH gradient -- 192 of the 248 MB a rank contributes at 1M
+        # Gaussians -- is final as soon as the LAST view's rasterizer backward has run, so its all-reduce starts there, on NCCL's
+        # own stream, and overlaps that view's field backward and the deferred spatial pass; the rest of the arena (everything
+        # but the SH slices, which then sit at its end) is reduced after the loop as before.
+        if overlap_sh_reduce is None:
+            overlap_sh_reduce = os.environ.get("B200GS_OVERLAP_SH_REDUCE") == "1"
+        self.overlap_sh_reduce = bool(overlap_sh_reduce) and self.shared_shs and world_size > 1
+        self._sh_work = None
         P = model.get_xyz.shape[0]
         # flat gradient arena: [every parameter the loss reaches | screen-space xy per Gaussian];
         # p.grad are views into it, so autograd accumulates in place and ONE collective (fp32 sum
         # over NVLink/NVSwitch) reduces everything. Parameters outside it keep grad None and the
         # optimiser skips them, as torch does in the reference.
-        self.trainable = [p for n, p in model.named_parameters() if p.requires_grad and _receives_grad(n, stage)]
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and _receives_grad(n, stage)]
+        is_sh = lambda n: n in ("_features_dc", "_features_rest")
+        if self.overlap_sh_reduce:                     # SH slices last: [other parameters | screen-space xy | f_dc | f_rest]
+            named = [x for x in named if not is_sh(x[0])] + [x for x in named if is_sh(x[0])]
+        self.trainable = [p for _, p in named]
         # every slice starts on a 256-byte boundary: the kernels use 128-bit loads / vector reductions on them
         al = lambda x: (x + 63) // 64 * 64
         n = sum(al(p.numel()) for p in self.trainable) + al(3 * P)
         self.arena = torch.zeros(n, dtype=torch.float32, device=model.get_xyz.device)
         self.views, off = [], 0
-        for p in self.trainable:
+        self.viewspace_grad = None
+        for name, p in named:
+            if self.overlap_sh_reduce and is_sh(name) and self.viewspace_grad is None:
+                self.viewspace_grad = self.arena[off:off + 3 * P].view(P, 3)
+                off += al(3 * P)
+                self._reduce_end = off                 # the post-loop all-reduce covers arena[:_reduce_end]
             flat = self.arena[off:off + p.numel()]
             if p.dim() == 4 and p.stride(1) == 1 and not p.is_contiguous():     # channels_last plane
                 N, C, H, W = p.shape
@@ -216,7 +234,9 @@ class ViewParallelTrainer:
                 v = flat.view(p.shape)
             self.views.append(v)
             off += al(p.numel())
-        self.viewspace_grad = self.arena[off:off + 3 * P].view(P, 3)
+        if self.viewspace_grad is None:
+            self.viewspace_grad = self.arena[off:off + 3 * P].view(P, 3)
+            self._reduce_end = n
         self.max_radii = torch.zeros(P, dtype=torch.int32, device=self.arena.device)
 
     def _bind(self):
@@ -224,6 +244,11 @@ class ViewParallelTrainer:
         self.max_radii.zero_()
         for p, v in zip(self.trainable, self.views):
             p.grad = v
+
+    def _start_sh_reduce(self, shs):
+        if self._sh_work is None and shs is not None and shs.grad is not None:
+            import torch.distributed as dist
+            self._sh_work = dist.all_reduce(shs.grad, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
 
     def local_views(self, n_global):
         """Indices of the global batch this rank renders: view b goes to rank b mod world_size."""
@@ -250,13 +275,17 @@ class ViewParallelTrainer:
         share_spatial = self.shared_shs and self.stage == "fine" and len(cams) > 1 and self.model._xyz.is_cuda
         if share_spatial:
             _field.begin_shared_step(self.model._deformation, self.model._xyz)
-        for cam, gt in zip(cams, gts):
+        self._sh_work = None
+        for vi, (cam, gt) in enumerate(zip(cams, gts)):
             pkg = self.render_fn(cam, self.model, self.bg, self.stage, shs) if self.shared_shs else \
                 self.render_fn(cam, self.model, self.bg, self.stage)
             _field.ACCUMULATE_INTO_GRAD = self.shared_shs     # p.grad are arena views: let the field kernels add into them
             _rast.SH_GRAD_ACCUMULATOR = shs.grad if (shs is not None and shs.is_cuda) else None
+            if self.overlap_sh_reduce and vi == len(cams) - 1:
+                # called by the rasterizer backward right after it has queued the kernel that adds this view's SH gradient
+                _rast.AFTER_SH_ACCUMULATE = lambda: self._start_sh_reduce(shs)
             try:
-                if self.shared_shs:
+                if self.shared_shs and gt.is_cuda:
                     # fused L1 (utils/loss_utils.py:23-24) + its gradient, then backward from the image
                     if total is None:
                         total = torch.zeros(1, device=gt.device)
@@ -270,6 +299,7 @@ class ViewParallelTrainer:
             finally:
                 _field.ACCUMULATE_INTO_GRAD = False
                 _rast.SH_GRAD_ACCUMULATOR = None
+                _rast.AFTER_SH_ACCUMULATE = None
             vg = pkg["viewspace_points"].grad
             if vg is not None:
                 self.viewspace_grad += vg
@@ -278,12 +308,19 @@ class ViewParallelTrainer:
                 total = loss.detach() if total is None else total + loss.detach()
         if share_spatial:
             _field.finish_shared_step()
+        if self.overlap_sh_reduce and shs is not None:
+            if shs.grad is None:                       # a rank without views still takes part in the collective
+                shs.grad = torch.zeros_like(shs)
+            self._start_sh_reduce(shs)                 # no-op when the rasterizer backward has already started it
+            self._sh_work.wait()
+            self._sh_work = None
         if shs is not None and shs.grad is not None:
             self.model._features_dc.grad += shs.grad[:, :1]
             self.model._features_rest.grad += shs.grad[:, 1:]
         if self.world_size > 1:
             import torch.distributed as dist
-            dist.all_reduce(self.arena, op=dist.ReduceOp.SUM, group=self.pg)
+            # with the SH slices already reduced (above) only the front of the arena is left
+            dist.all_reduce(self.arena[:self._reduce_end] if self.overlap_sh_reduce else self.arena, op=dist.ReduceOp.SUM, group=self.pg)
             dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=self.pg)
         if self.regulation is not None:
             # plane-only term, identical on every rank: added once, after the reduce

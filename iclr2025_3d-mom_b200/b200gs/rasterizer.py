@@ -19,6 +19,9 @@ NUM_CHANNELS = 3
 # Set by b200gs.engine.ViewParallelTrainer for the duration of a step: a [P,M,3] buffer that the backward ADDS the SH
 # gradient into (b200gs_rast_backward_accumulate_sh); autograd then gets None for `sh`. None = ordinary behaviour.
 SH_GRAD_ACCUMULATOR = None
+# Optional callable the backward invokes right after queueing the kernel that adds into SH_GRAD_ACCUMULATOR (the trainer starts
+# the SH gradient's all-reduce there on the last view of a step); None = nothing.
+AFTER_SH_ACCUMULATE = None
 
 _pinned = {}
 
@@ -136,6 +139,8 @@ class _CModule:
                 dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(), ptr(dL_dsh) if has_sh else None,
                 dL_dscales.data_ptr(), dL_drotations.data_ptr(), current_stream()),
                 "rasterize_gaussians_backward")
+            if use_acc and AFTER_SH_ACCUMULATE is not None:
+                AFTER_SH_ACCUMULATE()
             if debug:
                 torch.cuda.synchronize(dev)
         return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, (None if use_acc else dL_dsh), dL_dscales, dL_drotations

@@ -75,3 +75,64 @@ def test_two_rank_step_equals_single_process():
             continue
         assert torch.equal(r0[k], r1[k]), f"ranks diverged on {k}"                  # replicas stay identical
         assert torch.allclose(single[k].float(), r0[k].float(), rtol=1e-5, atol=1e-7), k
+
+
+class TinyModelSH(TinyModel):
+    """+ the two SH parameters the trainer concatenates once per step when it shares the SH tensor between views."""
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(3)
+        self._features_dc = nn.Parameter(torch.randn(50, 1, 3, generator=g))
+        self._features_rest = nn.Parameter(torch.randn(50, 15, 3, generator=g) * 0.1)
+
+
+def fake_render_shs(cam, model, bg, stage, shs=None):
+    """As fake_render, with a colour term that depends on the step's shared SH tensor."""
+    pkg = fake_render(cam, model, bg, stage)
+    feats = shs if shs is not None else torch.cat((model._features_dc, model._features_rest), dim=1)
+    colour = (feats * torch.linspace(0.5, 1.5, 16)[None, :, None]).sum(1).mean(0) * cam          # [3]
+    pkg["render"] = pkg["render"] + colour[:, None, None]
+    return pkg
+
+
+def _run_sh(rank, world, port, ret, overlap):
+    sys.path.insert(0, os.path.join(ROOT, "iclr2025_3d-mom_b200"))
+    from b200gs.engine import ViewParallelTrainer
+    if world > 1:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    model = TinyModelSH()
+    model.optimizer = torch.optim.Adam([{"params": [model._xyz], "lr": 1e-2}, {"params": [model._opacity], "lr": 5e-2},
+                                        {"params": [model._features_dc], "lr": 2.5e-3}, {"params": [model._features_rest], "lr": 1.25e-4},
+                                        {"params": list(model._deformation.parameters()), "lr": 1e-3}], lr=0.0, eps=1e-15)
+    tr = ViewParallelTrainer(model, torch.tensor([0.1, 0.2, 0.3]), stage="fine", world_size=world, rank=rank,
+                             render_fn=fake_render_shs, shared_shs=True, overlap_sh_reduce=overlap)
+    assert tr.overlap_sh_reduce == (overlap and world > 1)
+    if tr.overlap_sh_reduce:      # SH slices at the end of the arena, outside the post-loop all-reduce
+        assert tr._reduce_end < tr.arena.numel() and model._features_rest in tr.trainable[-1:]
+    cams = [0.5 + 0.25 * b for b in range(4)]
+    g = torch.Generator().manual_seed(1)
+    gts = [torch.rand(3, 5, 6, generator=g) for _ in range(4)]
+    for _ in range(3):
+        mine = tr.local_views(4)
+        tr.step([cams[i] for i in mine], [gts[i] for i in mine], global_batch=4)
+    out = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    out["viewspace"] = tr.viewspace_grad.clone(); out["max_radii"] = tr.max_radii.clone()
+    ret[(rank if world > 1 else -1, overlap)] = out
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def test_overlapped_sh_reduce_equals_single_process():
+    """Opt-in path: the SH gradient reduced by its own (early, asynchronous) all-reduce and the rest of the arena by the
+    post-loop one give the same parameters as the single-process run and as the one-collective path."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    _run_sh(0, 1, 0, ret, False)
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_run_sh, args=(2, port, ret, True), nprocs=2, join=True)
+    mp.spawn(_run_sh, args=(2, port + 1, ret, False), nprocs=2, join=True)
+    single, o0, o1, p0 = ret[(-1, False)], ret[(0, True)], ret[(1, True)], ret[(0, False)]
+    for k in single:
+        assert torch.equal(o0[k], o1[k]), f"ranks diverged on {k}"
+        assert torch.allclose(single[k].float(), o0[k].float(), rtol=1e-5, atol=1e-7), k
+        assert torch.allclose(p0[k].float(), o0[k].float(), rtol=1e-6, atol=1e-8), k
