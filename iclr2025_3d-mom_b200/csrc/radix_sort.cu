@@ -48,7 +48,10 @@ __global__ void __launch_bounds__(256) rs_scan_hist(u32* __restrict__ g_hist)
     h[threadIdx.x] = block_exclusive_scan_256(v, s_warp);
 }
 
-template <bool HAS_VALS, int IPT>
+// LB_BATCH (opt-in "lookback_parallel"): the decoupled look-back of a digit walks its predecessors' states LB_BATCH at a
+// time (independent volatile loads in flight together) instead of one dependent L2 round trip per predecessor -- with a
+// few hundred tiles resident at once the serial walk is what a pass on ~1M keys spends its time in.  Same sums, same result.
+template <bool HAS_VALS, int IPT, int LB_BATCH>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_onesweep_pass(const u32* __restrict__ keys_in, const u32* __restrict__ vals_in,
                  u32* __restrict__ keys_out, u32* __restrict__ vals_out, u32 n, int shift, u32 mask,
@@ -106,12 +109,33 @@ rs_onesweep_pass(const u32* __restrict__ keys_in, const u32* __restrict__ vals_i
         st_volatile_u32(lb, count | LB_INCL);
     } else {
         st_volatile_u32(lb, count | LB_AGG);
-        for (u32 t = tile; t-- > 0;) {
-            const u32* p = lookback + (size_t)t * RS_RADIX + tid;
-            u32 v;
-            do { v = ld_volatile_u32(p); } while ((v & (LB_AGG | LB_INCL)) == 0);
-            prefix += v & LB_VALUE;
-            if (v & LB_INCL) break;
+        if constexpr (LB_BATCH <= 1) {
+            for (u32 t = tile; t-- > 0;) {
+                const u32* p = lookback + (size_t)t * RS_RADIX + tid;
+                u32 v;
+                do { v = ld_volatile_u32(p); } while ((v & (LB_AGG | LB_INCL)) == 0);
+                prefix += v & LB_VALUE;
+                if (v & LB_INCL) break;
+            }
+        } else {
+            int t = (int)tile - 1;                  // next predecessor to take
+            bool done = false;
+            while (!done) {
+                u32 v[LB_BATCH];
+#pragma unroll
+                for (int k = 0; k < LB_BATCH; ++k)  // before tile 0: an inclusive 0 (never reached: tile 0 publishes INCL)
+                    v[k] = t - k >= 0 ? ld_volatile_u32(lookback + (size_t)(t - k) * RS_RADIX + tid) : LB_INCL;
+                int consumed = 0;                   // taken strictly in order; the first unpublished state ends the batch
+#pragma unroll
+                for (int k = 0; k < LB_BATCH; ++k) {
+                    if (!done && consumed == k && (v[k] & (LB_AGG | LB_INCL)) != 0) {
+                        prefix += v[k] & LB_VALUE;
+                        done = (v[k] & LB_INCL) != 0;
+                        consumed = k + 1;
+                    }
+                }
+                t -= consumed;                      // an unpublished predecessor is simply fetched again
+            }
         }
         st_volatile_u32(lb, ((prefix + count) & LB_VALUE) | LB_INCL);
     }
@@ -175,18 +199,18 @@ int radix_sort_pairs(u32* keys_a, u32* vals_a, u32* keys_b, u32* vals_b, size_t 
     u32 *kin = keys_a, *kout = keys_b, *vin = vals_a, *vout = vals_b;
     for (int p = 0; p < plan.passes; ++p) {
         u32* lb = lookback + (size_t)p * tiles * RS_RADIX;
-        if (vals_a && small)
-            rs_onesweep_pass<true, RS_IPT_SMALL><<<(unsigned)tiles, RS_THREADS, 0, stream>>>(
-                kin, vin, kout, vout, (u32)n, spec.shift[p], spec.mask[p], g_hist + p * RS_RADIX, lb, tickets + p);
-        else if (vals_a)
-            rs_onesweep_pass<true, RS_IPT><<<(unsigned)tiles, RS_THREADS, 0, stream>>>(
-                kin, vin, kout, vout, (u32)n, spec.shift[p], spec.mask[p], g_hist + p * RS_RADIX, lb, tickets + p);
-        else if (small)
-            rs_onesweep_pass<false, RS_IPT_SMALL><<<(unsigned)tiles, RS_THREADS, 0, stream>>>(
-                kin, nullptr, kout, nullptr, (u32)n, spec.shift[p], spec.mask[p], g_hist + p * RS_RADIX, lb, tickets + p);
-        else
-            rs_onesweep_pass<false, RS_IPT><<<(unsigned)tiles, RS_THREADS, 0, stream>>>(
-                kin, nullptr, kout, nullptr, (u32)n, spec.shift[p], spec.mask[p], g_hist + p * RS_RADIX, lb, tickets + p);
+#define RS_LAUNCH(HV, IPTV, LBV) rs_onesweep_pass<HV, IPTV, LBV><<<(unsigned)tiles, RS_THREADS, 0, stream>>>( \
+            kin, HV ? vin : nullptr, kout, HV ? vout : nullptr, (u32)n, spec.shift[p], spec.mask[p], g_hist + p * RS_RADIX, lb, tickets + p)
+        const bool hv = vals_a != nullptr, par = g_opt_lookback_parallel != 0;
+        if (hv && small && par) RS_LAUNCH(true, RS_IPT_SMALL, 8);
+        else if (hv && small) RS_LAUNCH(true, RS_IPT_SMALL, 1);
+        else if (hv && par) RS_LAUNCH(true, RS_IPT, 8);
+        else if (hv) RS_LAUNCH(true, RS_IPT, 1);
+        else if (small && par) RS_LAUNCH(false, RS_IPT_SMALL, 8);
+        else if (small) RS_LAUNCH(false, RS_IPT_SMALL, 1);
+        else if (par) RS_LAUNCH(false, RS_IPT, 8);
+        else RS_LAUNCH(false, RS_IPT, 1);
+#undef RS_LAUNCH
         u32* t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }

@@ -330,6 +330,9 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
 // offsets), so large splats do not serialise a thread as in rasterizer_impl.cu:70-111.
 constexpr u64 EM_AGG = 1ull << 62, EM_INCL = 1ull << 63, EM_VALUE = (1ull << 62) - 1;
 
+// WARP_LB (opt-in "lookback_parallel"): warp 0 looks back over 32 predecessors per step (ballots over their states, one
+// shuffle reduction) instead of thread 0 walking them one dependent L2 round trip at a time.  Same prefix, same output.
+template <bool WARP_LB>
 __global__ void __launch_bounds__(256)
 emit_instances_kernel(const u32* __restrict__ sorted_idx, u32 n_vis, const u32* __restrict__ tiles_touched,
                       const uint2* __restrict__ rect, int grid_x, u32* __restrict__ out_tile,
@@ -356,7 +359,35 @@ emit_instances_kernel(const u32* __restrict__ sorted_idx, u32 n_vis, const u32* 
     u32 total;
     const u32 off = block_exclusive_scan_256(cnt, s_scan, &total);
     s_off[tid] = off; s_rect[tid] = rc; s_gid[tid] = gid;
-    if (tid == 0) {
+    if (WARP_LB && tid < 32) {
+        const u32 lane = tid;
+        u64 prefix = 0;
+        if (lane == 0) {
+            s_off[256] = total;
+            st_volatile_u64(status + tile, (u64)total | (tile == 0 ? EM_INCL : EM_AGG));
+        }
+        long long t = (long long)tile - 1;          // nearest predecessor not yet taken
+        bool done = tile == 0;
+        while (!done) {
+            const long long idx = t - (long long)lane;
+            const u64 v = idx >= 0 ? ld_volatile_u64(status + idx) : EM_INCL;       // before tile 0: an inclusive 0
+            const u32 m_ready = __ballot_sync(0xffffffffu, (v & (EM_AGG | EM_INCL)) != 0);
+            const u32 m_incl = __ballot_sync(0xffffffffu, (v & EM_INCL) != 0);
+            const u32 n_ready = m_ready == 0xffffffffu ? 32u : (u32)__ffs((int)~m_ready) - 1u;    // published states, nearest first, without a gap
+            const u32 incl_in = m_incl & (n_ready == 32u ? 0xffffffffu : ((1u << n_ready) - 1u));
+            const u32 take = incl_in ? (u32)__ffs((int)incl_in) : n_ready;          // up to and including the first inclusive one
+            u64 contrib = lane < take ? (v & EM_VALUE) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+            prefix += contrib;
+            if (incl_in) done = true; else t -= (long long)take;
+        }
+        if (lane == 0) {
+            if (tile != 0) st_volatile_u64(status + tile, (prefix + total) | EM_INCL);
+            s_base = prefix;
+        }
+    }
+    if (!WARP_LB && tid == 0) {
         s_off[256] = total;
         u64 prefix = 0;
         if (tile == 0) {
@@ -626,8 +657,12 @@ int rast_forward_stage2(int P, long long R, long long n_visible, int W, int H, c
         const u32 nblk = (u32)((n_visible + 255) / 256);
         cudaMemsetAsync(b.emit_status, 0, ((size_t)nblk + 1) * sizeof(u64), stream);
         cudaMemsetAsync(b.emit_ticket, 0, 64 * sizeof(u32), stream);
-        emit_instances_kernel<<<nblk, 256, 0, stream>>>(sorted_gid, (u32)n_visible, g.tiles_touched, g.rect,
-                                                        d.grid_x, b.ikeys_a, b.ivals_a, b.emit_status, b.emit_ticket);
+        if (g_opt_lookback_parallel != 0)
+            emit_instances_kernel<true><<<nblk, 256, 0, stream>>>(sorted_gid, (u32)n_visible, g.tiles_touched, g.rect,
+                                                                  d.grid_x, b.ikeys_a, b.ivals_a, b.emit_status, b.emit_ticket);
+        else
+            emit_instances_kernel<false><<<nblk, 256, 0, stream>>>(sorted_gid, (u32)n_visible, g.tiles_touched, g.rect,
+                                                                   d.grid_x, b.ikeys_a, b.ivals_a, b.emit_status, b.emit_ticket);
         // 3. stable sort by tile id => (tile, depth, index) order
         side = radix_sort_pairs(b.ikeys_a, b.ivals_a, b.ikeys_b, b.ivals_b, (size_t)R, 0, d.tile_bits,
                                 b.sort_temp, b.sort_temp_bytes, stream);

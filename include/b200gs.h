@@ -41,6 +41,9 @@ int b200gs_version(void);
  *                    (the depth sort of ~1M Gaussians is bound by the serial work per tile); the result is identical
  *   "hexplane_time_bwd" time-row HexPlane backward (default 0, not yet measured): 1 / 2 = both levels' rows requested before the
  *                    first is used, register budget for 3 / 2 resident CTAs per SM (hexplane.cu: hexplane_time_bwd2_kernel)
+ *   "lookback_parallel" chained scans of the radix sort passes and of the instance emission (default 0, not yet measured):
+ *                    predecessors' states are read 8 (per digit) / 32 (per warp) at a time instead of one dependent L2 round
+ *                    trip each; identical results
  * Same arithmetic in every variant.  ("mlp_bwd_ablate" is a profiling aid, not a variant: it removes one part of the MLP
  * backward kernel -- WRONG RESULTS -- so that tools/native/mlp_variant_check can time what that part costs.)  set: 0 on success, non-zero for an unknown name; get: the value, or -1 for an unknown name. */
 int b200gs_set_option(const char* name, int value);
