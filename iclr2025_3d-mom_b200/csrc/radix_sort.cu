@@ -185,9 +185,13 @@ int radix_sort_pairs(u32* keys_a, u32* vals_a, u32* keys_b, u32* vals_b, size_t 
     cudaMemsetAsync(temp, 0, ((size_t)plan.passes * RS_RADIX + 256 + (size_t)plan.passes * tiles * RS_RADIX) * sizeof(u32), stream);
 
     DigitSpec spec;
+    // digit width: 8 bits per pass, or (opt-in "sort_balanced_digits") the key bits spread evenly over the passes -- the 12..15
+    // tile-id bits sort in two passes either way, but 6 + 6 bits scatter a 4096-key tile into 64 runs of 256 B per pass instead
+    // of 256 runs of 64 B in the first and 16 in the second.  Any digit split gives the same (stable) result.
+    const int per = g_opt_sort_balanced_digits != 0 ? (end_bit - begin_bit + plan.passes - 1) / plan.passes : RS_RADIX_BITS;
     for (int p = 0; p < RS_MAX_PASSES; ++p) {
-        int lo = begin_bit + p * RS_RADIX_BITS;
-        int nb = end_bit - lo; if (nb > RS_RADIX_BITS) nb = RS_RADIX_BITS; if (nb < 1) nb = 1;
+        int lo = begin_bit + p * per;
+        int nb = end_bit - lo; if (nb > per) nb = per; if (nb < 1) nb = 1;
         spec.shift[p] = lo < 32 ? lo : 31;
         spec.mask[p] = (1u << nb) - 1;
     }
