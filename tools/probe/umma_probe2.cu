@@ -10,6 +10,8 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#include <sys/wait.h>
+#include <unistd.h>
 #include "tc5_common.cuh"
 using namespace b200gs; using namespace b200gs::tc5;
 
@@ -99,11 +101,14 @@ int main()
         {"K-major, type 1 (SW128_BASE32B), SBO 1024, LBO 16, image ^p&7", T1, 16, 1024, 1},
     };
     int exact = 0;
-    for (const Config& c : configs) {           // one process: a configuration that kills the context ends the list (results so far are flushed)
-        const int rc = run(c);
+    for (const Config& c : configs) {           // one process per configuration: an illegal descriptor kills the CUDA context
         fflush(stdout);
-        if (rc == 0) ++exact;
-        if (rc >= 2) break;
+        const pid_t pid = fork();
+        if (pid == 0) { const int rc = run(c); fflush(stdout); _exit(rc); }
+        int status = 0;
+        waitpid(pid, &status, 0);
+        if (WIFEXITED(status) && WEXITSTATUS(status) == 0) ++exact;
+        else if (!WIFEXITED(status)) printf("%-58s child died (signal %d)\n", c.name, WTERMSIG(status));
     }
     printf("%d configuration(s) exact\n", exact);
     return 0;
