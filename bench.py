@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--scale-mu", type=float, default=0.010, help="S-coarse 0.010 / S-fine 0.004 (SURVEY.md 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--render-frames", type=int, default=30, help="frames per GPU for the render-FPS side measurement (0 = skip)")
+    ap.add_argument("--no-shared-spatial", action="store_true",
+                    help="render every frame with the full six-plane HexPlane pass instead of sharing the spatial product over the sequence")
     ap.add_argument("--cpu-points", type=int, default=0, help="override the cpu_baseline sample size")
     return ap.parse_args()
 
@@ -290,7 +292,14 @@ def render_fps(args, model, device, world, rank, impl, ref_render=None):
         n = args.render_frames
         cams = syn.orbit_cameras(n * world, W, H, device=device)[rank::world]
         fn = (lambda c: engine.render(c, model, bg, stage="fine")) if impl == "b200" else (lambda c: ref_render(c, model, bg, "fine"))
-        with torch.no_grad():
+        # our arm renders the sequence the way engine.render_frames does: the spatial half of the HexPlane field is evaluated
+        # once for the whole trajectory (the Gaussians do not move between frames), every frame samples its time planes only
+        import contextlib
+        shared = contextlib.nullcontext()
+        if impl == "b200" and not args.no_shared_spatial:
+            from b200gs import field as _field
+            shared = _field.shared_spatial_product(model._deformation, model._xyz)
+        with torch.no_grad(), shared:
             for c in cams[:3]:
                 fn(c)
             torch.cuda.synchronize()
@@ -518,8 +527,18 @@ def _main():
     if not timer:
         model.optimizer.step = opt_step
     render = None
+    render_note = None
     if args.render_frames > 0:
-        render = render_fps(args, model, device, world, rank, impl, ref_render=None if impl == "b200" else trainer.render_fn)
+        try:
+            render = render_fps(args, model, device, world, rank, impl, ref_render=None if impl == "b200" else trainer.render_fn)
+        except Exception as ex:                      # the side measurement must not take the headline down: fall back to per-frame passes
+            if impl != "b200" or args.no_shared_spatial:
+                raise
+            render_note = f"shared spatial product failed ({type(ex).__name__}: {ex}); per-frame six-plane passes measured instead"
+            args.no_shared_spatial = True
+            from b200gs import field as _field
+            _field._SHARED = None
+            render = render_fps(args, model, device, world, rank, impl, ref_render=None)
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
@@ -617,7 +636,11 @@ def _main():
     if render is not None:
         res["render"] = render
         res["config"]["render"] = (f"video rendering, {args.render_frames} frames per GPU of an orbit with advancing time, frames sharded "
-                                   "round-robin over ranks; fps = device time, e2e_fps = wall clock incl. to8b + D2H per frame")
+                                   "round-robin over ranks; fps = device time, e2e_fps = wall clock incl. to8b + D2H per frame"
+                                   + ("" if impl != "b200" or args.no_shared_spatial else
+                                      "; spatial HexPlane product evaluated once per sequence (engine.render_frames), time planes per frame"))
+        if render_note:
+            res["config"]["render_note"] = render_note
     if impl != "b200":
         res["impl"] = "reference"
         res["reference_stack"] = "reference CUDA rasterizer (oracle/_ref, unmodified) + PyTorch port of HexPlane/deformation + torch.optim.Adam, on GPU"

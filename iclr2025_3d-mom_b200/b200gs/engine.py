@@ -167,6 +167,21 @@ def render(cam, pc, bg_color, scaling_modifier=1.0, stage="fine", delta_scale=1,
             "depth": depth}
 
 
+def render_frames(cams, pc, bg_color, stage="fine", **kw):
+    """render() for every camera of a sequence over ONE static model (render_4DGS.py:41-76), as a generator: in the fine
+    stage the time-independent half of the HexPlane field is evaluated once for the whole sequence
+    (field.shared_spatial_product) instead of once per frame."""
+    from . import field as _field
+    with torch.no_grad():
+        if stage == "fine" and pc.get_xyz.is_cuda:
+            with _field.shared_spatial_product(pc._deformation, pc._xyz):
+                for cam in cams:
+                    yield render(cam, pc, bg_color, stage=stage, **kw)
+        else:
+            for cam in cams:
+                yield render(cam, pc, bg_color, stage=stage, **kw)
+
+
 def _receives_grad(name, stage):
     """Parameters the reference's loss reaches (SURVEY.md Appendix C iii): timenet, the opacity /
     SH heads and the aabb never do; in the coarse stage the whole deformation field is bypassed."""

@@ -15,6 +15,7 @@ Differences that do not change results:
 Configurations the reference can express but does not train with are rejected loudly
 (NotImplementedError) instead of silently falling back to PyTorch operators.
 """
+import contextlib
 import ctypes
 import itertools
 
@@ -218,8 +219,9 @@ MASK_SPATIAL, MASK_TIME, MASK_ALL = 0x0B, 0x34, 0x3F
 _SHARED = None
 
 
-def begin_shared_step(net, xyz_param):
-    """net: deform_network; xyz_param: the leaf the views will query (its .grad receives the spatial xyz gradient)."""
+def begin_shared_step(net, xyz_param, inference=False):
+    """net: deform_network; xyz_param: the leaf the views will query (its .grad receives the spatial xyz gradient).
+    inference: no gradient accumulator is allocated (see shared_spatial_product)."""
     global _SHARED
     grid = net.deformation_net.grid
     planes = grid._planes()
@@ -232,8 +234,23 @@ def begin_shared_step(net, xyz_param):
     order = _cell_order(xyz, grid.aabb)
     check(_lib.lib().b200gs_hexplane_forward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(order), None, 0.0, MASK_SPATIAL, None,
                                                     S.data_ptr(), current_stream()), "hexplane_forward(spatial)")
-    _SHARED = {"key": (xyz.data_ptr(), xyz_param._version, P), "S": S, "A": torch.zeros_like(S), "xyz_param": xyz_param, "grid": grid,
+    _SHARED = {"key": (xyz.data_ptr(), xyz_param._version, P), "S": S, "A": None if inference else torch.zeros_like(S), "xyz_param": xyz_param, "grid": grid,
                "order": order, "used": False}
+
+
+@contextlib.contextmanager
+def shared_spatial_product(net, xyz_param):
+    """Rendering a sequence of frames of ONE static model (render_4DGS.py:41-76 renders a whole trajectory from fixed
+    Gaussians): the product of the three spatial planes depends on xyz only, so it is evaluated once for the sequence and
+    every frame samples just its time planes (b200gs_hexplane_time_forward: 1-D lerps from shared memory) and multiplies.
+    Same values as the per-frame six-plane pass up to FP32 re-association (tests/test_hexplane_split_parity.py).  Use under
+    torch.no_grad(); nothing is accumulated and no backward is deferred.  The model must not change inside the block."""
+    global _SHARED
+    begin_shared_step(net, xyz_param, inference=True)
+    try:
+        yield
+    finally:
+        _SHARED = None
 
 
 def finish_shared_step():
