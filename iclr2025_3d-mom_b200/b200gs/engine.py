@@ -171,15 +171,16 @@ def render_frames(cams, pc, bg_color, stage="fine", **kw):
     """render() for every camera of a sequence over ONE static model (render_4DGS.py:41-76), as a generator: in the fine
     stage the time-independent half of the HexPlane field is evaluated once for the whole sequence
     (field.shared_spatial_product) instead of once per frame."""
+    import contextlib
     from . import field as _field
-    with torch.no_grad():
+    with contextlib.ExitStack() as stack:
         if stage == "fine" and pc.get_xyz.is_cuda:
-            with _field.shared_spatial_product(pc._deformation, pc._xyz):
-                for cam in cams:
-                    yield render(cam, pc, bg_color, stage=stage, **kw)
-        else:
-            for cam in cams:
-                yield render(cam, pc, bg_color, stage=stage, **kw)
+            with torch.no_grad():
+                stack.enter_context(_field.shared_spatial_product(pc._deformation, pc._xyz))
+        for cam in cams:
+            with torch.no_grad():              # per frame, not across the yield: the consumer keeps its own grad mode
+                out = render(cam, pc, bg_color, stage=stage, **kw)
+            yield out
 
 
 def _receives_grad(name, stage):
