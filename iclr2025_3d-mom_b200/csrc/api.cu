@@ -21,6 +21,7 @@ int g_opt_sort_small_tiles = env_int("B200GS_SORT_SMALL_TILES", 0);      // not 
 int g_opt_hexplane_time_bwd = env_int("B200GS_HEXPLANE_TIME_BWD", 0);    // not yet measured: opt-in
 int g_opt_lookback_parallel = env_int("B200GS_LOOKBACK_PARALLEL", 0);    // not yet measured: opt-in
 int g_opt_sort_balanced_digits = env_int("B200GS_SORT_BALANCED_DIGITS", 0);    // not yet measured: opt-in
+int g_opt_hexplane_time_fwd = env_int("B200GS_HEXPLANE_TIME_FWD", 0);    // not yet measured: opt-in
 int g_opt_mlp_bwd_ablate = 0;                                             // timing experiments only (wrong results); never from the environment
 
 void set_error(const char* fmt, ...)
@@ -115,6 +116,7 @@ int b200gs_set_option(const char* name, int value)
     if (name && !strcmp(name, "mlp_bwd_ablate")) { b200gs::g_opt_mlp_bwd_ablate = value; return 0; }
     if (name && !strcmp(name, "lookback_parallel")) { b200gs::g_opt_lookback_parallel = value; return 0; }
     if (name && !strcmp(name, "sort_balanced_digits")) { b200gs::g_opt_sort_balanced_digits = value; return 0; }
+    if (name && !strcmp(name, "hexplane_time_fwd")) { b200gs::g_opt_hexplane_time_fwd = value; return 0; }
     set_error("b200gs_set_option: unknown option '%s'", name ? name : "(null)");
     return -1;
 }
@@ -127,6 +129,7 @@ int b200gs_get_option(const char* name)
     if (name && !strcmp(name, "mlp_bwd_ablate")) return b200gs::g_opt_mlp_bwd_ablate;
     if (name && !strcmp(name, "lookback_parallel")) return b200gs::g_opt_lookback_parallel;
     if (name && !strcmp(name, "sort_balanced_digits")) return b200gs::g_opt_sort_balanced_digits;
+    if (name && !strcmp(name, "hexplane_time_fwd")) return b200gs::g_opt_hexplane_time_fwd;
     return -1;
 }
 

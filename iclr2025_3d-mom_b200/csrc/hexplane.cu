@@ -430,6 +430,45 @@ hexplane_time_fwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const _
     }
 }
 
+// Opt-in variant ("hexplane_time_fwd" = 1 / 2, unmeasured): compile-time 2 levels, both levels' factor rows requested before the
+// first is used, both feature rows stored at the end; same arithmetic per element as the kernel above.  MINB = resident CTAs per
+// SM the register budget is set for (3: 42 registers like the kernel above, 2: no cap).
+template <int MINB>
+__global__ void __launch_bounds__(512, MINB)
+hexplane_time_fwd2_kernel(const __grid_constant__ b200gs_hexplane_desc d, const __grid_constant__ TimeRowSetup ts, long long P,
+                          const float* __restrict__ pts, const unsigned int* __restrict__ order, float t,
+                          const float* __restrict__ factor, float* __restrict__ feat, int tiled)
+{
+    constexpr int L = 2, F = L * HP_C;
+    extern __shared__ float R[];
+    time_rows_prepare(d, t, R, ts);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, slot = lane >> 3, cg = lane & 7;
+    const AabbNorm an = aabb_norm(d.aabb);
+    const long long ppi = (long long)(blockDim.x >> 5) * 4;
+    const long long chunk = ((P + gridDim.x - 1) / gridDim.x + ppi - 1) / ppi * ppi;
+    const long long begin = (long long)blockIdx.x * chunk, end = begin + chunk < P ? begin + chunk : P;
+    for (long long base = begin + (long long)(threadIdx.x >> 5) * 4; base < end; base += ppi) {
+        const long long i = base + slot;
+        if (i >= end) continue;
+        const size_t g = order ? (size_t)__ldg(order + i) : (size_t)i;
+        float4 f[L];
+#pragma unroll
+        for (int l = 0; l < L; ++l)
+            f[l] = factor ? __ldg(reinterpret_cast<const float4*>(factor + g * F + l * HP_C + cg * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+        float c[4], scale[3];
+        normalized_coords(pts, nullptr, t, an, g, c, scale);
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) f[l] = mul4(f[l], row_sample(R + ts.off[l][a], c[a], d.res[l][a], cg).v);
+        }
+#pragma unroll
+        for (int l = 0; l < L; ++l)
+            *reinterpret_cast<float4*>(feat + (tiled ? tc5::stash_off((long long)g, l * HP_C + cg * 4) : g * F + l * HP_C + cg * 4)) = f[l];
+    }
+}
+
 __global__ void __launch_bounds__(256, 3)
 hexplane_time_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const __grid_constant__ TimeRowSetup ts, long long P,
                          const float* __restrict__ pts, const unsigned int* __restrict__ order, float t,
@@ -825,6 +864,12 @@ int b200gs_hexplane_time_forward(const b200gs_hexplane_desc* desc, long long P, 
     long long blocks = (P + 63) / 64;                // 16 warps x 4 point slots per block; the kernels are latency bound, so as many warps as fit
     const long long cap = (long long)NUM_SMS * (smem * 3 <= 220 * 1024 ? 3 : (smem * 2 <= 220 * 1024 ? 2 : 1));
     if (blocks > cap) blocks = cap;
+    if (g_opt_hexplane_time_fwd != 0 && desc->levels == 2) {            // opt-in variant, see hexplane_time_fwd2_kernel
+        auto kern = g_opt_hexplane_time_fwd == 2 ? hexplane_time_fwd2_kernel<2> : hexplane_time_fwd2_kernel<3>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (g_opt_hexplane_time_fwd == 2 && blocks > (long long)NUM_SMS * 2) blocks = (long long)NUM_SMS * 2;
+        kern<<<(unsigned)blocks, 512, smem, (cudaStream_t)stream>>>(*desc, ts, P, pts, order, time_scalar, factor, features, features_tiled);
+    } else
     hexplane_time_fwd_kernel<<<(unsigned)blocks, 512, smem, (cudaStream_t)stream>>>(*desc, ts, P, pts, order, time_scalar, factor, features, features_tiled);
     return check_launch("hexplane_time_forward");
 }

@@ -39,6 +39,8 @@ int b200gs_version(void);
  *                    past the next layer's MMA issue (deform_mlp_tc5.cu)
  *   "sort_small_tiles" radix sort (default 0, not yet measured): 2048-key tiles instead of 4096 for inputs up to 4M keys
  *                    (the depth sort of ~1M Gaussians is bound by the serial work per tile); the result is identical
+ *   "hexplane_time_fwd" time-row HexPlane forward (default 0, not yet measured): 1 / 2 = both levels' factor rows requested up front,
+ *                    register budget for 3 / 2 resident CTAs per SM
  *   "hexplane_time_bwd" time-row HexPlane backward (default 0, not yet measured): 1 / 2 = both levels' rows requested before the
  *                    first is used, register budget for 3 / 2 resident CTAs per SM (hexplane.cu: hexplane_time_bwd2_kernel)
  *   "lookback_parallel" chained scans of the radix sort passes and of the instance emission (default 0, not yet measured):

@@ -1,4 +1,5 @@
-// Standalone check of the time-row HexPlane backward variants through the C ABI ("hexplane_time_bwd" = 0 / 1 / 2) on the
+// Standalone check of the time-row HexPlane kernel variants through the C ABI ("hexplane_time_fwd" = 0 / 1: features bit-identical;
+// "hexplane_time_bwd" = 0 / 1 / 2) on the
 // reference's field shape (2 levels, 64 / 128 spatial resolution, 50 time steps, 32 channels), one timestamp per launch:
 // d_factor_accum and d_pts must be bit-identical (same arithmetic per element), the time-plane gradients (vector REDs into
 // replicated rows: order dependent) equal to 1e-5 of their scale; device time per launch (CUDA events, 10 launches after a warm-up).
@@ -58,12 +59,30 @@ int main(int argc, char** argv)
     cudaStream_t st; CK(cudaStreamCreate(&st));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     const float t = 0.37f;
-    BK(b200gs_hexplane_time_forward(&d, P, pts, nullptr, t, factor, feat, tiled, st));
-    CK(cudaStreamSynchronize(st));
-    printf("b200gs %d: P = %lld, d_features %s, scratch %zu bytes\n", b200gs_version(), P, tiled ? "tiled" : "row-major", sb);
+    printf("b200gs %d: P = %lld, features / d_features %s, scratch %zu bytes\n", b200gs_version(), P, tiled ? "tiled" : "row-major", sb);
+    bool fwd_ok = true;
+    {
+        std::vector<float> r_feat;
+        for (int variant = 0; variant < 3; ++variant) {
+            BK(b200gs_set_option("hexplane_time_fwd", variant));
+            float total = 0;
+            for (int rep = -1; rep < 10; ++rep) {
+                CK(cudaEventRecord(e0, st));
+                BK(b200gs_hexplane_time_forward(&d, P, pts, nullptr, t, factor, feat, tiled, st));
+                CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st));
+                float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep >= 0) total += ms;
+            }
+            std::vector<float> a = to_host(feat, rowsP * F);
+            size_t bad = 0;
+            if (variant == 0) r_feat = a; else for (size_t i = 0; i < a.size(); ++i) bad += memcmp(&a[i], &r_feat[i], 4) != 0;
+            printf("hexplane_time_fwd = %d: %.3f ms per launch%s\n", variant, total / 10, variant == 0 ? "" : (bad ? "  features DIFFER" : "  features bit-identical"));
+            fwd_ok &= bad == 0;
+        }
+        BK(b200gs_set_option("hexplane_time_fwd", 0));
+    }
     std::vector<float> r_dfac, r_dpts, r_gp[2][3];
     const int tk[3] = {2, 4, 5};
-    bool ok = true;
+    bool ok = fwd_ok;
     for (int variant = 0; variant < 3; ++variant) {
         BK(b200gs_set_option("hexplane_time_bwd", variant));
         float total = 0;
