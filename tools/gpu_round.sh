@@ -11,6 +11,7 @@ tools/native/mlp_variant_check 1000000 ablate > gpurun_out/mlp_bwd_ablate_$TAG.l
 tools/native/sort_check 1000000 32 > gpurun_out/sort_check_$TAG.log 2>&1; tail -9 gpurun_out/sort_check_$TAG.log
 tools/native/sort_check 5100000 12 > gpurun_out/sort_check12_$TAG.log 2>&1; tail -9 gpurun_out/sort_check12_$TAG.log
 tools/native/hexplane_time_check > gpurun_out/hexplane_time_check_$TAG.log 2>&1; tail -4 gpurun_out/hexplane_time_check_$TAG.log
+tools/native/view_check 1000000 1280 720 0.01 8 > gpurun_out/view_check_$TAG.log 2>&1; tail -16 gpurun_out/view_check_$TAG.log
 tools/native/rast_check 1000000 1280 720 0.01 10 > gpurun_out/rast_check_$TAG.log 2>&1; sed -n 2,4p gpurun_out/rast_check_$TAG.log
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" ; tail -3 gpurun_out/pytest_$TAG.log
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_b200_$TAG.json 2> gpurun_out/bench_b200_$TAG.err; echo "bench rc=$?"
