@@ -563,6 +563,10 @@ size_t bwd_smem() { return (size_t)(2 * MW * MW + 2 * MW * MW) * 4 + 98304 + 2 *
 
 }  // namespace tc5
 
+int deform_mlp_backward_tc5_db(const b200gs_mlp_weights* w, const b200gs_mlp_grads* gw, long long P, const float* feat,
+                               const float* saved, const float* d_pts, const float* d_scales, const float* d_rot,
+                               float* d_feat, unsigned dy_sbo, cudaStream_t stream);      // deform_mlp_bwd_tc5_db.cu
+
 int deform_mlp_backward_tc5(const b200gs_mlp_weights* w, const b200gs_mlp_grads* gw, long long P, const float* feat,
                             const float* saved, const float* d_pts, const float* d_scales, const float* d_rot,
                             float* d_feat, cudaStream_t stream)
@@ -577,6 +581,8 @@ int deform_mlp_backward_tc5(const b200gs_mlp_weights* w, const b200gs_mlp_grads*
     // aligned W1 / W2 gradient rows for its 128-bit REDs
     bool v2 = g_opt_mlp_bwd_v2 != 0 && ((uintptr_t)gw->w1 & 15) == 0;
     for (int h = 0; h < 3; ++h) v2 = v2 && (!w->w2[h] || ((uintptr_t)gw->w2[h] & 15) == 0);
+    if (v2 && (g_opt_mlp_bwd_v2 == 151 || g_opt_mlp_bwd_v2 == 183))      // EXPERIMENTAL: one dY image per group, double buffered
+        return deform_mlp_backward_tc5_db(w, gw, P, feat, saved, d_pts, d_scales, d_rot, d_feat, g_opt_mlp_bwd_v2 == 183 ? 512u : 1024u, stream);
     if (v2 && g_opt_mlp_bwd_ablate != 0) {           // timing experiments, wrong results (see the kernel's ABL comment)
         void (*kern)(tc5::BwdArgs) = nullptr;
         switch (g_opt_mlp_bwd_ablate) {
