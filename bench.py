@@ -315,6 +315,14 @@ def render_fps(args, model, device, world, rank, impl, ref_render=None):
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
+            ms_plain = None
+            if impl == "b200" and not args.no_shared_spatial:          # the same frames with the full six-plane pass per frame, for reference
+                e0.record()
+                for c in cams:
+                    fn(c)
+                e1.record()
+                torch.cuda.synchronize()
+                ms_plain = e0.elapsed_time(e1)
             if impl == "b200":
                 from b200gs import output
                 ring = output.FrameRing(H, W, depth=4, device=device)      # pinned buffers are allocated once, outside the loop
@@ -336,11 +344,15 @@ def render_fps(args, model, device, world, rank, impl, ref_render=None):
             wall = time.perf_counter() - t0
         if world > 1:
             import torch.distributed as dist
-            t = torch.tensor([ms, wall * 1e3], device=device)
+            t = torch.tensor([ms, wall * 1e3, ms_plain if ms_plain is not None else 0.0], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1]) / 1e3
+            if ms_plain is not None:
+                ms_plain = float(t[2])
         out[tag] = {"fps": n * world / (ms / 1e3), "e2e_fps": n * world / wall, "frames": n * world,
                     "d2h_bytes_per_frame": 3 * W * H if impl == "b200" else 12 * W * H}
+        if ms_plain is not None:
+            out[tag]["fps_full_field_per_frame"] = n * world / (ms_plain / 1e3)
     return out
 
 
