@@ -113,7 +113,12 @@ int b200gs_set_option(const char* name, int value)
     if (name && !strcmp(name, "mlp_fwd_elect")) { b200gs::g_opt_mlp_fwd_elect = value; return 0; }
     if (name && !strcmp(name, "sort_small_tiles")) { b200gs::g_opt_sort_small_tiles = value; return 0; }
     if (name && !strcmp(name, "hexplane_time_bwd")) { b200gs::g_opt_hexplane_time_bwd = value; return 0; }
-    if (name && !strcmp(name, "mlp_bwd_ablate")) { b200gs::g_opt_mlp_bwd_ablate = value; return 0; }
+    if (name && !strcmp(name, "mlp_bwd_ablate")) {          // wrong results by design: only for a process that says it is profiling
+        const char* e = getenv("B200GS_PROFILING");
+        if (value != 0 && !(e && e[0] == '1')) { set_error("b200gs_set_option: mlp_bwd_ablate needs B200GS_PROFILING=1 in the environment"); return -1; }
+        b200gs::g_opt_mlp_bwd_ablate = value;
+        return 0;
+    }
     if (name && !strcmp(name, "lookback_parallel")) { b200gs::g_opt_lookback_parallel = value; return 0; }
     if (name && !strcmp(name, "sort_balanced_digits")) { b200gs::g_opt_sort_balanced_digits = value; return 0; }
     if (name && !strcmp(name, "hexplane_time_fwd")) { b200gs::g_opt_hexplane_time_fwd = value; return 0; }

@@ -49,7 +49,8 @@ int b200gs_version(void);
  *   "sort_balanced_digits" radix sort (default 0, not yet measured): key bits spread evenly over the passes (6 + 6 for 12 tile-id
  *                    bits) instead of 8 bits per pass; identical results
  * Same arithmetic in every variant.  ("mlp_bwd_ablate" is a profiling aid, not a variant: it removes one part of the MLP
- * backward kernel -- WRONG RESULTS -- so that tools/native/mlp_variant_check can time what that part costs.)  set: 0 on success, non-zero for an unknown name; get: the value, or -1 for an unknown name. */
+ * backward kernel -- WRONG RESULTS -- so that tools/native/mlp_variant_check can time what that part costs; it is refused
+ * unless the environment has B200GS_PROFILING=1.)  set: 0 on success, non-zero for an unknown name; get: the value, or -1 for an unknown name. */
 int b200gs_set_option(const char* name, int value);
 int b200gs_get_option(const char* name);
 

@@ -104,5 +104,7 @@ def test_kernel_variant_options_defaults_and_toggle():
     for name in (b"sort_small_tiles", b"hexplane_time_bwd", b"lookback_parallel", b"sort_balanced_digits", b"hexplane_time_fwd", b"mlp_bwd_ablate"):      # unmeasured variants stay opt-in
         if os.environ.get("B200GS_" + name.decode().upper()) is None:
             assert L.b200gs_get_option(name) == 0
+    if os.environ.get("B200GS_PROFILING") != "1":                  # the wrong-results profiling builds cannot be switched on by accident
+        assert L.b200gs_set_option(b"mlp_bwd_ablate", 2) != 0 and L.b200gs_get_option(b"mlp_bwd_ablate") == 0
     assert L.b200gs_set_option(b"no_such_option", 1) != 0 and b"unknown option" in L.b200gs_last_error()
     assert L.b200gs_get_option(b"no_such_option") == -1

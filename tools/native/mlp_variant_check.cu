@@ -182,6 +182,7 @@ int main(int argc, char** argv)
 {
     const long long P = argc > 1 ? atoll(argv[1]) : 1000000;
     if (argc > 2 && !strcmp(argv[2], "ablate")) {
+        setenv("B200GS_PROFILING", "1", 1);          // the library refuses the ablation builds otherwise
         cudaStream_t st; CK(cudaStreamCreate(&st));
         run_ablations(P, st);
         return 0;
