@@ -15,7 +15,8 @@ static thread_local char g_err[512] = "";
 // on a B200 (bit-identical outputs; gradients equal up to float-atomic order); 0 selects the first-generation kernels. The
 // environment (B200GS_MLP_BWD_V2 / B200GS_MLP_FWD_ELECT = integer) overrides the initial value.
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : dflt; }
-int g_opt_mlp_bwd_v2 = env_int("B200GS_MLP_BWD_V2", 7);
+static int env_mlp_bwd() { const int v = env_int("B200GS_MLP_BWD_V2", 7); const char* e = getenv("B200GS_PROFILING"); return (v >= 16 && !(e && e[0] == '1')) ? 7 : v; }
+int g_opt_mlp_bwd_v2 = env_mlp_bwd();
 int g_opt_mlp_fwd_elect = env_int("B200GS_MLP_FWD_ELECT", 2);
 int g_opt_sort_small_tiles = env_int("B200GS_SORT_SMALL_TILES", 0);      // not yet measured: opt-in
 int g_opt_hexplane_time_bwd = env_int("B200GS_HEXPLANE_TIME_BWD", 0);    // not yet measured: opt-in
@@ -109,7 +110,12 @@ int b200gs_version(void) { return 100; }
 
 int b200gs_set_option(const char* name, int value)
 {
-    if (name && !strcmp(name, "mlp_bwd_v2")) { b200gs::g_opt_mlp_bwd_v2 = value; return 0; }
+    if (name && !strcmp(name, "mlp_bwd_v2")) {
+        const char* e = getenv("B200GS_PROFILING");          // values >= 16 are unvalidated experiments (deform_mlp_bwd_tc5.cu)
+        if (value >= 16 && !(e && e[0] == '1')) { set_error("b200gs_set_option: mlp_bwd_v2 = %d is experimental and needs B200GS_PROFILING=1 in the environment", value); return -1; }
+        b200gs::g_opt_mlp_bwd_v2 = value;
+        return 0;
+    }
     if (name && !strcmp(name, "mlp_fwd_elect")) { b200gs::g_opt_mlp_fwd_elect = value; return 0; }
     if (name && !strcmp(name, "sort_small_tiles")) { b200gs::g_opt_sort_small_tiles = value; return 0; }
     if (name && !strcmp(name, "hexplane_time_bwd")) { b200gs::g_opt_hexplane_time_bwd = value; return 0; }

@@ -34,7 +34,7 @@ int b200gs_version(void);
  * environment variable B200GS_<NAME>=<integer> overrides the initial value:
  *   "mlp_bwd_v2"     deformation-MLP backward (default 7): bit 0 = alternating weight slots + elected MMA issuer + coalesced
  *                    gradient flush; bits 1-2 = how d_out reaches a phase (3 = prefetched into L2 one phase ahead); bit 3 =
- *                    d_features leave TMEM in four parts; 23 / 55 / 87 / 119 / 151 / 183 are UNVALIDATED experiments (deform_mlp_bwd_tc5.cu)
+ *                    d_features leave TMEM in four parts; values >= 16 (23 / 55 / 87 / 119 / 151 / 183) are UNVALIDATED experiments, refused unless B200GS_PROFILING=1 (deform_mlp_bwd_tc5.cu)
  *   "mlp_fwd_elect"  deformation-MLP forward (default 2): 1 = elected MMA issuer, 2 = plus activation-stash stores deferred
  *                    past the next layer's MMA issue (deform_mlp_tc5.cu)
  *   "sort_small_tiles" radix sort (default 0, not yet measured): 2048-key tiles instead of 4096 for inputs up to 4M keys

@@ -106,5 +106,7 @@ def test_kernel_variant_options_defaults_and_toggle():
             assert L.b200gs_get_option(name) == 0
     if os.environ.get("B200GS_PROFILING") != "1":                  # the wrong-results profiling builds cannot be switched on by accident
         assert L.b200gs_set_option(b"mlp_bwd_ablate", 2) != 0 and L.b200gs_get_option(b"mlp_bwd_ablate") == 0
+        keep = L.b200gs_get_option(b"mlp_bwd_v2")
+        assert L.b200gs_set_option(b"mlp_bwd_v2", 23) != 0 and L.b200gs_get_option(b"mlp_bwd_v2") == keep      # unvalidated experiment
     assert L.b200gs_set_option(b"no_such_option", 1) != 0 and b"unknown option" in L.b200gs_last_error()
     assert L.b200gs_get_option(b"no_such_option") == -1

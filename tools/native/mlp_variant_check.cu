@@ -181,8 +181,8 @@ static void run_ablations(long long P, cudaStream_t st)
 int main(int argc, char** argv)
 {
     const long long P = argc > 1 ? atoll(argv[1]) : 1000000;
+    setenv("B200GS_PROFILING", "1", 1);              // the library refuses experimental variants and ablation builds otherwise
     if (argc > 2 && !strcmp(argv[2], "ablate")) {
-        setenv("B200GS_PROFILING", "1", 1);          // the library refuses the ablation builds otherwise
         cudaStream_t st; CK(cudaStreamCreate(&st));
         run_ablations(P, st);
         return 0;
