@@ -92,6 +92,9 @@ class FusedAdam(Optimizer):
                 buckets.setdefault((beta1, beta2, eps), []).append(
                     (p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), (lr / bc1) * -1, bc2 ** 0.5))
         stream = current_stream()
+        if buckets:
+            from . import field as _field          # parameters change below without a version bump (raw pointers)
+            _field.invalidate_inference_cache()
         for (beta1, beta2, eps), items in buckets.items():
             arr = (_AdamTensor * len(items))()
             for i, it in enumerate(items):

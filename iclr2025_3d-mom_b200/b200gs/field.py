@@ -18,6 +18,7 @@ Configurations the reference can express but does not train with are rejected lo
 import contextlib
 import ctypes
 import itertools
+import os
 
 import torch
 import torch.nn as nn
@@ -289,6 +290,34 @@ def _shared_for(xyz, P):
     return None
 
 
+# Opt-in (B200GS_INFERENCE_SPATIAL_CACHE=1 or field.INFERENCE_SPATIAL_CACHE = True; not yet run on a GPU): what
+# shared_spatial_product does for a caller that can wrap its frame loop, done implicitly for callers that cannot -- the
+# reference's own render_4DGS.py running unchanged through the launcher.  Under torch.no_grad() the spatial product is kept
+# between calls for as long as xyz, the aabb and every plane are the same tensors at the same version; FusedAdam.step() writes
+# parameters through raw pointers (no version bump), so it drops the cache explicitly.
+INFERENCE_SPATIAL_CACHE = os.environ.get("B200GS_INFERENCE_SPATIAL_CACHE") == "1"
+_INFER = None
+
+
+def invalidate_inference_cache():
+    global _INFER
+    _INFER = None
+
+
+def _inference_shared(xyz, P, aabb, planes, levels, res, order):
+    global _INFER
+    if not INFERENCE_SPATIAL_CACHE or torch.is_grad_enabled():
+        return None
+    key = (xyz.data_ptr(), xyz._version, P, aabb.data_ptr(), aabb._version) + tuple((p.data_ptr(), p._version) for p in planes)
+    if _INFER is None or _INFER["key"] != key:
+        S = torch.empty((P, 32 * levels), dtype=torch.float32, device=xyz.device)
+        d = _hex_desc(aabb, planes, levels, res)
+        check(_lib.lib().b200gs_hexplane_forward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(order), None, 0.0, MASK_SPATIAL, None,
+                                                        S.data_ptr(), current_stream()), "hexplane_forward(spatial, inference cache)")
+        _INFER = {"key": key, "S": S, "A": None, "used": False, "order": order}
+    return _INFER
+
+
 class _DeformFn(torch.autograd.Function):
     """(pts, scales, rot) = field(xyz, scales, rot, t, scene_flow, frame_num, delta_scale).
 
@@ -313,6 +342,8 @@ class _DeformFn(torch.autograd.Function):
         order = _cell_order(xyz, aabb)
         ctx.order = order
         sh = _shared_for(xyz, P)
+        if sh is None:
+            sh = _inference_shared(xyz, P, aabb, planes, levels, res, order)
         ctx.shared = sh
         ctx.time_rows = False
         ctx.feat_tiled = False
