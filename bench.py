@@ -648,7 +648,7 @@ def _main():
         try:
             from b200gs import _lib as _l
             res["config"]["kernel_options"] = {n: int(_l.lib().b200gs_get_option(n.encode()))
-                                               for n in ("mlp_fwd_elect", "mlp_bwd_v2", "sort_small_tiles", "hexplane_time_bwd", "lookback_parallel", "sort_balanced_digits", "hexplane_time_fwd")}
+                                               for n in ("mlp_fwd_elect", "mlp_bwd_v2", "hexplane_time_fwd", "hexplane_time_bwd", "lookback_parallel")}
         except Exception as ex:              # informational only
             res["config"]["kernel_options"] = f"unavailable: {ex}"
     if render is not None:

@@ -57,6 +57,7 @@ class FusedAdam(Optimizer):
         # one launch per distinct (betas, eps) (the reference has a single combination)
         buckets = {}
         keep = []
+        touched = []
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
             lr = float(group["lr"])
@@ -85,6 +86,7 @@ class FusedAdam(Optimizer):
                     v = torch.empty_like(p).copy_(v); state["exp_avg_sq"] = v
                 if not _same_layout(g, p):
                     g = torch.empty_like(p).copy_(g); keep.append(g)
+                touched.append(p)
                 state["step"] += 1
                 step = float(state["step"])
                 bc1 = 1 - beta1 ** step
@@ -93,8 +95,11 @@ class FusedAdam(Optimizer):
                     (p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), (lr / bc1) * -1, bc2 ** 0.5))
         stream = current_stream()
         if buckets:
-            from . import field as _field          # parameters change below without a version bump (raw pointers)
-            _field.invalidate_inference_cache()
+            # the kernel writes the parameters through raw pointers: tell autograd (saved-tensor checks) and every cache keyed
+            # on `_version` (field._cell_order, the shared spatial HexPlane product) that they changed
+            from . import field as _field
+            _field.drop_shared()
+            torch.autograd.graph.increment_version(touched)
         for (beta1, beta2, eps), items in buckets.items():
             arr = (_AdamTensor * len(items))()
             for i, it in enumerate(items):

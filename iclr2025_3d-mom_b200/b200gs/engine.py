@@ -292,36 +292,40 @@ class ViewParallelTrainer:
         if share_spatial:
             _field.begin_shared_step(self.model._deformation, self.model._xyz)
         self._sh_work = None
-        for vi, (cam, gt) in enumerate(zip(cams, gts)):
-            pkg = self.render_fn(cam, self.model, self.bg, self.stage, shs) if self.shared_shs else \
-                self.render_fn(cam, self.model, self.bg, self.stage)
-            _field.ACCUMULATE_INTO_GRAD = self.shared_shs     # p.grad are arena views: let the field kernels add into them
-            _rast.SH_GRAD_ACCUMULATOR = shs.grad if (shs is not None and shs.is_cuda) else None
-            if self.overlap_sh_reduce and vi == len(cams) - 1:
-                # called by the rasterizer backward right after it has queued the kernel that adds this view's SH gradient
-                _rast.AFTER_SH_ACCUMULATE = lambda: self._start_sh_reduce(shs)
-            try:
-                if self.shared_shs and gt.is_cuda:
-                    # fused L1 (utils/loss_utils.py:23-24) + its gradient, then backward from the image
-                    if total is None:
-                        total = torch.zeros(1, device=gt.device)
-                    img = pkg["render"]
-                    d_img = fusedops.l1_loss_and_grad(img, gt, 1.0 / (img.numel() * B), total)
-                    img.backward(d_img)
-                    loss = None
-                else:
-                    loss = (pkg["render"] - gt).abs().mean() / B
-                    loss.backward()
-            finally:
-                _field.ACCUMULATE_INTO_GRAD = False
-                _rast.SH_GRAD_ACCUMULATOR = None
-                _rast.AFTER_SH_ACCUMULATE = None
-            vg = pkg["viewspace_points"].grad
-            if vg is not None:
-                self.viewspace_grad += vg
-            torch.maximum(self.max_radii, pkg["radii"], out=self.max_radii)
-            if loss is not None:
-                total = loss.detach() if total is None else total + loss.detach()
+        try:
+            for vi, (cam, gt) in enumerate(zip(cams, gts)):
+                pkg = self.render_fn(cam, self.model, self.bg, self.stage, shs) if self.shared_shs else \
+                    self.render_fn(cam, self.model, self.bg, self.stage)
+                _field.ACCUMULATE_INTO_GRAD = self.shared_shs     # p.grad are arena views: let the field kernels add into them
+                _rast.SH_GRAD_ACCUMULATOR = shs.grad if (shs is not None and shs.is_cuda) else None
+                if self.overlap_sh_reduce and vi == len(cams) - 1:
+                    # called by the rasterizer backward right after it has queued the kernel that adds this view's SH gradient
+                    _rast.AFTER_SH_ACCUMULATE = lambda: self._start_sh_reduce(shs)
+                try:
+                    if self.shared_shs and gt.is_cuda:
+                        # fused L1 (utils/loss_utils.py:23-24) + its gradient, then backward from the image
+                        if total is None:
+                            total = torch.zeros(1, device=gt.device)
+                        img = pkg["render"]
+                        d_img = fusedops.l1_loss_and_grad(img, gt, 1.0 / (img.numel() * B), total)
+                        img.backward(d_img)
+                        loss = None
+                    else:
+                        loss = (pkg["render"] - gt).abs().mean() / B
+                        loss.backward()
+                finally:
+                    _field.ACCUMULATE_INTO_GRAD = False
+                    _rast.SH_GRAD_ACCUMULATOR = None
+                    _rast.AFTER_SH_ACCUMULATE = None
+                vg = pkg["viewspace_points"].grad
+                if vg is not None:
+                    self.viewspace_grad += vg
+                torch.maximum(self.max_radii, pkg["radii"], out=self.max_radii)
+                if loss is not None:
+                    total = loss.detach() if total is None else total + loss.detach()
+        except BaseException:
+            _field.drop_shared()               # never leave a half-used spatial product behind (a later render() would reuse it)
+            raise
         if share_spatial:
             _field.finish_shared_step()
         if self.overlap_sh_reduce and shs is not None:

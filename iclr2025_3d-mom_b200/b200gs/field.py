@@ -79,18 +79,20 @@ _lib.register("b200gs_hexplane_order", ctypes.c_int, [ctypes.c_longlong, _P, _P,
 
 _ORDER_CACHE = {}
 ORDER_MIN_POINTS = 1 << 14
+ORDER_MAX_AGE = 64          # optimiser steps (version bumps of xyz) a cached order is kept for
 
 
 def _cell_order(pts, aabb):
-    """Cell-sorted visiting order of the query points (performance hint for the sampling kernels).
-    Cached per device on (storage, version): within one training iteration every view and the
-    backward pass query the same positions, so the sort is paid once per optimiser step."""
+    """Cell-sorted visiting order of the query points (a locality HINT for the sampling kernels: any permutation gives the
+    same results).  Cached per device on the storage: within one training iteration every view and the backward pass query
+    the same positions, and across iterations the Gaussians move by a small fraction of a cell, so the order is re-sorted
+    only every ORDER_MAX_AGE parameter updates (FusedAdam bumps `_version` per step) or when the tensor / aabb changes."""
     P = int(pts.shape[0])
     if P < ORDER_MIN_POINTS:
         return None
-    key = (pts.data_ptr(), pts._version, P, aabb.data_ptr(), aabb._version)
+    key = (pts.data_ptr(), P, aabb.data_ptr(), aabb._version)
     hit = _ORDER_CACHE.get(pts.device)
-    if hit is not None and hit[0] == key:
+    if hit is not None and hit[0] == key and 0 <= pts._version - hit[2] < ORDER_MAX_AGE:
         return hit[1]
     L = _lib.lib()
     order = torch.empty((P,), dtype=torch.int32, device=pts.device)
@@ -98,7 +100,7 @@ def _cell_order(pts, aabb):
     scratch = torch.empty((nbytes,), dtype=torch.uint8, device=pts.device)
     check(L.b200gs_hexplane_order(P, pts.data_ptr(), aabb.data_ptr(), order.data_ptr(), scratch.data_ptr(), nbytes,
                                   current_stream()), "hexplane_order")
-    _ORDER_CACHE[pts.device] = (key, order)
+    _ORDER_CACHE[pts.device] = (key, order, pts._version)
     return order
 
 
@@ -188,8 +190,9 @@ class _HexPlaneFn(torch.autograd.Function):
         grads = [torch.zeros_like(p, memory_format=torch.preserve_format) if n else None for p, n in zip(planes, need_planes)]
         d_pts = torch.empty_like(pts) if ctx.needs_input_grad[0] else None
         d = _hex_desc(aabb, planes, levels, res, grads)
+        d_feat = d_feat.contiguous()          # kept alive in this frame until the launch has been queued
         check(_lib.lib().b200gs_hexplane_backward(ctypes.byref(d), P, pts.data_ptr(), _optr(ctx.order),
-                                                  tt.data_ptr() if has_t else None, ts, d_feat.contiguous().data_ptr(),
+                                                  tt.data_ptr() if has_t else None, ts, d_feat.data_ptr(),
                                                   d_pts.data_ptr() if d_pts is not None else None, current_stream()),
               "hexplane_backward")
         return (d_pts, None, None, None, None, *grads)
@@ -235,8 +238,8 @@ def begin_shared_step(net, xyz_param, inference=False):
     order = _cell_order(xyz, grid.aabb)
     check(_lib.lib().b200gs_hexplane_forward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(order), None, 0.0, MASK_SPATIAL, None,
                                                     S.data_ptr(), current_stream()), "hexplane_forward(spatial)")
-    _SHARED = {"key": (xyz.data_ptr(), xyz_param._version, P), "S": S, "A": None if inference else torch.zeros_like(S), "xyz_param": xyz_param, "grid": grid,
-               "order": order, "used": False}
+    _SHARED = {"key": _shared_key(xyz, xyz_param._version, P, grid.aabb, planes), "S": S, "A": None if inference else torch.zeros_like(S),
+               "xyz_param": xyz_param, "grid": grid, "order": order, "used": False}
 
 
 @contextlib.contextmanager
@@ -283,11 +286,24 @@ def finish_shared_step():
         xyz_param.grad += d_xyz
 
 
-def _shared_for(xyz, P):
+def _shared_key(xyz, version, P, aabb, planes):
+    """Identity of everything the spatial product depends on: the same tensors at the same versions.  FusedAdam.step writes
+    parameters through raw pointers and bumps their versions explicitly (adam.py), so an optimiser step always changes it."""
+    return (xyz.data_ptr(), version, P, aabb.data_ptr(), aabb._version) + tuple((p.data_ptr(), p._version) for p in planes)
+
+
+def _shared_for(xyz, P, aabb, planes):
     sh = _SHARED
-    if sh is not None and sh["key"] == (xyz.data_ptr(), xyz._version, P):
+    if sh is not None and sh["key"] == _shared_key(xyz, xyz._version, P, aabb, planes):
         return sh
     return None
+
+
+def drop_shared():
+    """Forget the per-step / per-sequence spatial product (called by FusedAdam.step and by the trainer's error path)."""
+    global _SHARED, _INFER
+    _SHARED = None
+    _INFER = None
 
 
 # Opt-in (B200GS_INFERENCE_SPATIAL_CACHE=1 or field.INFERENCE_SPATIAL_CACHE = True; not yet run on a GPU): what
@@ -341,7 +357,7 @@ class _DeformFn(torch.autograd.Function):
         d = _hex_desc(aabb, planes, levels, res)
         order = _cell_order(xyz, aabb)
         ctx.order = order
-        sh = _shared_for(xyz, P)
+        sh = _shared_for(xyz, P, aabb, planes)
         if sh is None:
             sh = _inference_shared(xyz, P, aabb, planes, levels, res, order)
         ctx.shared = sh
@@ -423,7 +439,9 @@ class _DeformFn(torch.autograd.Function):
                 g = gws[i + 4 * h]
                 getattr(mg, name)[h] = g.data_ptr() if (g is not None and heads[h]) else None
         d_feat = torch.empty_like(feat)
-        cp = lambda t: t.contiguous().data_ptr() if t is not None else None
+        # contiguous copies of the upstream gradients stay referenced until the launch has been queued
+        d_pts, d_scales, d_rot = (t.contiguous() if t is not None else None for t in (d_pts, d_scales, d_rot))
+        cp = lambda t: t.data_ptr() if t is not None else None
         check(L.b200gs_deform_mlp_backward(ctypes.byref(mw), ctypes.byref(mg), P, feat.data_ptr(), saved.data_ptr(),
                                            cp(d_pts) if heads[0] else None, cp(d_scales) if heads[1] else None,
                                            cp(d_rot) if heads[2] else None, d_feat.data_ptr(), stream), "deform_mlp_backward")

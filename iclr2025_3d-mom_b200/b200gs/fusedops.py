@@ -47,7 +47,9 @@ class _Activations(torch.autograd.Function):
         ds = torch.empty_like(so) if need[0] else None
         dr = torch.empty_like(r) if need[1] else None
         do = torch.empty_like(oo) if need[2] else None
-        p = lambda t: t.contiguous().data_ptr() if t is not None else None
+        # contiguous copies of the upstream gradients stay referenced until the launch has been queued
+        gs, gr, go = (t.contiguous() if t is not None else None for t in (gs, gr, go))
+        p = lambda t: t.data_ptr() if t is not None else None
         check(_lib.lib().b200gs_activations_backward(P, so.data_ptr(), r.data_ptr(), oo.data_ptr(), p(gs), p(gr), p(go),
                                                      p(ds), p(dr), p(do), current_stream()), "activations_backward")
         return ds, dr, do

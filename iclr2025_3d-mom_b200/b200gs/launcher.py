@@ -33,7 +33,20 @@ def install(reference_root):
     from . import densify
     from .adam import FusedAdam
     from .field import deform_network
-    gm.deform_network = deform_network
+    reference_deform_network = gm.deform_network
+
+    def make_deform_network(args):
+        """scene/gaussian_model.py:53 calls `deform_network(args)`: the fused module for the configurations its kernels cover
+        (the one train_4DGS.py trains with by default: width 64, 32 channels, 2 or 4 levels, no_do / no_dshs), the reference's
+        own PyTorch module -- on top of the same rasterizer / Adam / densify drop-ins -- for everything else
+        (e.g. arguments/dynerf/default.py, arguments/hypernerf/default.py)."""
+        try:
+            return deform_network(args)
+        except NotImplementedError as ex:
+            print(f"[b200gs] {ex}; using the reference's scene.deformation.deform_network for the field", file=sys.stderr)
+            return reference_deform_network(args)
+    if getattr(reference_deform_network, "__name__", "") != "make_deform_network":
+        gm.deform_network = make_deform_network
     densify.patch_gaussian_model(gm.GaussianModel)
     if not getattr(gm.GaussianModel, "_b200gs_patched", False):
         for name in ("training_setup", "training_setup_jih"):

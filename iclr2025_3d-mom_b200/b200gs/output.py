@@ -29,7 +29,10 @@ def to8b(image):
 
 class FrameRing:
     """Pinned-host ring for finished frames. `push(image)` quantises on the current stream and starts an async
-    D2H copy on a side stream; `pop()` returns the oldest frame as a numpy array once its copy has landed."""
+    D2H copy on a side stream; `pop()` returns the oldest frame as a numpy array once its copy has landed.  By default the
+    array is a COPY (safe to append to a list, as render_4DGS.py:60-76 does before `imageio.mimwrite`); `pop(copy=False)`
+    returns a view of the pinned slot, valid only until `depth` more frames have been pushed (for a writer that consumes
+    the frame immediately)."""
 
     def __init__(self, H, W, depth=4, device=None):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -55,10 +58,11 @@ class FrameRing:
         self.head = (self.head + 1) % len(self.host)
         self.count += 1
 
-    def pop(self):
+    def pop(self, copy=True):
         if self.count == 0:
             raise RuntimeError("FrameRing empty")
         slot = (self.head - self.count) % len(self.host)
         self.done[slot].synchronize()
         self.count -= 1
-        return self.host[slot].numpy()
+        frame = self.host[slot].numpy()
+        return frame.copy() if copy else frame

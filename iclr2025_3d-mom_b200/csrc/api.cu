@@ -15,14 +15,11 @@ static thread_local char g_err[512] = "";
 // on a B200 (bit-identical outputs; gradients equal up to float-atomic order); 0 selects the first-generation kernels. The
 // environment (B200GS_MLP_BWD_V2 / B200GS_MLP_FWD_ELECT = integer) overrides the initial value.
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : dflt; }
-static int env_mlp_bwd() { const int v = env_int("B200GS_MLP_BWD_V2", 7); const char* e = getenv("B200GS_PROFILING"); return (v >= 16 && !(e && e[0] == '1')) ? 7 : v; }
-int g_opt_mlp_bwd_v2 = env_mlp_bwd();
+int g_opt_mlp_bwd_v2 = env_int("B200GS_MLP_BWD_V2", 55);
 int g_opt_mlp_fwd_elect = env_int("B200GS_MLP_FWD_ELECT", 2);
-int g_opt_sort_small_tiles = env_int("B200GS_SORT_SMALL_TILES", 0);      // not yet measured: opt-in
-int g_opt_hexplane_time_bwd = env_int("B200GS_HEXPLANE_TIME_BWD", 0);    // not yet measured: opt-in
-int g_opt_lookback_parallel = env_int("B200GS_LOOKBACK_PARALLEL", 0);    // not yet measured: opt-in
-int g_opt_sort_balanced_digits = env_int("B200GS_SORT_BALANCED_DIGITS", 0);    // not yet measured: opt-in
-int g_opt_hexplane_time_fwd = env_int("B200GS_HEXPLANE_TIME_FWD", 0);    // not yet measured: opt-in
+int g_opt_hexplane_time_bwd = env_int("B200GS_HEXPLANE_TIME_BWD", 2);    // 0.417 -> 0.354 ms (profiles/r2a_hexplane_time_check.txt)
+int g_opt_lookback_parallel = env_int("B200GS_LOOKBACK_PARALLEL", 1);    // 111 -> 103 us per 1M-pair sort (profiles/r2a_sort_check.txt)
+int g_opt_hexplane_time_fwd = env_int("B200GS_HEXPLANE_TIME_FWD", 2);    // 0.134 -> 0.112 ms, bit-identical
 int g_opt_mlp_bwd_ablate = 0;                                             // timing experiments only (wrong results); never from the environment
 
 void set_error(const char* fmt, ...)
@@ -111,13 +108,11 @@ int b200gs_version(void) { return 100; }
 int b200gs_set_option(const char* name, int value)
 {
     if (name && !strcmp(name, "mlp_bwd_v2")) {
-        const char* e = getenv("B200GS_PROFILING");          // values >= 16 are unvalidated experiments (deform_mlp_bwd_tc5.cu)
-        if (value >= 16 && !(e && e[0] == '1')) { set_error("b200gs_set_option: mlp_bwd_v2 = %d is experimental and needs B200GS_PROFILING=1 in the environment", value); return -1; }
+        if (value != 0 && value != 1 && value != 3 && value != 5 && value != 7 && value != 55) { set_error("b200gs_set_option: mlp_bwd_v2 = %d is not built (0, 1, 3, 5, 7, 55)", value); return -1; }
         b200gs::g_opt_mlp_bwd_v2 = value;
         return 0;
     }
     if (name && !strcmp(name, "mlp_fwd_elect")) { b200gs::g_opt_mlp_fwd_elect = value; return 0; }
-    if (name && !strcmp(name, "sort_small_tiles")) { b200gs::g_opt_sort_small_tiles = value; return 0; }
     if (name && !strcmp(name, "hexplane_time_bwd")) { b200gs::g_opt_hexplane_time_bwd = value; return 0; }
     if (name && !strcmp(name, "mlp_bwd_ablate")) {          // wrong results by design: only for a process that says it is profiling
         const char* e = getenv("B200GS_PROFILING");
@@ -126,7 +121,6 @@ int b200gs_set_option(const char* name, int value)
         return 0;
     }
     if (name && !strcmp(name, "lookback_parallel")) { b200gs::g_opt_lookback_parallel = value; return 0; }
-    if (name && !strcmp(name, "sort_balanced_digits")) { b200gs::g_opt_sort_balanced_digits = value; return 0; }
     if (name && !strcmp(name, "hexplane_time_fwd")) { b200gs::g_opt_hexplane_time_fwd = value; return 0; }
     set_error("b200gs_set_option: unknown option '%s'", name ? name : "(null)");
     return -1;
@@ -135,11 +129,9 @@ int b200gs_get_option(const char* name)
 {
     if (name && !strcmp(name, "mlp_bwd_v2")) return b200gs::g_opt_mlp_bwd_v2;
     if (name && !strcmp(name, "mlp_fwd_elect")) return b200gs::g_opt_mlp_fwd_elect;
-    if (name && !strcmp(name, "sort_small_tiles")) return b200gs::g_opt_sort_small_tiles;
     if (name && !strcmp(name, "hexplane_time_bwd")) return b200gs::g_opt_hexplane_time_bwd;
     if (name && !strcmp(name, "mlp_bwd_ablate")) return b200gs::g_opt_mlp_bwd_ablate;
     if (name && !strcmp(name, "lookback_parallel")) return b200gs::g_opt_lookback_parallel;
-    if (name && !strcmp(name, "sort_balanced_digits")) return b200gs::g_opt_sort_balanced_digits;
     if (name && !strcmp(name, "hexplane_time_fwd")) return b200gs::g_opt_hexplane_time_fwd;
     return -1;
 }

@@ -66,7 +66,7 @@ __device__ __forceinline__ float4 lds128(u32 addr)
     return v;
 }
 
-// V2 (experimental, off by default: b200gs_set_option("mlp_bwd_v2", 1) or B200GS_MLP_BWD_V2=1; same arithmetic, same operands, same TMEM map):
+// V2 (same arithmetic, same operands, same TMEM map as the first generation):
 //   * the two 32 KB weight slots alternate between consecutive MMA groups and the image of the NEXT group is streamed in
 //     (cp.async) while the current phase computes, so no phase waits for its weights (W1 is re-streamed per tile from L2);
 //   * MMAs are issued from a warp-uniform branch by the elected lane of warp 0 with the shared-memory descriptors formed by
@@ -74,14 +74,12 @@ __device__ __forceinline__ float4 lds128(u32 addr)
 //     thread sits on the critical path of every phase);
 //   * the TMEM-resident weight gradients leave through a padded shared-memory transpose as hi + lo sums, one coalesced
 //     128-bit RED per 4 elements (8x fewer atomics than one scalar atomic per hi / lo element, whole lines per warp).
-// VER: 0 = default; otherwise bit 0 = V2, bits 1-2 = how the upstream gradients d_out reach a phase (0: loaded at its start,
-// 1: loaded into registers one phase ahead, 2 / 3: prefetched into L1 / L2 one phase ahead), bit 3 = the previous tile's
-// d_feature rows leave TMEM in four 8-column parts, one per MMA drain, instead of one 32 KB burst at the tile boundary;
-// bit 4 (EXPERIMENTAL, unvalidated: see tools/probe/umma_probe2.cu) = the dX chain reads its A operand dY from the MN-major
-// SWIZZLE_128B_BASE32B image of the weight-gradient MMAs, re-described as a K-major operand (rows = points, 128-byte rows of 32
-// out-features, 8-row group stride BwdArgs::dy_sbo), so dY is stored to shared memory twice (hi, lo) instead of four times;
-// bit 5 (EXPERIMENTAL, needs bit 4) = the K-major dY image is gone, so all four weight image pairs (128 KB) stay resident and
-// nothing is streamed per phase; the D_RH bounce borrows the idle dY image.
+// VER: 0 = first generation; otherwise bit 0 = V2, bits 1-2 = how the upstream gradients d_out reach a phase (0: loaded at its
+// start, 1: loaded into registers one phase ahead, 2 / 3: prefetched into L1 / L2 one phase ahead); bit 4 = SINGLE_DY: the dX
+// chain reads its A operand dY from the MN-major SWIZZLE_128B_BASE32B image of the weight-gradient MMAs, re-described as a
+// K-major operand (rows = points, 128-byte rows of 32 out-features, 8-row group stride BwdArgs::dy_sbo = 512 B -- the one
+// combination that reproduces the product exactly on hardware, tools/probe/umma_probe2.cu), so dY is stored to shared
+// memory twice (hi, lo) instead of four times: 0.744 -> 0.686 ms per 1M points (profiles/r2a_mlp_variant_check.txt).
 // ABL (timing experiments only, WRONG RESULTS, option "mlp_bwd_ablate"): what the kernel costs without one of its parts --
 // 1: d_out read from constants instead of global memory, 2: no operand stores to shared memory, 4: no MMAs (and no waits for
 // them), 8: no gradient math (dz / dW3 / bias sums), 16: no d_feature stores, 32: stash / feature rows from constants.
@@ -90,16 +88,15 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
 {
     constexpr bool A_NODIN = (ABL & 1) != 0, A_NOSTS = (ABL & 2) != 0, A_NOMMA = (ABL & 4) != 0, A_NOMATH = (ABL & 8) != 0,
                    A_NODFEAT = (ABL & 16) != 0, A_NOLOAD = (ABL & 32) != 0;
-    constexpr bool V2 = (VER & 1) != 0, DIN_AHEAD = ((VER >> 1) & 3) == 1, DIN_PREFETCH = ((VER >> 1) & 3) >= 2, SPLIT_FE = ((VER >> 3) & 1) != 0, SINGLE_DY = ((VER >> 4) & 1) != 0, RESIDENT_W = ((VER >> 5) & 1) != 0;
-    static_assert(!RESIDENT_W || (SINGLE_DY && V2), "resident weights need the single dY image");
+    constexpr bool V2 = (VER & 1) != 0, DIN_AHEAD = ((VER >> 1) & 3) == 1, DIN_PREFETCH = ((VER >> 1) & 3) >= 2, SINGLE_DY = ((VER >> 4) & 1) != 0;
+    static_assert(!SINGLE_DY || V2, "the single dY image is built on the V2 kernel");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* W2B = reinterpret_cast<float*>(smem_raw);                 // current head: hi [16 k-chunks][64 n][4] | lo  (32 KB)
     float* W1B = W2B + 2 * MW * MW;                                  // hi | lo                                      (32 KB)
-    // RESIDENT_W: [8 images: W2_0 hi | lo, W2_1 ..., W1 hi | lo] 128 KB | DYM | XH | barrier; the bounce scratch aliases DYM
-    unsigned char* DYM = smem_raw + (RESIDENT_W ? 8 : 4) * MW * MW * 4;   // 64 KB, MN-major swizzled  [out: 64 hi rows | 64 lo rows][p 128]
+    unsigned char* DYM = smem_raw + 4 * MW * MW * 4;        // 64 KB, MN-major swizzled  [out: 64 hi rows | 64 lo rows][p 128]
     unsigned char* XH = DYM + 65536;                                 // 32 KB, MN-major swizzled  [in 64][p 128]
-    unsigned char* DYK = RESIDENT_W ? DYM : XH + 32768;              // 2 planes x 16 chunks x 2064 B, K-major  [p 128][out 64]
-    u64* bar = reinterpret_cast<u64*>(RESIDENT_W ? XH + 32768 : DYK + 2 * KPLANE);
+    unsigned char* DYK = XH + 32768;              // 2 planes x 16 chunks x 2064 B, K-major  [p 128][out 64]
+    u64* bar = reinterpret_cast<u64*>(DYK + 2 * KPLANE);
     u32* tmem_slot = reinterpret_cast<u32*>(bar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // SIMT mapping: columns 32 c + 4 q + e, points 32 pg + 4 i + sub (i = 0..7)
@@ -121,13 +118,6 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
     };
     if constexpr (!V2) {
         copy_image_pair(W1B, 3);
-        cp_async_wait<0>();
-    }
-    if constexpr (RESIDENT_W) {                                       // all eight images in the forward's order, once
-        const float4* src = reinterpret_cast<const float4*>(images);
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) cp_async16(reinterpret_cast<float4*>(W2B) + tid + BT * i, src + tid + BT * i);
-        cp_async_commit();
         cp_async_wait<0>();
     }
     for (int i = tid; i < 98304 / 16; i += BT) reinterpret_cast<float4*>(DYM)[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // DYM + XH
@@ -201,42 +191,22 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
 #pragma unroll
     for (int e = 0; e < 4; ++e) gB1[e] = 0.f;
 
-    int fe_part = 0;                 // SPLIT_FE: 8-column parts of the previous tile's d_feature rows already stored
-    auto drain = [&](bool all = true) {   // wait for the committed MMA group; then D_FE of the previous tile can be stored
+    auto drain = [&](bool = true) {   // wait for the committed MMA group; then D_FE of the previous tile can be stored
         if (pending) {
             mbar_wait(bar, phase); phase ^= 1; pending = false;
             tc_fence_after();
         }
         if (prev_row >= 0) {
-            if constexpr (SPLIT_FE) {
-                // D_FE stays valid until this tile's feature-phase MMAs, so its rows can leave a quarter at a time
-                // (`all`: everything that is left -- the feature phase and the end of the kernel)
-                do {
-                    u32 v[8];
-                    tmem_ld8(lane_addr + C_FE + 32 * cT + 8 * fe_part, v);
-                    tmem_wait_ld();
-                    if (!A_NODFEAT && prev_row < a.P) {
+            u32 v[32];
+            tmem_ld32(lane_addr + C_FE + 32 * cT, v);
+            tmem_wait_ld();
+            if (!A_NODFEAT && prev_row < a.P) {
 #pragma unroll
-                        for (int j = 0; j < 2; ++j)
-                            *reinterpret_cast<float4*>(a.d_feat + (a.w.feat_tiled ? stash_off(prev_row, 32 * cT) + 16 * (2 * fe_part + j)
-                                                                                  : (size_t)prev_row * MW + 32 * cT + 4 * (2 * fe_part + j))) =
-                                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                    }
-                    ++fe_part;
-                } while (all && fe_part < 4);
-                if (fe_part == 4) { prev_row = -1; fe_part = 0; }
-            } else {
-                u32 v[32];
-                tmem_ld32(lane_addr + C_FE + 32 * cT, v);
-                tmem_wait_ld();
-                if (!A_NODFEAT && prev_row < a.P) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<float4*>(a.d_feat + (a.w.feat_tiled ? stash_off(prev_row, 32 * cT) + 16 * j : (size_t)prev_row * MW + 32 * cT + 4 * j)) =
-                            make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                }
-                prev_row = -1;
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(a.d_feat + (a.w.feat_tiled ? stash_off(prev_row, 32 * cT) + 16 * j : (size_t)prev_row * MW + 32 * cT + 4 * j)) =
+                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
             }
+            prev_row = -1;
         }
     };
 
@@ -293,7 +263,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
         load_stash(hrow, 0, (long long)blockIdx.x * ROWS + p0);
         load_phase_rows(next_phase(-1), xin, (long long)blockIdx.x * ROWS + p0);
     }
-    if constexpr (V2 && !RESIDENT_W) copy_image_pair(W2B, next_phase(-1));            // group 0's weights -> slot 0 (waited for before its MMAs)
+    if constexpr (V2) copy_image_pair(W2B, next_phase(-1));            // group 0's weights -> slot 0 (waited for before its MMAs)
     float din_next[8][4];
     if constexpr (DIN_AHEAD) load_phase_dout(next_phase(-1), din_next, (long long)blockIdx.x * ROWS + p0);
     for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
@@ -350,7 +320,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
             if constexpr (DIN_PREFETCH) prefetch_phase_dout(next_phase(h), blk);
             drain(false);            // the previous MMA group still reads DYK / DYM / XH and the W2 slot
             if constexpr (!V2) copy_image_pair(W2B, h);
-            else if constexpr (!RESIDENT_W) copy_image_pair((ngroup & 1u) ? W2B : W1B, next_phase(h));   // the NEXT group's image -> the slot the drained group used
+            else copy_image_pair((ngroup & 1u) ? W2B : W1B, next_phase(h));   // the NEXT group's image -> the slot the drained group used
             if (!h_staged) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) if (!A_NOSTS || i == 0) sts128(sXH + mn_off + (u32)(p0 + 4 * i) * 128u, tf32x4(hrow[i]));
@@ -369,12 +339,12 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
                 sts128(sDYM + mn_off + pp * 128u, hi);
                 sts128(sDYM + 32768u + mn_off + pp * 128u, lo);
             }
-            if constexpr (V2 && !RESIDENT_W) cp_async_wait<1>(); else if constexpr (!V2) cp_async_wait<0>();      // V2: all but the next group's image
+            if constexpr (V2) cp_async_wait<1>(); else cp_async_wait<0>();      // V2: all but the next group's image
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_before();
             __syncthreads();
             if constexpr (V2) {
-                issue_group(RESIDENT_W ? sW2 + (u32)h * 32768u : ((ngroup & 1u) ? sW1 : sW2), C_RH, rh_started, C_W2 + 64 * h);
+                issue_group((ngroup & 1u) ? sW1 : sW2, C_RH, rh_started, C_W2 + 64 * h);
                 ++ngroup;
             } else if (tid == 0) {
                 tc_fence_after();
@@ -406,7 +376,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
             if constexpr (DIN_PREFETCH) prefetch_phase_dout(next_phase(-1), blk + gridDim.x);
         }
         drain();
-        if constexpr (V2 && !RESIDENT_W) {          // the next tile's first image -> the slot the drained group used (an empty group keeps the count)
+        if constexpr (V2) {          // the next tile's first image -> the slot the drained group used (an empty group keeps the count)
             if (blk + gridDim.x < nblocks) copy_image_pair((ngroup & 1u) ? W2B : W1B, next_phase(-1));
             else cp_async_commit();
         }
@@ -426,16 +396,10 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
         }
         tc_fence_before();
         __syncthreads();
-        float4 rh[RESIDENT_W ? 8 : 1];
-        if constexpr (RESIDENT_W) {          // the scratch is the dY image itself: everybody reads before anybody writes dh into it
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rh[i] = lds128(sDYK + k_off + (u32)(p0 + 4 * i) * 16u);
-            __syncthreads();
-        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const u32 pp = (u32)(p0 + 4 * i);
-            const float4 r4 = RESIDENT_W ? rh[RESIDENT_W ? i : 0] : lds128(sDYK + k_off + pp * 16u);
+            const float4 r4 = lds128(sDYK + k_off + pp * 16u);
             float x[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -453,12 +417,12 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
             sts128(sDYM + 32768u + mn_off + pp * 128u, lo);
             sts128(sXH + mn_off + pp * 128u, tf32x4(frow[i]));
         }
-        if constexpr (V2 && !RESIDENT_W) cp_async_wait<1>();
+        if constexpr (V2) cp_async_wait<1>();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncthreads();
         if constexpr (V2) {
-            issue_group(RESIDENT_W ? sW2 + 3u * 32768u : ((ngroup & 1u) ? sW1 : sW2), C_FE, false, C_W1);
+            issue_group((ngroup & 1u) ? sW1 : sW2, C_FE, false, C_W1);
             ++ngroup;
         } else if (tid == 0) {
             tc_fence_after();
@@ -563,17 +527,13 @@ size_t bwd_smem() { return (size_t)(2 * MW * MW + 2 * MW * MW) * 4 + 98304 + 2 *
 
 }  // namespace tc5
 
-int deform_mlp_backward_tc5_db(const b200gs_mlp_weights* w, const b200gs_mlp_grads* gw, long long P, const float* feat,
-                               const float* saved, const float* d_pts, const float* d_scales, const float* d_rot,
-                               float* d_feat, unsigned dy_sbo, cudaStream_t stream);      // deform_mlp_bwd_tc5_db.cu
-
 int deform_mlp_backward_tc5(const b200gs_mlp_weights* w, const b200gs_mlp_grads* gw, long long P, const float* feat,
                             const float* saved, const float* d_pts, const float* d_scales, const float* d_rot,
                             float* d_feat, cudaStream_t stream)
 {
     tc5::BwdArgs a;
     a.w = *w; a.gw = *gw; a.P = P; a.feat = feat; a.saved = saved; a.d_pts = d_pts; a.d_scales = d_scales; a.d_rot = d_rot;
-    a.d_feat = d_feat; a.dy_sbo = 1024u;
+    a.d_feat = d_feat; a.dy_sbo = 512u;
     const long long nblocks = (P + tc5::ROWS - 1) / tc5::ROWS;
     const int grid = (int)(nblocks < NUM_SMS ? nblocks : NUM_SMS);
     const size_t smem = tc5::bwd_smem();
@@ -581,8 +541,6 @@ int deform_mlp_backward_tc5(const b200gs_mlp_weights* w, const b200gs_mlp_grads*
     // aligned W1 / W2 gradient rows for its 128-bit REDs
     bool v2 = g_opt_mlp_bwd_v2 != 0 && ((uintptr_t)gw->w1 & 15) == 0;
     for (int h = 0; h < 3; ++h) v2 = v2 && (!w->w2[h] || ((uintptr_t)gw->w2[h] & 15) == 0);
-    if (v2 && (g_opt_mlp_bwd_v2 == 151 || g_opt_mlp_bwd_v2 == 183))      // EXPERIMENTAL: one dY image per group, double buffered
-        return deform_mlp_backward_tc5_db(w, gw, P, feat, saved, d_pts, d_scales, d_rot, d_feat, g_opt_mlp_bwd_v2 == 183 ? 512u : 1024u, stream);
     if (v2 && g_opt_mlp_bwd_ablate != 0) {           // timing experiments, wrong results (see the kernel's ABL comment)
         void (*kern)(tc5::BwdArgs) = nullptr;
         switch (g_opt_mlp_bwd_ablate) {
@@ -605,13 +563,12 @@ int deform_mlp_backward_tc5(const b200gs_mlp_weights* w, const b200gs_mlp_grads*
             case 3: kern = tc5::deform_mlp_bwd_tc5_kernel<3>; break;
             case 5: kern = tc5::deform_mlp_bwd_tc5_kernel<5>; break;
             case 7: kern = tc5::deform_mlp_bwd_tc5_kernel<7>; break;
-            case 9: kern = tc5::deform_mlp_bwd_tc5_kernel<9>; break;
-            case 13: kern = tc5::deform_mlp_bwd_tc5_kernel<13>; break;
-            case 15: kern = tc5::deform_mlp_bwd_tc5_kernel<15>; break;
-            // EXPERIMENTAL (option bit 5 = 512-byte group stride instead of 1024, option bit 6 = resident weights)
-            case 23: case 55: kern = tc5::deform_mlp_bwd_tc5_kernel<23>; a.dy_sbo = g_opt_mlp_bwd_v2 == 55 ? 512u : 1024u; break;
-            case 87: case 119: kern = tc5::deform_mlp_bwd_tc5_kernel<55>; a.dy_sbo = g_opt_mlp_bwd_v2 == 119 ? 512u : 1024u; break;
-            default: break;
+            // 55 (default): ONE dY image -- the dX chain reads the MN-major SWIZZLE_128B_BASE32B image of the weight-gradient
+            // MMAs re-described as a K-major operand with a 512-byte 8-row group stride (exact on hardware: tools/probe/umma_probe2.cu,
+            // profiles/r2a_umma_probe2.txt; the 1024-byte stride is NOT and was removed)
+            case 55: kern = tc5::deform_mlp_bwd_tc5_kernel<23>; break;
+            default: set_error("deform_mlp_backward: mlp_bwd_v2 = %d is not built (0, 1, 3, 5, 7, 55)", g_opt_mlp_bwd_v2); return -1;
+            case 1: break;
         }
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<grid, tc5::BT, smem, stream>>>(a);

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) rs_scan_hist(u32* __restrict__ g_hist)
     h[threadIdx.x] = block_exclusive_scan_256(v, s_warp);
 }
 
-// LB_BATCH (opt-in "lookback_parallel"): the decoupled look-back of a digit walks its predecessors' states LB_BATCH at a
+// LB_BATCH (option "lookback_parallel", default on: 111 -> 103 us per 1M-pair 32-bit sort): the decoupled look-back of a digit walks its predecessors' states LB_BATCH at a
 // time (independent volatile loads in flight together) instead of one dependent L2 round trip per predecessor -- with a
 // few hundred tiles resident at once the serial walk is what a pass on ~1M keys spends its time in.  Same sums, same result.
 template <bool HAS_VALS, int IPT, int LB_BATCH>
@@ -179,16 +179,12 @@ int radix_sort_pairs(u32* keys_a, u32* vals_a, u32* keys_b, u32* vals_b, size_t 
     u32* g_hist = (u32*)temp;
     u32* tickets = g_hist + (size_t)plan.passes * RS_RADIX;
     u32* lookback = tickets + 256;
-    const bool small = g_opt_sort_small_tiles != 0 && n <= RS_SMALL_MAX_N;
-    const size_t tiles = small ? (n + RS_TILE_SMALL - 1) / RS_TILE_SMALL : plan.tiles;
+    const size_t tiles = plan.tiles;
     // clear what this call uses: digit bases, tickets, look-back state of `tiles` tiles per pass
     cudaMemsetAsync(temp, 0, ((size_t)plan.passes * RS_RADIX + 256 + (size_t)plan.passes * tiles * RS_RADIX) * sizeof(u32), stream);
 
     DigitSpec spec;
-    // digit width: 8 bits per pass, or (opt-in "sort_balanced_digits") the key bits spread evenly over the passes -- the 12..15
-    // tile-id bits sort in two passes either way, but 6 + 6 bits scatter a 4096-key tile into 64 runs of 256 B per pass instead
-    // of 256 runs of 64 B in the first and 16 in the second.  Any digit split gives the same (stable) result.
-    const int per = g_opt_sort_balanced_digits != 0 ? (end_bit - begin_bit + plan.passes - 1) / plan.passes : RS_RADIX_BITS;
+    const int per = RS_RADIX_BITS;       // (an even 6 + 6 split of the tile-id bits was measured: no gain, profiles/r2a_sort_check.txt)
     for (int p = 0; p < RS_MAX_PASSES; ++p) {
         int lo = begin_bit + p * per;
         int nb = end_bit - lo; if (nb > per) nb = per; if (nb < 1) nb = 1;
@@ -206,12 +202,8 @@ int radix_sort_pairs(u32* keys_a, u32* vals_a, u32* keys_b, u32* vals_b, size_t 
 #define RS_LAUNCH(HV, IPTV, LBV) rs_onesweep_pass<HV, IPTV, LBV><<<(unsigned)tiles, RS_THREADS, 0, stream>>>( \
             kin, HV ? vin : nullptr, kout, HV ? vout : nullptr, (u32)n, spec.shift[p], spec.mask[p], g_hist + p * RS_RADIX, lb, tickets + p)
         const bool hv = vals_a != nullptr, par = g_opt_lookback_parallel != 0;
-        if (hv && small && par) RS_LAUNCH(true, RS_IPT_SMALL, 8);
-        else if (hv && small) RS_LAUNCH(true, RS_IPT_SMALL, 1);
-        else if (hv && par) RS_LAUNCH(true, RS_IPT, 8);
+        if (hv && par) RS_LAUNCH(true, RS_IPT, 8);
         else if (hv) RS_LAUNCH(true, RS_IPT, 1);
-        else if (small && par) RS_LAUNCH(false, RS_IPT_SMALL, 8);
-        else if (small) RS_LAUNCH(false, RS_IPT_SMALL, 1);
         else if (par) RS_LAUNCH(false, RS_IPT, 8);
         else RS_LAUNCH(false, RS_IPT, 1);
 #undef RS_LAUNCH

@@ -19,9 +19,6 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_IPT = 16;                        // keys per thread
 constexpr int RS_TILE = RS_THREADS * RS_IPT;      // 4096 keys per tile
-constexpr int RS_IPT_SMALL = 8;                   // opt-in ("sort_small_tiles"): 2048-key tiles for inputs of a few million keys,
-constexpr int RS_TILE_SMALL = RS_THREADS * RS_IPT_SMALL;   // where a pass is bound by the serial work per tile, not by bandwidth
-constexpr size_t RS_SMALL_MAX_N = 4u << 20;
 constexpr int RS_MAX_PASSES = 4;
 
 struct RadixPlan {
@@ -37,11 +34,8 @@ inline RadixPlan radix_plan(size_t n, int begin_bit, int end_bit) {
     if (p.passes < 1) p.passes = 1;
     p.tiles = (n + RS_TILE - 1) / RS_TILE;
     if (p.tiles == 0) p.tiles = 1;
-    // [passes][256] global digit bases, [passes] tickets (padded to 256 u32), [passes][tiles][256] look-back -- sized for the
-    // small-tile variant (twice the tiles) so that the choice can be made per call
-    size_t lb_tiles = (n + RS_TILE_SMALL - 1) / RS_TILE_SMALL;
-    if (lb_tiles == 0) lb_tiles = 1;
-    p.temp_bytes = align_up(((size_t)p.passes * RS_RADIX + 256 + (size_t)p.passes * lb_tiles * RS_RADIX) * sizeof(u32), 256);
+    // [passes][256] global digit bases, [passes] tickets (padded to 256 u32), [passes][tiles][256] look-back
+    p.temp_bytes = align_up(((size_t)p.passes * RS_RADIX + 256 + (size_t)p.passes * p.tiles * RS_RADIX) * sizeof(u32), 256);
     return p;
 }
 

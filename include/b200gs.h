@@ -32,22 +32,21 @@ int b200gs_version(void);
 /* Kernel variants, process-wide. The defaults are the fastest variants that have passed tools/native/mlp_variant_check.cu on
  * a B200 (bit-identical outputs, gradients equal up to float-atomic order); 0 selects the first-generation kernel, the
  * environment variable B200GS_<NAME>=<integer> overrides the initial value:
- *   "mlp_bwd_v2"     deformation-MLP backward (default 7): bit 0 = alternating weight slots + elected MMA issuer + coalesced
- *                    gradient flush; bits 1-2 = how d_out reaches a phase (3 = prefetched into L2 one phase ahead); bit 3 =
- *                    d_features leave TMEM in four parts; values >= 16 (23 / 55 / 87 / 119 / 151 / 183) are UNVALIDATED experiments, refused unless B200GS_PROFILING=1 (deform_mlp_bwd_tc5.cu)
+ *   "mlp_bwd_v2"     deformation-MLP backward (default 55): bit 0 = alternating weight slots + elected MMA issuer + coalesced
+ *                    gradient flush; bits 1-2 = how d_out reaches a phase (3 = prefetched into L2 one phase ahead); 55 = 7 +
+ *                    ONE dY image in shared memory, read K-major by the dX chain and MN-major by the weight-gradient MMAs
+ *                    (deform_mlp_bwd_tc5.cu).  Built values: 0, 1, 3, 5, 7, 55; anything else is refused
  *   "mlp_fwd_elect"  deformation-MLP forward (default 2): 1 = elected MMA issuer, 2 = plus activation-stash stores deferred
  *                    past the next layer's MMA issue (deform_mlp_tc5.cu)
- *   "sort_small_tiles" radix sort (default 0, not yet measured): 2048-key tiles instead of 4096 for inputs up to 4M keys
- *                    (the depth sort of ~1M Gaussians is bound by the serial work per tile); the result is identical
- *   "hexplane_time_fwd" time-row HexPlane forward (default 0, not yet measured): 1 / 2 = both levels' factor rows requested up front,
- *                    register budget for 3 / 2 resident CTAs per SM
- *   "hexplane_time_bwd" time-row HexPlane backward (default 0, not yet measured): 1 / 2 = both levels' rows requested before the
+ *   "hexplane_time_fwd" time-row HexPlane forward (default 2): 1 / 2 = both levels' factor rows requested up front,
+ *                    register budget for 3 / 2 resident CTAs per SM; bit-identical outputs
+ *   "hexplane_time_bwd" time-row HexPlane backward (default 2): 1 / 2 = both levels' rows requested before the
  *                    first is used, register budget for 3 / 2 resident CTAs per SM (hexplane.cu: hexplane_time_bwd2_kernel)
- *   "lookback_parallel" chained scans of the radix sort passes and of the instance emission (default 0, not yet measured):
+ *   "lookback_parallel" chained scans of the radix sort passes and of the instance emission (default 1):
  *                    predecessors' states are read 8 (per digit) / 32 (per warp) at a time instead of one dependent L2 round
  *                    trip each; identical results
- *   "sort_balanced_digits" radix sort (default 0, not yet measured): key bits spread evenly over the passes (6 + 6 for 12 tile-id
- *                    bits) instead of 8 bits per pass; identical results
+ * Measured on a B200 in round 2 (profiles/r2a_*.txt); the variants that lost ("sort_small_tiles", "sort_balanced_digits", the
+ * resident-weight and double-buffered MLP backward kernels) were deleted.
  * Same arithmetic in every variant.  ("mlp_bwd_ablate" is a profiling aid, not a variant: it removes one part of the MLP
  * backward kernel -- WRONG RESULTS -- so that tools/native/mlp_variant_check can time what that part costs; it is refused
  * unless the environment has B200GS_PROFILING=1.)  set: 0 on success, non-zero for an unknown name; get: the value, or -1 for an unknown name. */

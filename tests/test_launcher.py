@@ -48,8 +48,7 @@ def test_launcher_patches_reference_gaussian_model():
     try:
         from b200gs import launcher
         gm = launcher.install(REF)
-        from b200gs.field import deform_network
-        assert gm.deform_network is deform_network
+        assert gm.deform_network.__name__ == "make_deform_network"
         import diff_gaussian_rasterization
         assert "b200gs" in diff_gaussian_rasterization.GaussianRasterizer.__module__
         hyper = types.SimpleNamespace(
@@ -59,6 +58,13 @@ def test_launcher_patches_reference_gaussian_model():
             kplanes_config={'grid_dimensions': 2, 'input_coordinate_dim': 4, 'output_coordinate_dim': 32, 'resolution': [8, 8, 8, 5]})
         model = gm.GaussianModel(3, hyper)                       # the reference's own constructor (gaussian_model.py:48-70)
         assert type(model._deformation).__module__ == "b200gs.field"
+        # a configuration outside the fused kernels (arguments/dynerf/default.py: width 128, 16 channels, no_do=False) falls
+        # back to the reference's own field module instead of crashing at construction
+        import copy
+        wide = copy.deepcopy(hyper); wide.net_width = 128; wide.no_do = False
+        wide.kplanes_config = dict(hyper.kplanes_config, output_coordinate_dim=16)
+        model_wide = gm.GaussianModel(3, wide)
+        assert type(model_wide._deformation).__module__ == "scene.deformation"
         assert gm.GaussianModel._prune_optimizer.__name__ == "<lambda>" and gm.GaussianModel._b200gs_patched
         # the reference's render() imports cleanly on top of the drop-ins
         import gaussian_renderer
