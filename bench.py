@@ -1,23 +1,28 @@
 #!/usr/bin/env python
-"""Headline benchmark: 4DGS training throughput, 1M Gaussians, 1280x720 (BASELINE.json C3).
+"""Headline benchmark: 4DGS training throughput, 1M Gaussians, 1280x720, a batch of 8 views per optimiser step
+(BASELINE.json C3: "8 views over N x B200").
 
     python bench.py --gpus N --steps K --warmup W              # this repo (sm_100a kernels via the C ABI)
     python bench.py --impl reference --gpus N --steps K ...    # the reference's own code path
 
-One step = one fine-stage training iteration over this rank's batch of views
-(train_4DGS.py:172-297): per view HexPlane deformation -> exp/normalize/sigmoid -> rasterize ->
-L1 -> backward through all of it; then (N > 1) ONE flat NCCL all-reduce of the gradients and one
-fused Adam step over every parameter.  Views are sharded over ranks (weak scaling: the per-GPU
-batch is fixed), `value` = view-iterations per second summed over all ranks, timed on the device
-with CUDA events between barriers, max over ranks.  `e2e` repeats the measurement through the same
-public API with the per-view ground-truth images living in pinned HOST memory (copied inside the
-timed region, as train_4DGS.py:194 does) and the loss read back to the host every step.
+One step = one fine-stage training iteration over the GLOBAL batch of 8 views (train_4DGS.py:172-297): per view HexPlane
+deformation -> exp/normalize/sigmoid -> rasterize -> L1 -> backward through all of it; then the gradient exchange
+(N > 1: NCCL all-reduce of the SH gradient on a side stream + of the flat arena), the plane regulariser and one fused Adam
+step over every parameter.  The 8 views are sharded over the ranks (8 / 4 / 2 / 1 views per GPU): STRONG scaling, the
+configuration BASELINE.json names.  `value` = view-iterations per second of the whole job, timed on the device with CUDA events
+between barriers, max over ranks.  For N > 1 a second block (`weak`) repeats the measurement with 8 views PER GPU.
+`e2e` repeats the measurement through the same public API with the ground-truth images in pinned HOST memory as the dataset
+holds them (uint8 HWC), uploaded inside the timed region every step (prefetched on a side stream), and the loss read back to
+the host every step (asynchronously, through a pinned ring).
 
-The reference arm runs the reference's own CUDA rasterizer (oracle/_ref/libref_rast.so, built
-unmodified from /root/reference by oracle/build_ref.sh), a plain-PyTorch port of its HexPlane /
-deformation modules (oracle/field_torch.py, pinned bit-exact against the real modules) and
-torch.optim.Adam, on the same GPU, same scene, same loop.  `cpu_baseline` is the CPU port
-(oracle/raster_cpu.c + the torch field on CPU tensors) timed on the host cores for ONE view.
+Side blocks in the same JSON line: `render` (BASELINE config 4: five 60-frame camera paths at 1920x1080 and 1280x720, frames
+sharded over ranks), `raster_only` (config 2: rasterizer fwd+bwd alone at 200k / 512^2 and 1M / 720p), `kernels` (live
+per-kernel durations and roofline fractions), `timeline` (where a step's time goes, CUDA events), `cpu_baseline`
+(config 1 + a CPU port of one view-iteration, timed on the host cores after the timed region).
+
+The reference arm runs the reference's own CUDA rasterizer (oracle/_ref/libref_rast.so, built unmodified from
+/root/reference by oracle/build_ref.sh), a plain-PyTorch port of its HexPlane / deformation modules (oracle/field_torch.py,
+pinned bit-exact against the real modules) and torch.optim.Adam, on the same GPU, same scene, same loop.
 """
 import argparse
 import json
@@ -43,12 +48,15 @@ def parse():
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--width", type=int, default=1280)
     ap.add_argument("--height", type=int, default=720)
-    ap.add_argument("--views-per-gpu", type=int, default=8)
+    ap.add_argument("--global-batch", type=int, default=8, help="views per optimiser step over ALL GPUs (BASELINE config 3: 8)")
+    ap.add_argument("--views-per-gpu", type=int, default=8, help="per-GPU batch of the weak-scaling block (N > 1)")
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling block at N > 1")
     ap.add_argument("--scale-mu", type=float, default=0.010, help="S-coarse 0.010 / S-fine 0.004 (SURVEY.md 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--render-frames", type=int, default=30, help="frames per GPU for the render-FPS side measurement (0 = skip)")
+    ap.add_argument("--render-frames", type=int, default=60, help="frames per camera path of the render block (0 = skip)")
+    ap.add_argument("--no-raster-only", action="store_true", help="skip the config-2 rasterizer-only block")
     ap.add_argument("--no-shared-spatial", action="store_true",
-                    help="render every frame with the full six-plane HexPlane pass instead of sharing the spatial product over the sequence")
+                    help="render every frame with the full six-plane HexPlane pass instead of sharing the spatial product over a sequence")
     ap.add_argument("--cpu-points", type=int, default=0, help="override the cpu_baseline sample size")
     return ap.parse_args()
 
@@ -96,20 +104,6 @@ class ClockSampler:
                 "samples": len(self.rows), "reasons": sorted(reasons)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {"hexplane_bwd_kernel": 348.4e6, "deform_mlp_bwd_tc5_kernel": 1561.1e6, "deform_mlp_fwd_tc5v2_kernel": 1317.6e6,
-               "hexplane_time_fwd_kernel": 485.5e6, "hexplane_time_bwd_kernel": 1037.8e6}
-ROOFLINE_NOTES = {
-    "deform_mlp_bwd_tc5_kernel": "HBM is the binding roofline (1.58 KB/point: 1 KB activation stash + features + d_features; the tensor pipe is 15 % "
-                                 "busy), but the kernel is SIMT / shared-memory-port bound today: per phase the gradient math runs at 0.4 IPC per scheduler (two warps each) "
-                                 "and 164 KB of operand stores go through the 128 B/clk shared-memory port (DESIGN.md section 7); traffic = ncu dram bytes of the first-generation kernel",
-    "deform_mlp_fwd_tc5v2_kernel": "HBM is the binding roofline (1.37 KB/point, 1 KB of it the activation stash); tensor pipe 26 % busy",
-    "hexplane_bwd_kernel": "average over the step's V time-plane passes and its one spatial pass; algorithmic HBM bytes only (xyz, order, "
-                           "d_feature, shared spatial product in; d_xyz, its gradient accumulator, plane gradients out); the 3 KB/point/pass of "
-                           "plane texel gathers + vector REDs are served by L1/L2 (planes are 11.6 MB), which is what bounds this kernel; "
-                           "traffic = ncu dram bytes of the full six-plane launch",
-    "hexplane_fwd_kernel": "plane texel gathers (6.1 KB/point) are L1/L2 traffic, not HBM",
-}
 
 
 def peaks():
@@ -119,19 +113,36 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, keyed by kernel name, from the committed summary of the
+    `ncu --set full` capture of THIS tree's default kernels (profiles/ncu_dram_bytes.json, written by tools/ncu_summary.py);
+    {} when there is none -- `roofline.traffic` is then null rather than a stale constant."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_dram_bytes.json")))
+        return {k: v for k, v in d.get("kernels", {}).items()}, d.get("source")
+    except Exception:
+        return {}, None
+
+
 # ---------------------------------------------------------------------------------------------
+def scene_images_u8(args, n_global):
+    """Seeded ground-truth images the way the dataset holds them: uint8 [H,W,3] (PIL), one per view of the global batch."""
+    g = torch.Generator().manual_seed(1234)
+    return [(torch.rand(args.height, args.width, 3, generator=g) * 255.999).to(torch.uint8) for _ in range(n_global)]
+
+
 def build_scene(args, device, world, rank, impl):
+    """raw Gaussians, THIS rank's cameras, its ground-truth images as pinned float32 [3,H,W] host tensors
+    (= u8 / 255 exactly as utils/general_utils.py:PILtoTorch converts them), and the global batch size."""
     from b200gs import synthetic as syn
     raw = syn.make_gaussians(args.points, scale_mu=args.scale_mu, device="cpu")
-    n_global = args.views_per_gpu * world
+    n_global = getattr(args, "global_views", None) or args.views_per_gpu * world
     cams_all = syn.orbit_cameras(n_global, args.width, args.height, device=device)
     mine = list(range(rank, n_global, world))
-    g = torch.Generator().manual_seed(1234)
-    gts_host = []
-    for b in range(n_global):
-        img = torch.rand(3, args.height, args.width, generator=g)
-        if b in mine:
-            gts_host.append(img.pin_memory())
+    u8 = scene_images_u8(args, n_global)
+    pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
+    gts_host = [pin((u8[b].float() / 255.0).permute(2, 0, 1).contiguous()) for b in mine]
+    build_scene.last_u8 = [pin(u8[b].contiguous()) for b in mine]
     cams = [cams_all[b] for b in mine]
     return raw, cams, gts_host, n_global
 
@@ -278,70 +289,82 @@ def make_reference_trainer(args, raw, device, world, rank):
                                              regulation_fn=ref_regulation)
 
 
-# ---- render FPS (BASELINE.json metric, second half; config C4 style) ---------------------------------
-def render_fps(args, model, device, world, rank, impl, ref_render=None):
-    """Video rendering (render_4DGS.py:41-76): frames of an orbit with advancing time, sharded round-robin over
-    ranks, no collective. `fps` = frames rendered per second on the device (deformation + rasterizer forward),
-    `e2e_fps` adds the output path per frame: to8b + D2H into pinned host memory (our arm: GPU quantise + async
-    3 B/pixel copy through a pinned ring; reference arm: the blocking float copy + host clip/cast of render_4DGS.py:49)."""
+# ---- render FPS (BASELINE.json config 4) -------------------------------------------------------------
+def render_block(args, model, device, world, rank, impl, ref_render=None):
+    """Video rendering (render_4DGS.py:41-76): the five camera paths (up-down, side, zoom-in, circle, vfx; 60 frames each, time
+    advancing along the path) of b200gs.synthetic.video_trajectories at 1920x1080 and 1280x720, frame f of path j on rank
+    (60 j + f) mod N, no collective.  `fps` = frames per second on the device (deformation + rasterizer forward), `e2e_fps` adds
+    the output path per frame: to8b + D2H into host memory (our arm: GPU quantise + async 3 B/pixel copy through a pinned ring
+    + the host-side copy out of the ring; reference arm: the blocking float copy + host clip/cast of render_4DGS.py:49)."""
+    import contextlib
     import numpy as np
     from b200gs import engine, synthetic as syn
     out = {}
     bg = torch.zeros(3, device=device)
-    for tag, (W, H) in (("1280x720", (args.width, args.height)), ("1920x1080", (1920, 1080))):
-        n = args.render_frames
-        cams = syn.orbit_cameras(n * world, W, H, device=device)[rank::world]
+    for tag, (W, H) in (("1920x1080", (1920, 1080)), ("1280x720", (args.width, args.height))):
+        paths = syn.video_trajectories(W, H, frames=args.render_frames, device=device)
+        # this rank's frames, grouped by path (a path is one sequence over the static model)
+        mine, k = [], 0
+        for name, cams in paths.items():
+            sel = [c for i, c in enumerate(cams) if (k + i) % world == rank]
+            k += len(cams)
+            mine.append(sel)
+        n_total = k
         fn = (lambda c: engine.render(c, model, bg, stage="fine")) if impl == "b200" else (lambda c: ref_render(c, model, bg, "fine"))
-        # our arm renders the sequence the way engine.render_frames does: the spatial half of the HexPlane field is evaluated
-        # once for the whole trajectory (the Gaussians do not move between frames), every frame samples its time planes only
-        # (its one-off cost is inside both timed regions: a fresh context is entered after the start event / clock)
-        import contextlib
 
         def shared():
             if impl == "b200" and not args.no_shared_spatial:
                 from b200gs import field as _field
                 return _field.shared_spatial_product(model._deformation, model._xyz)
             return contextlib.nullcontext()
+
+        def run_all(consume=None):
+            for sel in mine:
+                with shared():          # the spatial half of the HexPlane field once per path, time planes per frame
+                    for c in sel:
+                        r = fn(c)
+                        if consume is not None:
+                            consume(r["render"])
         with torch.no_grad():
             with shared():
-                for c in cams[:3]:
+                for c in mine[0][:3]:
                     fn(c)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            with shared():
-                for c in cams:
-                    fn(c)
-            e1.record()
+            e0.record(); run_all(); e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
             ms_plain = None
-            if impl == "b200" and not args.no_shared_spatial:          # the same frames with the full six-plane pass per frame, for reference
+            if impl == "b200" and not args.no_shared_spatial:          # the same frames with the full six-plane pass per frame
                 e0.record()
-                for c in cams:
-                    fn(c)
+                for sel in mine:
+                    for c in sel:
+                        fn(c)
                 e1.record()
                 torch.cuda.synchronize()
                 ms_plain = e0.elapsed_time(e1)
+            frames_out = []
             if impl == "b200":
                 from b200gs import output
                 ring = output.FrameRing(H, W, depth=4, device=device)      # pinned buffers are allocated once, outside the loop
-                ring.push(fn(cams[0])["render"]); ring.pop()
+                ring.push(fn(mine[0][0])["render"]); ring.pop()
+
+                def consume(img):
+                    if ring.count == 4:
+                        frames_out.append(ring.pop())
+                    ring.push(img)
+            else:
+                def consume(img):
+                    frames_out.append((255 * np.clip(img.cpu().numpy(), 0, 1)).astype(np.uint8))
             torch.cuda.synchronize()
             t0 = time.perf_counter()
+            run_all(consume)
             if impl == "b200":
-                with shared():
-                    for c in cams:
-                        if ring.count == 4:
-                            ring.pop()
-                        ring.push(fn(c)["render"])
-                    while ring.count:
-                        ring.pop()
-            else:
-                for c in cams:
-                    (255 * np.clip(fn(c)["render"].cpu().numpy(), 0, 1)).astype(np.uint8)
+                while ring.count:
+                    frames_out.append(ring.pop())
             torch.cuda.synchronize()
             wall = time.perf_counter() - t0
+            del frames_out
         if world > 1:
             import torch.distributed as dist
             t = torch.tensor([ms, wall * 1e3, ms_plain if ms_plain is not None else 0.0], device=device)
@@ -349,17 +372,133 @@ def render_fps(args, model, device, world, rank, impl, ref_render=None):
             ms, wall = float(t[0]), float(t[1]) / 1e3
             if ms_plain is not None:
                 ms_plain = float(t[2])
-        out[tag] = {"fps": n * world / (ms / 1e3), "e2e_fps": n * world / wall, "frames": n * world,
+        out[tag] = {"fps": n_total / (ms / 1e3), "e2e_fps": n_total / wall, "frames": n_total, "paths": list(paths.keys()),
                     "d2h_bytes_per_frame": 3 * W * H if impl == "b200" else 12 * W * H}
         if ms_plain is not None:
-            out[tag]["fps_full_field_per_frame"] = n * world / (ms_plain / 1e3)
+            out[tag]["fps_full_field_per_frame"] = n_total / (ms_plain / 1e3)
     return out
 
 
-# ---- cpu baseline ---------------------------------------------------------------------------------
+# ---- rasterizer alone (BASELINE.json config 2) ---------------------------------------------------------
+def raster_only_block(args, device, impl):
+    """Static 3DGS rasterizer fwd+bwd through the rasterizer API alone (coarse-stage semantics: no deformation field), SH degree 3,
+    at 200k Gaussians / 512x512 (config 2) and 1M / 1280x720, S-coarse scene, 5 warm-up + 20 timed repetitions, CUDA events.
+    Our arm calls the drop-in's `_C` entry points; the reference arm its own CUDA code (oracle/_ref) with the torch.zeros fills
+    its glue does (rasterize_points.cu:58-60, :154-163).  Same seeded inputs on both sides."""
+    from b200gs import synthetic as syn
+    out = {}
+    E = torch.Tensor([])
+    for tag, (P, W, H, mu) in (("200k_512x512", (200000, 512, 512, 0.010)), ("1M_1280x720", (1000000, 1280, 720, 0.010))):
+        raw = syn.make_gaussians(P, scale_mu=mu, device=device); act = syn.activated(raw)
+        cam = syn.make_camera(W, H, device=device)
+        bg = torch.zeros(3, device=device)
+        gt = torch.rand(3, H, W, device=device)
+        dLd = torch.zeros(1, H, W, device=device)
+        st = {}
+        if impl == "b200":
+            from b200gs.rasterizer import _C
+
+            def fwd():
+                st["o"] = _C.rasterize_gaussians(bg, act["means3D"], E, act["opacities"], act["scales"], act["rotations"], 1.0, E, cam.viewmatrix,
+                                                 cam.projmatrix, cam.tanfovx, cam.tanfovy, H, W, act["shs"], 3, cam.campos, False, False)
+            fwd()
+            R, color, depth, radii, geom, binb, img = st["o"]
+            dLc = torch.sign(color - gt) / (3 * H * W)
+
+            def bwd():
+                _C.rasterize_gaussians_backward(bg, act["means3D"], radii, E, act["scales"], act["rotations"], 1.0, E, cam.viewmatrix, cam.projmatrix,
+                                                cam.tanfovx, cam.tanfovy, dLc, dLd, act["shs"], 3, cam.campos, geom, R, binb, img, False)
+        else:
+            import ref_harness as rh
+            L = rh.rast(); p = rh._p
+            col = torch.zeros(3, H, W, device=device); dep = torch.zeros(1, H, W, device=device)
+            rad = torch.zeros(P, dtype=torch.int32, device=device)
+
+            def fwd():
+                col.zero_(); dep.zero_(); rad.zero_()
+                st["R"] = L.ref_rast_forward(P, 3, 16, p(bg), W, H, p(act["means3D"]), p(act["shs"]), None, p(act["opacities"]), p(act["scales"]), 1.0,
+                                             p(act["rotations"]), None, p(cam.viewmatrix), p(cam.projmatrix), p(cam.campos), cam.tanfovx, cam.tanfovy, 0,
+                                             p(col), p(dep), p(rad), 0)
+            fwd()
+            R = st["R"]
+            dLc = torch.sign(col - gt) / (3 * H * W)
+
+            def bwd():
+                z = lambda *s: torch.zeros(*s, device=device)
+                g = [z(P, 3), z(P, 2, 2), z(P, 1), z(P, 3), z(P, 1), z(P, 3), z(P, 6), z(P, 16, 3), z(P, 3), z(P, 4)]
+                L.ref_rast_backward(P, 3, 16, R, p(bg), W, H, p(act["means3D"]), p(act["shs"]), None, p(act["scales"]), 1.0, p(act["rotations"]), None,
+                                    p(cam.viewmatrix), p(cam.projmatrix), p(cam.campos), cam.tanfovx, cam.tanfovy, p(rad), p(dLc), p(dLd),
+                                    *[p(t) for t in g], 0)
+
+        def timeit(fn, n=20, warm=5):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+        tf, tb = timeit(fwd), timeit(bwd)
+        out[tag] = {"fwd_ms": round(tf, 4), "bwd_ms": round(tb, 4), "fwd_bwd_ms": round(tf + tb, 4), "fwd_bwd_per_s": 1e3 / (tf + tb),
+                    "instances": int(R), "scene": f"scale_mu={mu}"}
+        del raw, act
+        torch.cuda.empty_cache()
+    return out
+
+
+# ---- cpu baselines ---------------------------------------------------------------------------------
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cpu_c1(args):
+    """BASELINE.json config 1 exactly as SURVEY.md 8(d) words it: the reference's PyTorch path on CPU tensors -- deform_network
+    forward (effective config: 2 levels, T = 50, 64 features) + eval_sh degree 3 + clamp + cov3D (R S)(R S)^T + projection --
+    200k synthetic Gaussians, 512x512 camera, one timestep, all host threads, 3 warm-up + 10 timed repetitions, median.
+    Runs the pinned restatements (oracle/field_torch.py, oracle/cpu_path_torch.py): the reference tree does not exist here."""
+    import statistics
+    from b200gs import engine, synthetic as syn
+    from b200gs.field import deform_network
+    from oracle import cpu_path_torch as cp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = 200_000
+    raw = syn.make_gaussians(P, scale_mu=args.scale_mu, device="cpu")
+    cam = syn.make_camera(512, 512)
+    torch.manual_seed(6666)
+    net = deform_network(engine.default_hyper())
+    sd = {k: v.detach().clone().contiguous() for k, v in net.state_dict().items()}
+
+    def once():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            cp.c1_forward(sd, 2, raw["xyz"], raw["log_scale"], raw["rot"], raw["opacity_logit"], raw["shs"], raw["scene_flow"], 0.5, 3,
+                          cam.viewmatrix, cam.projmatrix, cam.campos)
+        return time.perf_counter() - t0
+    first = once()
+    warm, timed = (3, 10) if first < 1.5 else (1, 3)          # keep the leg inside ~30 s on a slow host
+    for _ in range(warm - 1):
+        once()
+    ts = [once() for _ in range(timed)]
+    med = statistics.median(ts)
+    return {"config": "C1: HexPlane deformation + SH eval + projection forward, 200000 Gaussians, 512x512, 1 timestep", "seconds_median": med,
+            "forwards_per_s": 1.0 / med, "warmup": warm, "timed": timed, "cores": cores, "cpu": _cpu_model(), "kind": "port",
+            "seconds_all": [round(t, 4) for t in ts]}
+
+
 def cpu_baseline(args, raw, cam):
-    """CPU port of ONE view-iteration (field fwd/bwd in torch on CPU tensors, rasterizer fwd/bwd in
-    oracle/raster_cpu.c with OpenMP, Adam in C) on the host cores; sample bounded by --cpu-points."""
+    """CPU port of ONE view-iteration of the benchmarked workload (field fwd/bwd in torch on CPU tensors, rasterizer fwd/bwd in
+    oracle/raster_cpu.c with OpenMP, Adam in C) on the host cores, on a bounded sample (--cpu-points Gaussians, image scaled with
+    them), 1 warm-up + 2 timed repetitions (median), scaled linearly to the full workload.  Plus config 1 (`c1`)."""
+    import statistics
     import numpy as np
     from b200gs import engine
     from oracle import field_torch, raster_cpu as rc
@@ -373,36 +512,46 @@ def cpu_baseline(args, raw, cam):
     sub = {k: v[:P].clone() for k, v in raw.items()}
     torch.manual_seed(6666)
     hyper = engine.default_hyper()
-    # reference-initialised field parameters without touching CUDA: build the product module on CPU (parameters only)
     from b200gs.field import deform_network
-    net = deform_network(hyper)
-    sd = {k: v.detach().clone().contiguous().requires_grad_(v.dtype.is_floating_point and "poc" not in k and not k.endswith("aabb"))
-          for k, v in net.state_dict().items()}
-    xyz = sub["xyz"].clone().requires_grad_(True); scl = sub["log_scale"].clone().requires_grad_(True)
-    rot = sub["rot"].clone().requires_grad_(True); opa = sub["opacity_logit"].clone().requires_grad_(True)
-    shs = sub["shs"].clone().requires_grad_(True)
-    t0 = time.perf_counter()
-    tt = torch.full((P, 1), 0.5)
-    pts, sc, rt, op, sh = field_torch.deform_forward(sd, 2, xyz, scl, rot, opa, shs, tt, sub["scene_flow"], 3, 1)
-    a_sc, a_rt, a_op = torch.exp(sc), torch.nn.functional.normalize(rt), torch.sigmoid(op)
-    s = rc.forward(pts.detach().numpy(), a_op.detach().numpy(), camc.viewmatrix.numpy(), camc.projmatrix.numpy(), camc.campos.numpy(),
-                   W, H, camc.tanfovx, camc.tanfovy, np.zeros(3, np.float32), shs=sh.detach().numpy(), scales=a_sc.detach().numpy(),
-                   rots=a_rt.detach().numpy())
+    net = deform_network(hyper)                   # reference-initialised field parameters, CPU tensors only
     gt = np.random.default_rng(0).random((3, H, W), dtype=np.float32)
-    dL = np.sign(s["color"] - gt).astype(np.float32) / (3 * H * W)
-    g = rc.backward(s, dL, np.zeros((1, H, W), np.float32))
-    torch.autograd.backward([pts, a_sc, a_rt, a_op, sh],
-                            [torch.from_numpy(g["means3D"]), torch.from_numpy(g["scales"]), torch.from_numpy(g["rotations"]),
-                             torch.from_numpy(g["opacity"]).reshape(P, 1), torch.from_numpy(g["sh"])])
-    for q in [xyz, scl, rot, opa, shs] + [v for v in sd.values() if v.requires_grad and v.grad is not None]:
-        pn = q.detach().numpy(); m = np.zeros_like(pn); v = np.zeros_like(pn)
-        rc.adam_step(pn, q.grad.numpy().copy(), m, v, 1e-3, 1)
-    dt = time.perf_counter() - t0
-    # one view-iteration on the sample; the per-view cost scales ~linearly with Gaussians and pixels
-    return {"value": (1.0 / dt) * frac, "unit": "view-iters/s", "cores": cores, "kind": "port",
-            "sample": f"1 view-iteration (field fwd/bwd + raster fwd/bwd + Adam) at {P} Gaussians, {W}x{H}, measured {dt:.2f} s, "
-                      f"scaled by {frac:.3f} to the {args.points}-Gaussian {args.width}x{args.height} workload",
-            "measured_seconds": dt, "instances": int(s["R"])}
+    inst = [0]
+
+    def once():
+        sd = {k: v.detach().clone().contiguous().requires_grad_(v.dtype.is_floating_point and "poc" not in k and not k.endswith("aabb"))
+              for k, v in net.state_dict().items()}
+        xyz = sub["xyz"].clone().requires_grad_(True); scl = sub["log_scale"].clone().requires_grad_(True)
+        rot = sub["rot"].clone().requires_grad_(True); opa = sub["opacity_logit"].clone().requires_grad_(True)
+        shs = sub["shs"].clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        tt = torch.full((P, 1), 0.5)
+        pts, sc, rt, op, sh = field_torch.deform_forward(sd, 2, xyz, scl, rot, opa, shs, tt, sub["scene_flow"], 3, 1)
+        a_sc, a_rt, a_op = torch.exp(sc), torch.nn.functional.normalize(rt), torch.sigmoid(op)
+        s = rc.forward(pts.detach().numpy(), a_op.detach().numpy(), camc.viewmatrix.numpy(), camc.projmatrix.numpy(), camc.campos.numpy(),
+                       W, H, camc.tanfovx, camc.tanfovy, np.zeros(3, np.float32), shs=sh.detach().numpy(), scales=a_sc.detach().numpy(),
+                       rots=a_rt.detach().numpy())
+        dL = np.sign(s["color"] - gt).astype(np.float32) / (3 * H * W)
+        g = rc.backward(s, dL, np.zeros((1, H, W), np.float32))
+        torch.autograd.backward([pts, a_sc, a_rt, a_op, sh],
+                                [torch.from_numpy(g["means3D"]), torch.from_numpy(g["scales"]), torch.from_numpy(g["rotations"]),
+                                 torch.from_numpy(g["opacity"]).reshape(P, 1), torch.from_numpy(g["sh"])])
+        for q in [xyz, scl, rot, opa, shs] + [v for v in sd.values() if v.requires_grad and v.grad is not None]:
+            pn = q.detach().numpy(); m = np.zeros_like(pn); v = np.zeros_like(pn)
+            rc.adam_step(pn, q.grad.numpy().copy(), m, v, 1e-3, 1)
+        inst[0] = int(s["R"])
+        return time.perf_counter() - t0
+    once()
+    ts = [once(), once()]
+    dt = statistics.median(ts)
+    res = {"value": (1.0 / dt) * frac, "unit": "view-iters/s", "cores": cores, "kind": "port", "cpu": _cpu_model(),
+           "sample": f"1 view-iteration (field fwd/bwd + raster fwd/bwd + Adam) at {P} Gaussians, {W}x{H}, 1 warm-up + 2 timed, median {dt:.2f} s, "
+                     f"scaled by {frac:.3f} to the {args.points}-Gaussian {args.width}x{args.height} workload",
+           "measured_seconds": dt, "instances": inst[0]}
+    try:
+        res["c1"] = cpu_c1(args)
+    except Exception as ex:
+        res["c1"] = {"failed": f"{type(ex).__name__}: {ex}"}
+    return res
 
 
 # ---------------------------------------------------------------------------------------------
@@ -422,6 +571,64 @@ def main():
     if line is not None:
         os.write(real_fd, (line + "\n").encode())
     os.close(real_fd)
+
+
+PHASES = ("preprocess_fwd", "depth_sort", "emit_instances", "tile_sort", "tile_ranges", "composite_fwd", "composite_bwd", "preprocess_bwd")
+
+
+def read_phases():
+    import ctypes
+    from b200gs import _lib
+    L = _lib.lib()
+    L.b200gs_profile_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float)]
+    out = {}
+    for name in PHASES:
+        n, ms = ctypes.c_int(0), ctypes.c_float(0.0)
+        if L.b200gs_profile_read(name.encode(), ctypes.byref(n), ctypes.byref(ms)) == 0 and n.value > 0:
+            out[name] = {"calls": n.value, "ms_total": ms.value, "ms_avg": ms.value / n.value}
+    return out
+
+
+def run_steps(trainer, cams, gts, n_global, steps, barrier, max_over_ranks):
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        trainer.step(cams, gts, global_batch=n_global)
+    e1.record()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1))
+
+
+def run_steps_e2e(trainer, cams, host_images, n_global, steps, device, barrier, max_over_ranks, impl):
+    """Ground truth in pinned host memory, uploaded every step inside the timed region; loss read back every step."""
+    from b200gs import engine
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    f0.record()
+    last = None
+    if impl == "b200":
+        feeder = engine.HostImageFeeder(host_images, device)
+        ring = engine.LossRing(depth=4)
+        feeder.prefetch()
+        for k in range(steps):
+            g = feeder.take()
+            if k + 1 < steps:
+                feeder.prefetch()                      # next step's upload overlaps this step
+            loss = trainer.step(cams, g, global_batch=n_global)
+            feeder.release()
+            ring.push(loss)
+            v = ring.read(lag=1)                       # the previous step's loss: no pipeline drain
+            last = v if v is not None else last
+        last = ring.read(lag=0)
+    else:
+        for _ in range(steps):                         # what train_4DGS.py:194,236 does: blocking float upload, loss.item() per step
+            g_step = [g.to(device, non_blocking=True) for g in host_images]
+            last = float(trainer.step(cams, g_step, global_batch=n_global))
+    f1.record()
+    barrier()
+    return max_over_ranks(f0.elapsed_time(f1)), time.perf_counter() - t_wall, last
 
 
 def _main():
@@ -453,7 +660,11 @@ def _main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
+    if args.global_batch % world != 0:
+        raise SystemExit(f"--global-batch {args.global_batch} does not divide over {world} ranks")
+    args.global_views = args.global_batch          # strong scaling: the batch BASELINE.json names, sharded over the ranks
     raw, cams, gts_host, n_global = build_scene(args, device, world, rank, impl)
+    host_u8 = build_scene.last_u8
     if impl == "b200":
         model, trainer = make_b200_trainer(args, raw, device, world, rank)
     else:
@@ -462,7 +673,9 @@ def _main():
             if rank == 0:
                 return json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_rast.so missing (run oracle/build_ref.sh where /root/reference exists)"})
             return None
-    gts_dev = [g.to(device, non_blocking=True) for g in gts_host]
+    # device-resident inputs of the `value` measurement: our arm keeps the dataset's uint8 images, the reference arm the float
+    # tensors its loss needs
+    gts_dev = [g.to(device, non_blocking=True) for g in (host_u8 if impl == "b200" else gts_host)]
     V = len(cams)
     pairs_per_view = None
     if impl == "b200":
@@ -470,13 +683,14 @@ def _main():
         from b200gs import engine as _eng
         from b200gs.rasterizer import _C as _rc
         with torch.no_grad():
-            pk0 = _eng.render(cams[0], model, torch.zeros(3, device=device), stage="fine")
+            _eng.render(cams[0], model, torch.zeros(3, device=device), stage="fine")
         try:
             sv = _eng.LAST_RASTER_STATE
             nc = _rc.export_state("n_contrib", args.points, sv[0], args.width, args.height, sv[1], sv[2], sv[3])
             pairs_per_view = int(nc.view(torch.int32).to(torch.int64).sum())
+            instances = int(sv[0])
         except Exception:
-            pairs_per_view = None
+            pairs_per_view, instances = None, None
 
     def barrier():
         if world > 1:
@@ -493,7 +707,7 @@ def _main():
         return ms
 
     # Per-entry-point device timing (CUDA events on the launching stream) is taken INSIDE the timed steps:
-    # our arm through b200gs._lib.CallTimer, the reference arm for its optimiser step only.
+    # our arm through b200gs._lib.CallTimer + the library's phase timing, the reference arm for its optimiser step only.
     adam_ms = []
     opt_step = model.optimizer.step
     timer = None
@@ -509,156 +723,226 @@ def _main():
             return r
         model.optimizer.step = timed_opt_step
 
-    for _ in range(max(args.warmup, 3)):
+    W_ = max(args.warmup, 3)
+    for _ in range(W_):
         trainer.step(cams, gts_dev, global_batch=n_global)
     adam_ms.clear()
     if timer:
         timer.reset()
-    barrier()
+        _b200lib.lib().b200gs_profile_enable(1)
+    timeline = None
     with ClockSampler(local) as clk:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            trainer.step(cams, gts_dev, global_batch=n_global)
-        e1.record()
-        barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1))
+        ms = run_steps(trainer, cams, gts_dev, n_global, args.steps, barrier, max_over_ranks)
         calls = timer.summary() if timer else {}
+        phases = {}
         if timer:
+            phases = read_phases()
+            _b200lib.lib().b200gs_profile_enable(0)
             timer.__exit__()
             adam_t = calls.get("b200gs_adam_multi", {}).get("ms_avg", 0.0)
         else:
             adam_t = sum(a.elapsed_time(b) for a, b in adam_ms) / max(len(adam_ms), 1)
-        # end to end: ground truth in pinned host memory, copied per view inside the timed region; loss read back
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_wall = time.perf_counter()
-        f0.record()
-        last = 0.0
-        for _ in range(args.steps):
-            g_step = [g.to(device, non_blocking=True) for g in gts_host]
-            last = float(trainer.step(cams, g_step, global_batch=n_global))
-        f1.record()
-        barrier()
-        ms_e2e = max_over_ranks(f0.elapsed_time(f1))
-        wall_e2e = time.perf_counter() - t_wall
+        ms_e2e, wall_e2e, last = run_steps_e2e(trainer, cams, host_u8 if impl == "b200" else gts_host, n_global, args.steps, device,
+                                               barrier, max_over_ranks, impl)
+        if impl == "b200":
+            # where one step's time goes: CUDA events around its phases (main stream + the SH side stream), one extra step
+            trainer.timeline = {}
+            trainer.step(cams, gts_dev, global_batch=n_global)
+            torch.cuda.synchronize()
+            tl, trainer.timeline = trainer.timeline, None
+            def span(a, b):
+                return round(tl[a].elapsed_time(tl[b]), 4) if a in tl and b in tl else None
+            timeline = {"views_ms": span("step_start", "views_done"), "deferred_field_backward_ms": span("views_done", "field_done"),
+                        "arena_allreduce_ms": span("field_done", "arena_reduced"), "regulariser_adam_ms": span("arena_reduced", "adam_done"),
+                        "join_sh_side_stream_ms": span("adam_done", "step_end"), "step_ms": span("step_start", "step_end"),
+                        "sh_side_stream": {"start_after_step_start_ms": span("step_start", "sh_tail_start"),
+                                           "allreduce_sh_and_radii_ms": span("sh_tail_start", "sh_reduced"),
+                                           "adam_sh_ms": span("sh_reduced", "sh_tail_end"),
+                                           "end_after_step_start_ms": span("step_start", "sh_tail_end")}}
     if not timer:
         model.optimizer.step = opt_step
+
+    # ---- weak-scaling block (N > 1): 8 views per GPU, global batch 8 N ----
+    weak = None
+    if world > 1 and impl == "b200" and not args.no_weak:
+        from b200gs import synthetic as syn
+        nw = args.views_per_gpu * world
+        cams_w = syn.orbit_cameras(nw, args.width, args.height, device=device)[rank::world]
+        g = torch.Generator().manual_seed(4321 + rank)
+        host_w = [(torch.rand(args.height, args.width, 3, generator=g) * 255.999).to(torch.uint8).pin_memory() for _ in cams_w]
+        dev_w = [h.to(device) for h in host_w]
+        for _ in range(2):
+            trainer.step(cams_w, dev_w, global_batch=nw)
+        ms_w = run_steps(trainer, cams_w, dev_w, nw, args.steps, barrier, max_over_ranks)
+        ms_we, _, _ = run_steps_e2e(trainer, cams_w, host_w, nw, args.steps, device, barrier, max_over_ranks, impl)
+        weak = {"scaling": "weak", "views_per_gpu": args.views_per_gpu, "global_batch": nw, "value": nw * args.steps / (ms_w / 1e3),
+                "unit": "view-iters/s", "ms_per_step": ms_w / args.steps, "e2e_value": nw * args.steps / (ms_we / 1e3)}
+        del host_w, dev_w
+
     render = None
     render_note = None
     if args.render_frames > 0:
         try:
-            render = render_fps(args, model, device, world, rank, impl, ref_render=None if impl == "b200" else trainer.render_fn)
+            render = render_block(args, model, device, world, rank, impl, ref_render=None if impl == "b200" else trainer.render_fn)
         except Exception as ex:                      # the side measurement must not take the headline down: fall back to per-frame passes
             if impl != "b200" or args.no_shared_spatial:
                 raise
             render_note = f"shared spatial product failed ({type(ex).__name__}: {ex}); per-frame six-plane passes measured instead"
             args.no_shared_spatial = True
             from b200gs import field as _field
-            _field._SHARED = None
-            render = render_fps(args, model, device, world, rank, impl, ref_render=None)
+            _field.drop_shared()
+            render = render_block(args, model, device, world, rank, impl, ref_render=None)
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
             dist.destroy_process_group()
         return None
 
-    views_total = V * world * args.steps
+    views_total = n_global * args.steps
     value = views_total / (ms / 1e3)
     e2e_value = views_total / (ms_e2e / 1e3)
     pk, pk_kind = peaks()
-    n_params = sum(p.numel() for p in trainer.trainable)
-    adam_bytes = 28.0 * n_params                                   # p, m, v read+written, g read
-    adam_gbs = adam_bytes / (adam_t * 1e-3) / 1e9 if adam_t > 0 else None
     hbm = pk.get("hbm_gbs")
+    n_params = sum(p.numel() for p in trainer.trainable)
+    n_sh = sum(p.numel() for p in getattr(trainer, "sh_params", []))
     P_, F_ = args.points, 64
     plane_params = sum(p.numel() for n, p in model.named_parameters() if ".grids." in n)
+    R_ = instances if impl == "b200" and instances else 0
+    tiles = ((args.width + 15) // 16) * ((args.height + 15) // 16)
+    tile_bits = max(1, (tiles - 1).bit_length())
+    tile_passes = (tile_bits + 7) // 8
+    fp32_peak = 148 * 128 * 1.965e9                 # lane-instructions per second
     # algorithmic HBM bytes per launch: what each kernel must move when every
     # re-used operand (planes, weights) stays on chip
-    model_bytes = {
-        "b200gs_adam_multi": ("adam_multi_kernel", adam_bytes),
+    entry_models = {
+        "b200gs_adam_multi": ("adam_multi_kernel", 28.0 * (n_params - n_sh)),
+        "b200gs_adam_sh": ("adam_sh_kernel", 28.0 * n_sh),
         "b200gs_hexplane_forward": ("hexplane_fwd_kernel", P_ * (12 + 4 + 4 * F_)),
         "b200gs_hexplane_backward": ("hexplane_bwd_kernel", P_ * (12 + 4 + 4 * F_ + 12) + 4 * plane_params),
-        # shared-spatial step: V time-plane passes (factor S in, d(S) accumulated) + one spatial pass per optimiser step
-        "b200gs_hexplane_forward_masked": ("hexplane_fwd_kernel", (V * P_ * (12 + 4 + 4 * F_ + 4 * F_) + P_ * (12 + 4 + 4 * F_)) / (V + 1)),
-        "b200gs_hexplane_backward_masked": ("hexplane_bwd_kernel", (V * P_ * (12 + 4 + 4 * F_ + 4 * F_ + 8 * F_ + 12)
-                                                                     + P_ * (12 + 4 + 4 * F_ + 12) + 4 * plane_params) / (V + 1)),
-        # one-timestamp views: time planes from shared memory; streams xyz, S and the feature rows (+ the d(S) accumulator)
-        "b200gs_hexplane_time_forward": ("hexplane_time_fwd_kernel", P_ * (12 + 4 * F_ + 4 * F_)),
-        "b200gs_hexplane_time_backward": ("hexplane_time_bwd_kernel", P_ * (12 + 4 * F_ + 4 * F_ + 8 * F_ + 12)),
+        "b200gs_hexplane_forward_masked": ("hexplane_fwd_kernel (spatial planes, once per step)", P_ * (12 + 4 + 4 * F_)),
+        "b200gs_hexplane_backward_masked": ("hexplane_bwd_kernel (spatial planes, once per step)", P_ * (12 + 4 + 4 * F_ + 12) + 4 * plane_params),
+        "b200gs_hexplane_time_forward": ("hexplane_time_fwd2_kernel", P_ * (12 + 4 * F_ + 4 * F_)),
+        "b200gs_hexplane_time_backward": ("hexplane_time_bwd2_kernel", P_ * (12 + 4 * F_ + 4 * F_ + 8 * F_ + 12)),
         "b200gs_deform_mlp_forward": ("deform_mlp_fwd_tc5v2_kernel", P_ * (4 * F_ + 52 + 4 * 4 * 64 + 40)),
         "b200gs_deform_mlp_backward": ("deform_mlp_bwd_tc5_kernel", P_ * (4 * 4 * 64 + 4 * F_ + 40 + 4 * F_)),
         "b200gs_activations_forward": ("activations_fwd_kernel", P_ * 64),
         "b200gs_activations_backward": ("activations_bwd_kernel", P_ * 96),
         "b200gs_l1_loss_fwd_bwd": ("l1_fwd_bwd_kernel", 12 * 3 * args.width * args.height),
+        "b200gs_l1_loss_fwd_bwd_u8": ("l1_fwd_bwd_u8_kernel", (4 + 1 + 4) * 3 * args.width * args.height),
+        "b200gs_hexplane_regulation": ("hexplane_regulation_kernel", 8.0 * plane_params),
     }
+    phase_models = {      # SURVEY.md 8(d) formulas
+        "preprocess_fwd": ("preprocess_fwd_kernel", "hbm", 311.0 * P_),
+        "depth_sort": ("rs_histogram + rs_scan_hist + 4 x rs_onesweep_pass (32-bit depth keys + index)", "hbm", (4 + 4 * 16.0) * P_),
+        "emit_instances": ("emit_instances_kernel", "hbm", 16.0 * P_ + 8.0 * R_),
+        "tile_sort": (f"rs_histogram + rs_scan_hist + {tile_passes} x rs_onesweep_pass (tile id + Gaussian id)", "hbm", (4 + tile_passes * 16.0) * R_),
+        "tile_ranges": ("tile_ranges_kernel", "hbm", 4.0 * R_ + 8.0 * tiles),
+        "composite_fwd": ("composite_fwd_kernel", "fp32-issue", 30.0 * (pairs_per_view or 0)),
+        "composite_bwd": ("composite_bwd_kernel", "fp32-issue", 85.0 * (pairs_per_view or 0)),
+        "preprocess_bwd": ("preprocess_bwd_kernel", "hbm", 622.0 * P_),
+    }
+    # the reference's own sort moves (8 + 24 * ceil((32 + bits) / 8)) B per instance (64-bit keys): for comparison
+    ref_sort_bytes = (8 + 24 * ((32 + tile_bits + 7) // 8)) * R_
+    traffic, traffic_src = ncu_traffic()
     kernels = []
     for name, c in sorted(calls.items(), key=lambda kv: -kv[1]["ms_total"]):
         row = {"entry": name, "calls": c["calls"], "ms_avg": round(c["ms_avg"], 4), "share_of_step": round(c["ms_total"] / ms, 4)}
-        if name in model_bytes and c["ms_avg"] > 0:
-            kname, nbytes = model_bytes[name]
+        if name in entry_models and c["ms_avg"] > 0:
+            kname, nbytes = entry_models[name]
             gbs = nbytes / (c["ms_avg"] * 1e-3) / 1e9
             row.update({"kernel": kname, "bound": "hbm", "algorithmic_bytes_per_launch": nbytes, "achieved_gbs": round(gbs, 1),
                         "frac_of_measured_hbm_peak": round(gbs / hbm, 4)})
         kernels.append(row)
-    if pairs_per_view:
-        # compositing is FP32-issue bound: SURVEY.md 8d cost model (reference SASS) = 85 FP32 lane-instructions per evaluated
-        # pair in the backward; peak = 148 SMs x 128 lanes x 1.965 GHz. The entry also contains preprocess_bwd (HBM-bound, ~15 %).
-        for row in kernels:
-            if row["entry"] in ("b200gs_rast_backward", "b200gs_rast_backward_accumulate_sh"):
-                rate = pairs_per_view * 85 / (row["ms_avg"] * 1e-3)
-                row.update({"kernel": "composite_bwd_kernel (+ preprocess_bwd_kernel)", "bound": "fp32-issue", "pairs_per_launch": pairs_per_view,
-                            "achieved_lane_instr_per_s": rate, "frac_of_fp32_peak_on_reference_cost_model": round(rate / (148 * 128 * 1.965e9), 4)})
-    single = [k for k in kernels if "frac_of_measured_hbm_peak" in k]
+    for name, c in sorted(phases.items(), key=lambda kv: -kv[1]["ms_total"]):
+        kname, bound, work = phase_models[name]
+        row = {"phase": name, "kernel": kname, "calls": c["calls"], "ms_avg": round(c["ms_avg"], 4), "share_of_step": round(c["ms_total"] / ms, 4),
+               "bound": bound}
+        if c["ms_avg"] > 0 and work > 0:
+            if bound == "hbm":
+                gbs = work / (c["ms_avg"] * 1e-3) / 1e9
+                row.update({"algorithmic_bytes_per_launch": work, "achieved_gbs": round(gbs, 1), "frac_of_measured_hbm_peak": round(gbs / hbm, 4)})
+            else:
+                rate = work / (c["ms_avg"] * 1e-3)
+                row.update({"pairs_per_launch": pairs_per_view, "lane_instr_per_pair_reference_cost_model": work / max(pairs_per_view, 1),
+                            "achieved_lane_instr_per_s": rate, "frac_of_fp32_peak_on_reference_cost_model": round(rate / fp32_peak, 4)})
+        kernels.append(row)
+    single = [k for k in kernels if "frac_of_measured_hbm_peak" in k and ("phase" in k or not k["entry"].startswith("b200gs_rast_"))]
+    single.sort(key=lambda k: -k["share_of_step"])
     dom = single[0] if single else None
     launches_per_step = None
     if impl == "b200":
         # kernels of libb200gs launched in the timed region, counted per entry point by CallTimer (KERNELS table)
         launches_per_step = sum(c["kernels"] for c in calls.values()) / args.steps
+    vpg = n_global // world
     res = {
         "metric": "train_iters_per_s", "value": value, "unit": "view-iters/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": W_, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"C3 train_4DGS fine-stage iteration: HexPlane deform + raster fwd/bwd + plane regulariser + Adam, {args.points} Gaussians, "
-                               f"{args.width}x{args.height}, {args.views_per_gpu} views per GPU per optimizer step (global batch {n_global})",
-                   "scene": f"seeded synthetic, scale_mu={args.scale_mu}", "views_per_gpu": args.views_per_gpu,
+                               f"{args.width}x{args.height}, global batch {n_global} views per optimizer step over {world} GPU(s) ({vpg} per GPU)",
+                   "scene": f"seeded synthetic, scale_mu={args.scale_mu}", "global_batch": n_global, "views_per_gpu": vpg,
                    "iters_per_s_at_batch": value / n_global,
                    "l2": "per-step working set (>= 236 MB of parameters + Adam state + 1M-splat records) exceeds the 126 MB L2",
                    "parallelism": f"view-parallel dp{world}"},
-        "e2e": {"value": e2e_value, "unit": "view-iters/s", "h2d_bytes_per_step": V * 3 * args.height * args.width * 4,
+        "e2e": {"value": e2e_value, "unit": "view-iters/s",
+                "h2d_bytes_per_step": V * 3 * args.height * args.width * (1 if impl == "b200" else 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e * 1e3 / args.steps,
-                "last_loss": last},
+                "last_loss": last,
+                "how": ("uint8 HWC ground truth (the dataset's own format) uploaded from pinned memory on a side stream one step ahead, converted "
+                        "inside the L1 kernel; loss copied to a pinned ring every step and read one step late") if impl == "b200" else
+                       "float32 CHW ground truth uploaded per step, float(loss) per step (train_4DGS.py:194, :236)"},
         "clocks": clk.summary(),
         "gpu_launches": int(round(launches_per_step * args.steps)) if launches_per_step else 0,
     }
     peak_src = pk_kind + " (MEASURED_PEAKS.json hbm_gbs)" if pk_kind == "measured" else "fallback 6650"
     if impl == "b200" and dom is not None:
-        # the dominant kernel of the step by device time (largest share among the single-kernel entry points)
+        # the dominant kernel of the step by device time
+        compulsory = 92.0 * P_ if "deform_mlp" in dom["kernel"] else None
         res["roofline"] = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": hbm, "unit": "GB/s",
-                           "frac": dom["frac_of_measured_hbm_peak"], "traffic": NCU_TRAFFIC.get(dom["kernel"]), "peak_source": peak_src,
+                           "frac": dom["frac_of_measured_hbm_peak"], "traffic": traffic.get(dom["kernel"].split(" ")[0]),
+                           "traffic_source": traffic_src, "peak_source": peak_src,
                            "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "ms_per_launch": dom["ms_avg"],
-                           "share_of_step": dom["share_of_step"], "note": ROOFLINE_NOTES.get(dom["kernel"], "")}
+                           "share_of_step": dom["share_of_step"],
+                           "note": ("algorithmic bytes = this kernel's interface (activation stash 1 KB + features + d_features + 40 B of upstream "
+                                    "gradients per point); SURVEY.md 8(d)'s compulsory bytes for a fully fused HexPlane+MLP backward are 92 B/point "
+                                    "(see compulsory_frac): the stash and the feature rows are design traffic") if compulsory else ""}
+        if compulsory:
+            res["roofline"]["compulsory_bytes_per_launch"] = compulsory
+            res["roofline"]["compulsory_frac"] = round(compulsory / (dom["ms_avg"] * 1e-3) / 1e9 / hbm, 4)
         res["kernels"] = kernels
+        res["reference_sort_bytes_per_view"] = ref_sort_bytes
+        if timeline:
+            res["timeline"] = timeline
     else:
+        adam_bytes = 28.0 * n_params
+        adam_gbs = adam_bytes / (adam_t * 1e-3) / 1e9 if adam_t > 0 else None
         res["roofline"] = {"kernel": "torch foreach Adam", "bound": "hbm", "achieved": adam_gbs, "peak": hbm, "unit": "GB/s",
                            "frac": (adam_gbs / hbm) if adam_gbs else None, "traffic": None, "peak_source": peak_src,
                            "algorithmic_bytes_per_launch": adam_bytes, "ms_per_launch": adam_t, "params": n_params}
+    if weak is not None:
+        res["weak"] = weak
     if impl == "b200":
         # which kernel generations ran (include/b200gs.h: b200gs_set_option; environment B200GS_* overrides)
         try:
             from b200gs import _lib as _l
             res["config"]["kernel_options"] = {n: int(_l.lib().b200gs_get_option(n.encode()))
                                                for n in ("mlp_fwd_elect", "mlp_bwd_v2", "hexplane_time_fwd", "hexplane_time_bwd", "lookback_parallel")}
+            res["config"]["overlap_sh_reduce"] = bool(trainer.overlap_sh_reduce)
         except Exception as ex:              # informational only
             res["config"]["kernel_options"] = f"unavailable: {ex}"
     if render is not None:
         res["render"] = render
-        res["config"]["render"] = (f"video rendering, {args.render_frames} frames per GPU of an orbit with advancing time, frames sharded "
+        res["config"]["render"] = (f"video rendering (config C4), 5 camera paths x {args.render_frames} frames with advancing time, frames sharded "
                                    "round-robin over ranks; fps = device time, e2e_fps = wall clock incl. to8b + D2H per frame"
                                    + ("" if impl != "b200" or args.no_shared_spatial else
-                                      "; spatial HexPlane product evaluated once per sequence (engine.render_frames), time planes per frame"))
+                                      "; spatial HexPlane product evaluated once per path (engine.render_frames), time planes per frame"))
         if render_note:
             res["config"]["render_note"] = render_note
+    if not args.no_raster_only:
+        try:
+            res["raster_only"] = raster_only_block(args, device, impl)
+        except Exception as ex:
+            res["raster_only"] = {"failed": f"{type(ex).__name__}: {ex}"}
     if impl != "b200":
         res["impl"] = "reference"
         res["reference_stack"] = "reference CUDA rasterizer (oracle/_ref, unmodified) + PyTorch port of HexPlane/deformation + torch.optim.Adam, on GPU"

@@ -27,6 +27,11 @@ _lib.register("b200gs_adam_multi", ctypes.c_int,
                ctypes.c_void_p])
 
 
+_lib.register("b200gs_adam_sh", ctypes.c_int,
+              [ctypes.c_longlong, ctypes.c_int, ctypes.POINTER(_AdamTensor), ctypes.POINTER(_AdamTensor), ctypes.c_void_p,
+               ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_void_p])
+
+
 def _same_layout(a, b):
     return a.shape == b.shape and a.stride() == b.stride()
 
@@ -47,8 +52,46 @@ class FusedAdam(Optimizer):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False)
         super().__init__(params, defaults)
 
+    def _group_of(self, p):
+        for group in self.param_groups:
+            if any(q is p for q in group["params"]):
+                return group
+        raise KeyError("parameter is not in this optimiser")
+
     @torch.no_grad()
-    def step(self, closure=None):
+    def step_sh(self, f_dc, f_rest, sh_grad):
+        """The step of the two SH parameters ([P,1,3] and [P,M-1,3], scene/gaussian_model.py:136-140) with their gradient read
+        from ONE [P,M,3] buffer (what the rasterizer backward writes): same arithmetic and state as `step()`, one launch, no
+        split of the gradient.  The trainer calls it on a side stream as soon as the last view's SH gradient is complete and
+        passes `skip=(f_dc, f_rest)` to the `step()` that follows."""
+        P, M = int(sh_grad.shape[0]), int(sh_grad.shape[1])
+        if not (sh_grad.is_cuda and sh_grad.dtype == torch.float32 and sh_grad.is_contiguous() and tuple(f_dc.shape) == (P, 1, 3)
+                and tuple(f_rest.shape) == (P, M - 1, 3) and f_dc.is_contiguous() and f_rest.is_contiguous()):
+            raise RuntimeError("step_sh: expected contiguous float32 CUDA tensors [P,1,3], [P,M-1,3] and a [P,M,3] gradient")
+        descs = []
+        betas_eps = None
+        for p in (f_dc, f_rest):
+            group = self._group_of(p)
+            state = self.state[p]
+            if len(state) == 0:
+                state["step"] = torch.tensor(0.0, dtype=torch.float32)
+                state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            state["step"] += 1
+            step = float(state["step"])
+            beta1, beta2 = group["betas"]
+            if betas_eps is None:
+                betas_eps = (beta1, beta2, float(group["eps"]))
+            elif betas_eps != (beta1, beta2, float(group["eps"])):
+                raise RuntimeError("step_sh: the two SH groups must share betas / eps")
+            descs.append(_AdamTensor(p.data_ptr(), None, state["exp_avg"].data_ptr(), state["exp_avg_sq"].data_ptr(), p.numel(),
+                                     (float(group["lr"]) / (1 - beta1 ** step)) * -1, (1 - beta2 ** step) ** 0.5))
+        check(_lib.lib().b200gs_adam_sh(P, M, ctypes.byref(descs[0]), ctypes.byref(descs[1]), sh_grad.data_ptr(), *betas_eps,
+                                        current_stream()), "adam_sh")
+        torch.autograd.graph.increment_version([f_dc, f_rest])
+
+    @torch.no_grad()
+    def step(self, closure=None, skip=()):
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -64,7 +107,7 @@ class FusedAdam(Optimizer):
             eps = float(group["eps"])
             for p in group["params"]:
                 g = p.grad
-                if g is None:
+                if g is None or any(p is q for q in skip):
                     continue
                 if g.is_sparse:
                     raise RuntimeError("FusedAdam does not support sparse gradients")

@@ -183,6 +183,79 @@ def render_frames(cams, pc, bg_color, stage="fine", **kw):
             yield out
 
 
+class HostImageFeeder:
+    """Ground-truth images that live in HOST memory the way the dataset holds them (PIL -> uint8 [H,W,3],
+    scene/dataset_readers.py:1041-1057; the reference uploads a float32 copy per view, train_4DGS.py:194): `take()` returns
+    this step's images on the device, `prefetch()` queues the next step's host->device copies on a side stream so that they
+    overlap the current step; the L1 kernel converts u8 -> float on the device (fusedops.l1_loss_and_grad).  3 bytes per pixel
+    cross PCIe instead of 12, and never on the critical path.  `host_images`: pinned tensors, one per view of this rank."""
+
+    def __init__(self, host_images, device, slots=2):
+        self.host = list(host_images)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [[torch.empty_like(h, device=self.device) for h in self.host] for _ in range(slots)]
+        self.ready = [None] * slots
+        self.consumed = [None] * slots
+        self.head = 0                                  # next slot to fill
+        self.tail = 0                                  # next slot to hand out
+        self.bytes_per_step = sum(h.numel() * h.element_size() for h in self.host)
+
+    def prefetch(self, host_images=None):
+        src = self.host if host_images is None else host_images
+        slot = self.head % len(self.slots)
+        with torch.cuda.stream(self.stream):
+            if self.consumed[slot] is not None:
+                self.stream.wait_event(self.consumed[slot])      # the step that read this slot has finished with it
+            for d, h in zip(self.slots[slot], src):
+                d.copy_(h, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            self.ready[slot] = ev
+        self.head += 1
+
+    def take(self):
+        if self.tail == self.head:
+            self.prefetch()
+        slot = self.tail % len(self.slots)
+        torch.cuda.current_stream().wait_event(self.ready[slot])
+        self.tail += 1
+        return self.slots[slot]
+
+    def release(self):
+        """Call after the step that used the last take() has been queued: its slot may be refilled once that work is done."""
+        slot = (self.tail - 1) % len(self.slots)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.consumed[slot] = ev
+
+
+class LossRing:
+    """Per-step loss read-back without a host sync per step: the scalar is copied into a pinned ring asynchronously and read
+    `lag` steps later (train_4DGS.py:236 calls loss.item() every iteration, which drains the GPU queue each time)."""
+
+    def __init__(self, depth=4):
+        self.host = torch.zeros(depth, dtype=torch.float32).pin_memory()
+        self.events = [None] * depth
+        self.n = 0
+
+    def push(self, loss):
+        i = self.n % self.host.numel()
+        self.host[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[i] = ev
+        self.n += 1
+
+    def read(self, lag=1):
+        """Value pushed `lag` steps ago (lag=0: the latest; waits for its copy only)."""
+        if self.n - 1 - lag < 0:
+            return None
+        i = (self.n - 1 - lag) % self.host.numel()
+        self.events[i].synchronize()
+        return float(self.host[i])
+
+
 def _receives_grad(name, stage):
     """Parameters the reference's loss reaches (SURVEY.md Appendix C iii): timenet, the opacity /
     SH heads and the aabb never do; in the coarse stage the whole deformation field is bypassed."""
@@ -197,7 +270,20 @@ class ViewParallelTrainer:
     """One optimiser step over a batch of views sharded across ranks (replicated model).
 
     `render_fn(cam, model, bg, stage)` defaults to this module's `render`; tests inject a CPU
-    stand-in to exercise the sharding / flat-arena / collective logic over gloo."""
+    stand-in to exercise the sharding / flat-arena / collective logic over gloo.
+
+    Step anatomy on the GPU (`shared_shs`, the default with our own render):
+      * every trainable parameter except the two SH tensors has its `.grad` inside ONE flat FP32 arena
+        `[xyz | MLP | planes | opacity | scaling | rotation | screen-space xy]`; the SH gradient -- 192 of the 260 bytes a
+        Gaussian contributes -- lives in one `[P,16,3]` buffer that the rasterizer backward of every view adds into (the
+        first view of a step overwrites it, so it is never zero-filled);
+      * as soon as the LAST view's rasterizer backward has queued that addition, the SH tail starts on a side stream:
+        `ncclAllReduce(sum)` of the SH buffer (+ the `max` of the radii), then the Adam step of the two SH tensors straight
+        from that buffer (`FusedAdam.step_sh`) -- all of it overlapping the last view's field backward, the deferred spatial
+        HexPlane backward and the plane regulariser on the main stream;
+      * the main stream then reduces the (4x smaller) arena, adds the regulariser and takes the Adam step of everything
+        else; the step ends by joining the side stream.
+    Same sums, same Adam arithmetic as one collective + one optimiser launch (tests/test_dist_gloo.py, tests/test_dist_nccl.py)."""
 
     def __init__(self, model, bg_color, stage="fine", process_group=None, world_size=1, rank=0, render_fn=None,
                  regulation=None, regulation_fn=None, shared_shs=None, overlap_sh_reduce=None):
@@ -213,35 +299,34 @@ class ViewParallelTrainer:
         # our own render() takes the per-step SH tensor; an injected render_fn keeps the 4-argument form
         self.shared_shs = (render_fn is None) if shared_shs is None else bool(shared_shs)
         self.render_fn = render_fn or (lambda cam, m, bg, st, shs=None: render(cam, m, bg, stage=st, shs=shs))
-        # Opt-in (B200GS_OVERLAP_SH_REDUCE=1, not yet measured): the SH gradient -- 192 of the 248 MB a rank contributes at 1M
-        # Gaussians -- is final as soon as the LAST view's rasterizer backward has run, so its all-reduce starts there, on NCCL's
-        # own stream, and overlaps that view's field backward and the deferred spatial pass; the rest of the arena (everything
-        # but the SH slices, which then sit at its end) is reduced after the loop as before.
+        dev = model.get_xyz.device
+        # SH tail on a side stream, started from inside the last view's backward (B200GS_OVERLAP_SH_REDUCE=0: after the loop,
+        # on the main stream -- same collectives, same order, nothing overlapped)
         if overlap_sh_reduce is None:
-            overlap_sh_reduce = os.environ.get("B200GS_OVERLAP_SH_REDUCE") == "1"
-        self.overlap_sh_reduce = bool(overlap_sh_reduce) and self.shared_shs and world_size > 1
-        self._sh_work = None
+            overlap_sh_reduce = os.environ.get("B200GS_OVERLAP_SH_REDUCE", "1") != "0"
+        self.overlap_sh_reduce = bool(overlap_sh_reduce) and self.shared_shs and dev.type == "cuda"
+        self.side = torch.cuda.Stream(device=dev) if self.overlap_sh_reduce else None
+        self._sh_started = False
+        self._sh_done = None
+        self.timeline = None                           # bench.py: dict of CUDA events around the phases of the last step
         P = model.get_xyz.shape[0]
-        # flat gradient arena: [every parameter the loss reaches | screen-space xy per Gaussian];
-        # p.grad are views into it, so autograd accumulates in place and ONE collective (fp32 sum
-        # over NVLink/NVSwitch) reduces everything. Parameters outside it keep grad None and the
-        # optimiser skips them, as torch does in the reference.
+        # flat gradient arena: [every parameter the loss reaches except (shared_shs) the SH tensors | screen-space xy per
+        # Gaussian]; p.grad are views into it, so autograd accumulates in place and ONE collective (fp32 sum over
+        # NVLink/NVSwitch) reduces it. Parameters outside it keep grad None and the optimiser skips them, as torch does.
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and _receives_grad(n, stage)]
         is_sh = lambda n: n in ("_features_dc", "_features_rest")
-        if self.overlap_sh_reduce:                     # SH slices last: [other parameters | screen-space xy | f_dc | f_rest]
-            named = [x for x in named if not is_sh(x[0])] + [x for x in named if is_sh(x[0])]
+        self.sh_params = [p for n, p in named if is_sh(n)] if self.shared_shs else []
+        if len(self.sh_params) != 2:
+            self.sh_params = []
+        arena_named = [x for x in named if not (self.sh_params and is_sh(x[0]))]
         self.trainable = [p for _, p in named]
+        self.arena_params = [p for _, p in arena_named]
         # every slice starts on a 256-byte boundary: the kernels use 128-bit loads / vector reductions on them
         al = lambda x: (x + 63) // 64 * 64
-        n = sum(al(p.numel()) for p in self.trainable) + al(3 * P)
-        self.arena = torch.zeros(n, dtype=torch.float32, device=model.get_xyz.device)
+        n = sum(al(p.numel()) for p in self.arena_params) + al(3 * P)
+        self.arena = torch.zeros(n, dtype=torch.float32, device=dev)
         self.views, off = [], 0
-        self.viewspace_grad = None
-        for name, p in named:
-            if self.overlap_sh_reduce and is_sh(name) and self.viewspace_grad is None:
-                self.viewspace_grad = self.arena[off:off + 3 * P].view(P, 3)
-                off += al(3 * P)
-                self._reduce_end = off                 # the post-loop all-reduce covers arena[:_reduce_end]
+        for name, p in arena_named:
             flat = self.arena[off:off + p.numel()]
             if p.dim() == 4 and p.stride(1) == 1 and not p.is_contiguous():     # channels_last plane
                 N, C, H, W = p.shape
@@ -250,57 +335,100 @@ class ViewParallelTrainer:
                 v = flat.view(p.shape)
             self.views.append(v)
             off += al(p.numel())
-        if self.viewspace_grad is None:
-            self.viewspace_grad = self.arena[off:off + 3 * P].view(P, 3)
-            self._reduce_end = n
-        self.max_radii = torch.zeros(P, dtype=torch.int32, device=self.arena.device)
+        self.viewspace_grad = self.arena[off:off + 3 * P].view(P, 3)
+        self.max_radii = torch.zeros(P, dtype=torch.int32, device=dev)
+        self.sh_grad = None                            # [P,M,3], allocated with the first step's SH tensor
 
     def _bind(self):
         self.arena.zero_()
         self.max_radii.zero_()
-        for p, v in zip(self.trainable, self.views):
+        for p, v in zip(self.arena_params, self.views):
             p.grad = v
-
-    def _start_sh_reduce(self, shs):
-        if self._sh_work is None and shs is not None and shs.grad is not None:
-            import torch.distributed as dist
-            self._sh_work = dist.all_reduce(shs.grad, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
 
     def local_views(self, n_global):
         """Indices of the global batch this rank renders: view b goes to rank b mod world_size."""
         return list(range(self.rank, n_global, self.world_size))
 
+    def _mark(self, name):
+        if self.timeline is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.timeline[name] = ev
+
+    # ---- SH tail: all-reduce of the SH gradient (+ radii max), then the SH parameters' Adam step ----------------------------
+    def _sh_tail_body(self):
+        import torch.distributed as dist
+        m = self.model
+        self._mark("sh_tail_start")
+        if self.world_size > 1:
+            dist.all_reduce(self.sh_grad, op=dist.ReduceOp.SUM, group=self.pg)
+            dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=self.pg)
+        self._mark("sh_reduced")
+        opt = m.optimizer
+        if hasattr(opt, "step_sh") and self.sh_grad.is_cuda:
+            opt.step_sh(m._features_dc, m._features_rest, self.sh_grad)
+            self._sh_stepped = True
+        else:                                          # any other optimiser: hand it the two slices, stepped with the rest
+            m._features_dc.grad = self.sh_grad[:, :1]
+            m._features_rest.grad = self.sh_grad[:, 1:]
+            self._sh_stepped = False
+        self._mark("sh_tail_end")
+
+    def _sh_tail(self):
+        """Called once per step: from the last view's rasterizer backward (overlap), else after the view loop."""
+        if self._sh_started or not self.sh_params:
+            return
+        self._sh_started = True
+        if self.side is None:
+            self._sh_tail_body()
+            return
+        ready = torch.cuda.Event()
+        ready.record()                                 # on the stream the rasterizer backward has just been queued on
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            self._sh_tail_body()
+            self._sh_done = torch.cuda.Event()
+            self._sh_done.record(self.side)
+
     def step(self, cams, gts, global_batch=None):
-        """cams / gts: THIS rank's views. Loss = mean over the GLOBAL batch of per-view L1 means
-        (train_4DGS.py:205-210: l1 over the concatenated [B,3,H,W] tensor). Returns the summed
-        local loss (already scaled by 1/B) as a tensor."""
+        """cams / gts: THIS rank's views; a ground-truth image is a float32 [3,H,W] tensor or the dataset's own uint8 [H,W,3]
+        image (GPU path). Loss = mean over the GLOBAL batch of per-view L1 means (train_4DGS.py:205-210: l1 over the
+        concatenated [B,3,H,W] tensor). Returns the summed local loss (already scaled by 1/B) as a tensor."""
         B = global_batch or (len(cams) * self.world_size)
         self._bind()
+        self._mark("step_start")
         total = None
         shs = None
-        if self.shared_shs:
+        m = self.model
+        self._sh_started, self._sh_done, self._sh_stepped = False, None, False
+        if self.sh_params:
             # get_features (scene/gaussian_model.py:136-140) is the same tensor for every view of the step: build it once
-            # as a leaf, let the views' SH gradients accumulate in it, and split them back after the last view
-            m = self.model
+            # as a leaf; every view's SH gradient accumulates in ONE buffer that outlives the step
             shs = torch.cat((m._features_dc, m._features_rest), dim=1).detach().requires_grad_(True)
+            if self.sh_grad is None or self.sh_grad.shape != shs.shape:
+                self.sh_grad = torch.zeros_like(shs)
             if shs.is_cuda:
-                # the rasterizer backward adds every view's SH gradient straight into this buffer (no per-view allocation,
-                # no AccumulateGrad pass over 192 B per Gaussian)
-                shs.grad = torch.zeros_like(shs)
+                # the rasterizer backward adds every view's SH gradient straight into the buffer (the first view of the
+                # step overwrites it): no per-view allocation, no zero fill, no AccumulateGrad pass over 192 B per Gaussian
+                shs.grad = self.sh_grad
+            m._features_dc.grad = None
+            m._features_rest.grad = None
         from . import field as _field
-        share_spatial = self.shared_shs and self.stage == "fine" and len(cams) > 1 and self.model._xyz.is_cuda
+        share_spatial = self.shared_shs and self.stage == "fine" and len(cams) > 1 and m._xyz.is_cuda
         if share_spatial:
-            _field.begin_shared_step(self.model._deformation, self.model._xyz)
-        self._sh_work = None
+            _field.begin_shared_step(m._deformation, m._xyz)
+        first_sh = True
         try:
             for vi, (cam, gt) in enumerate(zip(cams, gts)):
-                pkg = self.render_fn(cam, self.model, self.bg, self.stage, shs) if self.shared_shs else \
-                    self.render_fn(cam, self.model, self.bg, self.stage)
+                pkg = self.render_fn(cam, m, self.bg, self.stage, shs) if self.shared_shs else \
+                    self.render_fn(cam, m, self.bg, self.stage)
                 _field.ACCUMULATE_INTO_GRAD = self.shared_shs     # p.grad are arena views: let the field kernels add into them
-                _rast.SH_GRAD_ACCUMULATOR = shs.grad if (shs is not None and shs.is_cuda) else None
-                if self.overlap_sh_reduce and vi == len(cams) - 1:
+                on_gpu = shs is not None and shs.is_cuda
+                _rast.SH_GRAD_ACCUMULATOR = self.sh_grad if on_gpu else None
+                _rast.SH_GRAD_OVERWRITE = first_sh
+                if on_gpu and self.overlap_sh_reduce and vi == len(cams) - 1:
                     # called by the rasterizer backward right after it has queued the kernel that adds this view's SH gradient
-                    _rast.AFTER_SH_ACCUMULATE = lambda: self._start_sh_reduce(shs)
+                    _rast.AFTER_SH_ACCUMULATE = self._sh_tail
                 try:
                     if self.shared_shs and gt.is_cuda:
                         # fused L1 (utils/loss_utils.py:23-24) + its gradient, then backward from the image
@@ -316,7 +444,9 @@ class ViewParallelTrainer:
                 finally:
                     _field.ACCUMULATE_INTO_GRAD = False
                     _rast.SH_GRAD_ACCUMULATOR = None
+                    _rast.SH_GRAD_OVERWRITE = False
                     _rast.AFTER_SH_ACCUMULATE = None
+                first_sh = False
                 vg = pkg["viewspace_points"].grad
                 if vg is not None:
                     self.viewspace_grad += vg
@@ -326,29 +456,40 @@ class ViewParallelTrainer:
         except BaseException:
             _field.drop_shared()               # never leave a half-used spatial product behind (a later render() would reuse it)
             raise
+        self._mark("views_done")
+        if self.sh_params:
+            if not shs.is_cuda:                        # CPU plumbing tests: autograd accumulated into the leaf itself
+                self.sh_grad = shs.grad if shs.grad is not None else torch.zeros_like(shs)
+            elif first_sh:                             # a rank without views still takes part in the collective
+                self.sh_grad.zero_()
+            self._sh_tail()                            # no-op when the last view's backward has already started it
         if share_spatial:
             _field.finish_shared_step()
-        if self.overlap_sh_reduce and shs is not None:
-            if shs.grad is None:                       # a rank without views still takes part in the collective
-                shs.grad = torch.zeros_like(shs)
-            self._start_sh_reduce(shs)                 # no-op when the rasterizer backward has already started it
-            self._sh_work.wait()
-            self._sh_work = None
-        if shs is not None and shs.grad is not None:
-            self.model._features_dc.grad += shs.grad[:, :1]
-            self.model._features_rest.grad += shs.grad[:, 1:]
+        self._mark("field_done")
         if self.world_size > 1:
             import torch.distributed as dist
-            # with the SH slices already reduced (above) only the front of the arena is left
-            dist.all_reduce(self.arena[:self._reduce_end] if self.overlap_sh_reduce else self.arena, op=dist.ReduceOp.SUM, group=self.pg)
-            dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=self.pg)
+            dist.all_reduce(self.arena, op=dist.ReduceOp.SUM, group=self.pg)
+            if not self.sh_params:
+                dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=self.pg)
+        self._mark("arena_reduced")
         if self.regulation is not None:
             # plane-only term, identical on every rank: added once, after the reduce
-            _field.accumulate_regulation(self.model._deformation.deformation_net.grid, *self.regulation,
+            _field.accumulate_regulation(m._deformation.deformation_net.grid, *self.regulation,
                                          loss_accum=total if (total is not None and total.numel() == 1 and total.dim() == 1) else None)
         if self.regulation_fn is not None:
             reg = self.regulation_fn()
             reg.backward()
             total = total + reg.detach()
-        self.model.optimizer.step()
+        if self._sh_done is not None:
+            # join BEFORE the main-stream optimiser launch when the SH tensors were not stepped on the side stream
+            if not self._sh_stepped:
+                torch.cuda.current_stream().wait_event(self._sh_done)
+        if self._sh_stepped:
+            m.optimizer.step(skip=tuple(self.sh_params))
+        else:
+            m.optimizer.step()
+        self._mark("adam_done")
+        if self._sh_done is not None and self._sh_stepped:
+            torch.cuda.current_stream().wait_event(self._sh_done)
+        self._mark("step_end")
         return total.reshape(()) if total is not None else total

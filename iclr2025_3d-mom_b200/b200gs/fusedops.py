@@ -16,6 +16,7 @@ _P = ctypes.c_void_p
 _lib.register("b200gs_activations_forward", ctypes.c_int, [ctypes.c_longlong, _P, _P, _P, _P, _P, _P, _P])
 _lib.register("b200gs_activations_backward", ctypes.c_int, [ctypes.c_longlong] + [_P] * 10)
 _lib.register("b200gs_l1_loss_fwd_bwd", ctypes.c_int, [ctypes.c_longlong, _P, _P, ctypes.c_float, _P, _P, _P])
+_lib.register("b200gs_l1_loss_fwd_bwd_u8", ctypes.c_int, [ctypes.c_int, ctypes.c_int, _P, _P, ctypes.c_float, _P, _P, _P])
 
 
 def _req(t, shape_tail):
@@ -60,7 +61,17 @@ def activations(scales, rotations, opacity):
 
 
 def l1_loss_and_grad(render, target, scale, loss_accum):
-    """loss_accum[0] += scale * sum|render - target|; returns d(loss)/d(render) (= scale * sign)."""
+    """loss_accum[0] += scale * sum|render - target|; returns d(loss)/d(render) (= scale * sign).
+    target: float32 [3,H,W], or the dataset's own uint8 [H,W,3] image (converted on the device as PILtoTorch does: u8 / 255)."""
+    if target.dtype == torch.uint8:
+        if not (render.is_cuda and target.is_cuda and render.dtype == torch.float32 and render.dim() == 3 and render.shape[0] == 3
+                and tuple(target.shape) == (render.shape[1], render.shape[2], 3)):
+            raise RuntimeError("l1_loss_and_grad: a uint8 target must be [H,W,3] on the GPU for a float32 [3,H,W] render")
+        r, t = render.detach().contiguous(), target.contiguous()
+        d = torch.empty_like(r)
+        check(_lib.lib().b200gs_l1_loss_fwd_bwd_u8(int(r.shape[1]), int(r.shape[2]), r.data_ptr(), t.data_ptr(), float(scale),
+                                                   loss_accum.data_ptr(), d.data_ptr(), current_stream()), "l1_loss_u8")
+        return d
     if not (render.is_cuda and target.is_cuda and render.dtype == torch.float32 and target.dtype == torch.float32):
         raise RuntimeError("l1_loss_and_grad needs float32 CUDA tensors (there is no CPU path)")
     if render.shape != target.shape:

@@ -22,6 +22,9 @@ SH_GRAD_ACCUMULATOR = None
 # Optional callable the backward invokes right after queueing the kernel that adds into SH_GRAD_ACCUMULATOR (the trainer starts
 # the SH gradient's all-reduce there on the last view of a step); None = nothing.
 AFTER_SH_ACCUMULATE = None
+# True for the first view of a step: the backward WRITES the accumulator (b200gs_rast_backward fills every row, zeros for culled
+# Gaussians) instead of adding into it, so the buffer never needs a zero fill.
+SH_GRAD_OVERWRITE = False
 
 _pinned = {}
 
@@ -124,12 +127,13 @@ class _CModule:
         has_sh = M != 0 and (colors is None or colors.numel() == 0)
         acc = SH_GRAD_ACCUMULATOR
         use_acc = has_sh and acc is not None and acc.shape == (P, M, 3) and acc.is_contiguous() and acc.device == dev
+        overwrite = use_acc and SH_GRAD_OVERWRITE      # first view of a step: the kernel writes every row, nothing to zero
         dL_dsh = acc if use_acc else (torch.empty((P, M, 3), **opts) if has_sh else torch.zeros((P, M, 3), **opts))
         dL_dscales = torch.empty((P, 3), **opts)
         dL_drotations = torch.empty((P, 4), **opts)
         if P != 0:
             arena = torch.empty((P, 12), **opts)
-            entry = L.b200gs_rast_backward_accumulate_sh if use_acc else L.b200gs_rast_backward
+            entry = L.b200gs_rast_backward_accumulate_sh if (use_acc and not overwrite) else L.b200gs_rast_backward
             check(entry(
                 P, int(degree), M, int(R), W, H, ptr(background), ptr(means3D), ptr(sh), ptr(colors), ptr(scales),
                 float(scale_modifier), ptr(rotations), ptr(cov3D_precomp), ptr(viewmatrix), ptr(projmatrix),

@@ -75,6 +75,32 @@ def orbit_cameras(n, W, H, distance=4.5, device="cpu"):
     return cams
 
 
+def video_trajectories(W, H, frames=60, distance=4.5, device="cpu"):
+    """The render_4DGS.py video paths (scene/dataset_readers.py:1168-1190: up-down, side, zoom-in, circle from
+    test_trajectory/*_{R,t}_list, plus vfx) restated for the synthetic scene: as in those files the rotation is the identity
+    and only the camera translation moves -- linearly between +a and -a (up-down: y, side: x), from 0 to -b in z (zoom-in),
+    on an ellipse in x / z (circle), or rising while moving in (vfx) -- with the amplitudes (0.08-0.09 and 0.24 scene units
+    at a scene depth of ~1) scaled to this scene's camera distance.  Frame i of a path carries time = linspace(0, 2, frames)[i] / 2
+    and frame_num = i (scene/dataset_readers.py:1004-1018, :1150-1159).  Returns {name: [SynthCamera] * frames}."""
+    k = distance
+    lin = np.linspace(1.0, -1.0, frames)
+    ang = np.linspace(0.0, 2.0 * math.pi, frames)
+    ramp = np.linspace(0.0, 1.0, frames)
+    paths = {
+        "up_down": [(0.0, 0.08 * k * a, 0.0) for a in lin],
+        "side": [(0.09 * k * a, 0.0, 0.0) for a in lin],
+        "zoom_in": [(0.0, 0.0, -0.24 * k * r) for r in ramp],
+        "circle": [(-0.04 * k * math.cos(a), -0.003 * k * math.sin(a), 0.09 * k * math.cos(a)) for a in ang],
+        "vfx": [(0.0, 0.16 * k * r, -0.24 * k * r) for r in ramp],
+    }
+    times = np.linspace(0.0, 2.0, frames, dtype=np.float32) / 2.0
+    out = {}
+    for name, offs in paths.items():
+        out[name] = [make_camera(W, H, R=np.eye(3), t=np.array([o[0], o[1], distance + o[2]]), time=float(times[i]), frame_num=i,
+                                 device=device) for i, o in enumerate(offs)]
+    return out
+
+
 def make_gaussians(P, scale_mu=0.004, sh_degree=3, seed=SEED, device="cpu"):
     """Raw (pre-activation) Gaussian parameters, generated on the CPU for reproducibility."""
     g = torch.Generator().manual_seed(seed)

@@ -79,6 +79,31 @@ __global__ void __launch_bounds__(AD_THREADS) adam_multi_kernel(const __grid_con
     }
 }
 
+// Adam over the two SH parameter tensors of scene/gaussian_model.py:136-140, _features_dc [P,1,3] and _features_rest
+// [P,M-1,3], whose gradient arrives as ONE [P,M,3] buffer (what the rasterizer backward writes, backward.cu:20-139): the
+// split / copy of the gradient disappears and the two tensors share one launch.  One thread per gradient element.
+struct AdamShArgs {
+    float* p_dc; float* m_dc; float* v_dc; float* p_rest; float* m_rest; float* v_rest;
+    const float* grad; long long P; int M;
+    float neg_step_dc, bcs_dc, neg_step_rest, bcs_rest, beta1_c, beta2, beta2_c, eps;
+};
+
+__global__ void __launch_bounds__(256) adam_sh_kernel(const __grid_constant__ AdamShArgs a)
+{
+    const long long row = 3LL * a.M, total = a.P * row;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const long long pt = e / row;
+        const int c = (int)(e - pt * row);
+        const float g = __ldg(a.grad + e);
+        const bool dc = c < 3;
+        const long long i = dc ? pt * 3 + c : pt * (row - 3) + (c - 3);
+        float* p = (dc ? a.p_dc : a.p_rest) + i; float* m = (dc ? a.m_dc : a.m_rest) + i; float* v = (dc ? a.v_dc : a.v_rest) + i;
+        float pp = *p, mm = *m, vv = *v;
+        adam_one(pp, g, mm, vv, a.beta1_c, a.beta2, a.beta2_c, a.eps, dc ? a.neg_step_dc : a.neg_step_rest, dc ? a.bcs_dc : a.bcs_rest);
+        *p = pp; *m = mm; *v = vv;
+    }
+}
+
 // ---- multi-tensor row gather: dst_t[i, :] = src_t[index[i], :] for every tensor t --------
 struct GatherTable {
     b200gs_gather_tensor t[B200GS_GATHER_MAX_TENSORS];
@@ -142,6 +167,25 @@ int b200gs_adam_multi(int n_tensors, const b200gs_adam_tensor* tensors, double b
         done += n;
     }
     return check_launch("adam_multi");
+}
+
+int b200gs_adam_sh(long long P, int M, const b200gs_adam_tensor* dc, const b200gs_adam_tensor* rest, const float* grad_pm3,
+                   double beta1, double beta2, double eps, b200gs_stream_t stream)
+{
+    if (P <= 0) return 0;
+    if (M < 2 || !dc || !rest || !grad_pm3 || !dc->param || !dc->exp_avg || !dc->exp_avg_sq || !rest->param || !rest->exp_avg || !rest->exp_avg_sq) {
+        set_error("adam_sh: null pointer or M < 2"); return -1;
+    }
+    if (dc->numel != 3 * P || rest->numel != 3LL * (M - 1) * P) { set_error("adam_sh: tensor sizes do not match [P,1,3] / [P,M-1,3]"); return -1; }
+    AdamShArgs a;
+    a.p_dc = dc->param; a.m_dc = dc->exp_avg; a.v_dc = dc->exp_avg_sq; a.p_rest = rest->param; a.m_rest = rest->exp_avg; a.v_rest = rest->exp_avg_sq;
+    a.grad = grad_pm3; a.P = P; a.M = M;
+    a.neg_step_dc = dc->neg_step_size; a.bcs_dc = dc->bias_correction2_sqrt; a.neg_step_rest = rest->neg_step_size; a.bcs_rest = rest->bias_correction2_sqrt;
+    a.beta1_c = (float)(1.0 - beta1); a.beta2 = (float)beta2; a.beta2_c = (float)(1.0 - beta2); a.eps = (float)eps;
+    long long blocks = (3LL * M * P + 255) / 256;
+    if (blocks > (long long)NUM_SMS * 16) blocks = (long long)NUM_SMS * 16;
+    adam_sh_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("adam_sh");
 }
 
 int b200gs_gather_rows_multi(int n_tensors, const b200gs_gather_tensor* tensors, const long long* index,

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 #include "rast_state.cuh"
 #include "../../include/b200gs.h"
 
@@ -21,6 +22,27 @@ int g_opt_hexplane_time_bwd = env_int("B200GS_HEXPLANE_TIME_BWD", 2);    // 0.41
 int g_opt_lookback_parallel = env_int("B200GS_LOOKBACK_PARALLEL", 1);    // 111 -> 103 us per 1M-pair sort (profiles/r2a_sort_check.txt)
 int g_opt_hexplane_time_fwd = env_int("B200GS_HEXPLANE_TIME_FWD", 2);    // 0.134 -> 0.112 ms, bit-identical
 int g_opt_mlp_bwd_ablate = 0;                                             // timing experiments only (wrong results); never from the environment
+
+// ---- opt-in phase timing ---------------------------------------------------------------------------------------------
+int g_prof_enabled = 0;
+static const char* const PROF_NAMES[PROF_SLOTS] = {"preprocess_fwd", "depth_sort", "emit_instances", "tile_sort", "tile_ranges",
+                                                   "composite_fwd", "composite_bwd", "preprocess_bwd"};
+struct ProfPair { cudaEvent_t a, b; };
+static std::vector<ProfPair> g_prof[PROF_SLOTS];          // recorded pairs per slot (only touched while profiling is enabled)
+static std::vector<ProfPair> g_prof_pool;
+void prof_mark(int slot, bool begin, cudaStream_t stream)
+{
+    if (slot < 0 || slot >= PROF_SLOTS) return;
+    if (begin) {
+        ProfPair p;
+        if (!g_prof_pool.empty()) { p = g_prof_pool.back(); g_prof_pool.pop_back(); }
+        else if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return;
+        cudaEventRecord(p.a, stream);
+        g_prof[slot].push_back(p);
+    } else if (!g_prof[slot].empty()) {
+        cudaEventRecord(g_prof[slot].back().b, stream);
+    }
+}
 
 void set_error(const char* fmt, ...)
 {
@@ -133,6 +155,36 @@ int b200gs_get_option(const char* name)
     if (name && !strcmp(name, "mlp_bwd_ablate")) return b200gs::g_opt_mlp_bwd_ablate;
     if (name && !strcmp(name, "lookback_parallel")) return b200gs::g_opt_lookback_parallel;
     if (name && !strcmp(name, "hexplane_time_fwd")) return b200gs::g_opt_hexplane_time_fwd;
+    return -1;
+}
+
+int b200gs_profile_enable(int enable)
+{
+    for (int s = 0; s < PROF_SLOTS; ++s) {               // (re)start from an empty record either way
+        for (auto& p : b200gs::g_prof[s]) b200gs::g_prof_pool.push_back(p);
+        b200gs::g_prof[s].clear();
+    }
+    b200gs::g_prof_enabled = enable != 0;
+    return 0;
+}
+
+int b200gs_profile_read(const char* phase, int* calls, float* total_ms)
+{
+    for (int s = 0; s < PROF_SLOTS; ++s) {
+        if (!phase || strcmp(phase, b200gs::PROF_NAMES[s])) continue;
+        float total = 0.f; int n = 0;
+        for (auto& p : b200gs::g_prof[s]) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(p.b) != cudaSuccess || cudaEventElapsedTime(&ms, p.a, p.b) != cudaSuccess) {
+                cudaGetLastError(); continue;
+            }
+            total += ms; ++n;
+        }
+        if (calls) *calls = n;
+        if (total_ms) *total_ms = total;
+        return 0;
+    }
+    set_error("b200gs_profile_read: unknown phase '%s'", phase ? phase : "(null)");
     return -1;
 }
 

@@ -24,6 +24,19 @@ int check_launch(const char* what);   // returns 0 or sets error and returns -1
 // opt-in kernel variants, see b200gs_set_option (api.cu)
 extern int g_opt_mlp_bwd_v2, g_opt_mlp_fwd_elect, g_opt_hexplane_time_bwd, g_opt_mlp_bwd_ablate, g_opt_lookback_parallel, g_opt_hexplane_time_fwd;
 
+// Opt-in phase timing (b200gs_profile_enable / b200gs_profile_read, api.cu): CUDA events recorded on the launching stream around
+// the kernels of one phase of a multi-kernel entry point, so that bench.py can report each kernel family's live duration
+// (preprocess, depth sort, emission, tile sort, compositing ...).  Disabled (the default): one predictable branch, no events.
+enum ProfSlot { PROF_PREPROCESS_FWD = 0, PROF_DEPTH_SORT, PROF_EMIT, PROF_TILE_SORT, PROF_TILE_RANGES, PROF_COMPOSITE_FWD,
+                PROF_COMPOSITE_BWD, PROF_PREPROCESS_BWD, PROF_SLOTS };
+extern int g_prof_enabled;
+void prof_mark(int slot, bool begin, cudaStream_t stream);
+struct ProfScope {
+    int slot; cudaStream_t stream;
+    ProfScope(int s, cudaStream_t st) : slot(s), stream(st) { if (g_prof_enabled) prof_mark(slot, true, stream); }
+    ~ProfScope() { if (g_prof_enabled) prof_mark(slot, false, stream); }
+};
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Bump allocator over a caller-owned byte buffer. 256-B alignment keeps every

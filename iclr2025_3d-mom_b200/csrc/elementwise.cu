@@ -90,6 +90,36 @@ __global__ void __launch_bounds__(256) l1_fwd_bwd_kernel(long long n, const floa
     }
 }
 
+// The same against the ground truth as the dataset holds it: uint8 HWC (a PIL image, scene/dataset_readers.py:1041), converted
+// on the device exactly like utils/general_utils.py:PILtoTorch does on the host (float(u8) / 255.0f, IEEE division): the view's
+// ground truth crosses PCIe as 3 B/pixel instead of 12.  render / d are CHW.
+__global__ void __launch_bounds__(256) l1_fwd_bwd_u8_kernel(int H, int W, const float* __restrict__ a, const unsigned char* __restrict__ gt,
+                                                            float scale, float* __restrict__ loss, float* __restrict__ d)
+{
+    float acc = 0.f;
+    const long long n = (long long)H * W;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float t = __fdiv_rn((float)__ldg(gt + 3 * i + c), 255.0f);
+            const float e = __ldg(a + c * n + i) - t;
+            acc += fabsf(e);
+            if (d) d[c * n + i] = e > 0.f ? scale : (e < 0.f ? -scale : 0.f);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ float part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += part[w];
+        atomicAdd(loss, s * scale);
+    }
+}
+
 // to8b of render_4DGS.py:49 / train_4DGS.py:335 on the device: out[y][x][c] = (uint8)(255 * clip(img[c][y][x], 0, 1))
 // (truncation, like numpy's astype), CHW float -> HWC bytes; 12 B read + 3 B written per pixel.
 __global__ void __launch_bounds__(256) to8b_hwc_kernel(int H, int W, const float* __restrict__ img, unsigned char* __restrict__ out)
@@ -143,6 +173,17 @@ int b200gs_l1_loss_fwd_bwd(long long n, const float* render, const float* target
     if (blocks < 1) blocks = 1;
     l1_fwd_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, render, target, scale, loss_accum, d_render);
     return check_launch("l1_loss");
+}
+
+int b200gs_l1_loss_fwd_bwd_u8(int H, int W, const float* render_chw, const unsigned char* target_hwc, float scale, float* loss_accum,
+                              float* d_render_chw, b200gs_stream_t stream)
+{
+    if (H <= 0 || W <= 0) return 0;
+    if (!render_chw || !target_hwc || !loss_accum) { set_error("l1_loss_u8: null pointer"); return -1; }
+    long long blocks = ((long long)H * W + 255) / 256;
+    if (blocks > (long long)NUM_SMS * 8) blocks = (long long)NUM_SMS * 8;
+    l1_fwd_bwd_u8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(H, W, render_chw, target_hwc, scale, loss_accum, d_render_chw);
+    return check_launch("l1_loss_u8");
 }
 
 int b200gs_to8b_hwc(int H, int W, const float* image_chw, unsigned char* out_hwc, b200gs_stream_t stream)

@@ -530,11 +530,14 @@ int rast_backward(int P, int D, int M, long long R, int W, int H, const float* b
     const int passes = radix_plan((size_t)R, 0, tile_bits).passes;
     const u32* sorted_list = (R > 0 && (passes & 1)) ? b.ivals_b : b.ivals_a;
 
-    cudaMemsetAsync(grad_arena, 0, (size_t)P * ACC * sizeof(float), stream);
-    if (R > 0)
-        composite_bwd_kernel<<<(unsigned)tiles, TILE_PIXELS, 0, stream>>>(
-            img.ranges, sorted_list, W, H, grid_x, g.recA, g.recB, g.recC, bg, img.final_T, img.n_contrib,
-            dL_dpix, dL_dpix_depth, grad_arena);
+    {
+        ProfScope prof(PROF_COMPOSITE_BWD, stream);
+        cudaMemsetAsync(grad_arena, 0, (size_t)P * ACC * sizeof(float), stream);
+        if (R > 0)
+            composite_bwd_kernel<<<(unsigned)tiles, TILE_PIXELS, 0, stream>>>(
+                img.ranges, sorted_list, W, H, grid_x, g.recA, g.recB, g.recC, bg, img.final_T, img.n_contrib,
+                dL_dpix, dL_dpix_depth, grad_arena);
+    }
 
     PreBwdArgs a;
     a.P = P; a.D = D; a.M = M; a.W = W; a.H = H;
@@ -551,6 +554,7 @@ int rast_backward(int P, int D, int M, long long R, int W, int H, const float* b
     a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;
     const size_t smem = a.dL_dsh ? (size_t)PB_WARPS * 32 * (3 * M + 1) * sizeof(float) : 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ProfScope prof(PROF_PREPROCESS_BWD, stream);
     preprocess_bwd_kernel<<<(P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, smem, stream>>>(a);
     return check_launch("rast_backward");
 }

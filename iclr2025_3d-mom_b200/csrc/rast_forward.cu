@@ -619,16 +619,32 @@ int rast_forward_stage1(int P, int D, int M, int W, int H, const float* means3D,
         if (smem > 200 * 1024) { set_error("rast_forward: too many SH coefficients"); return -1; }
         cudaFuncSetAttribute(preprocess_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
-    preprocess_fwd_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, smem, stream>>>(a);
+    {
+        ProfScope prof(PROF_PREPROCESS_FWD, stream);
+        preprocess_fwd_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, smem, stream>>>(a);
+    }
     if (check_launch("preprocess_fwd")) return -1;
     // The one device->host read of the forward pass (the reference does the same blocking
     // 4-byte copy at rasterizer_impl.cu:282): the caller sizes the binning buffer from it.
+    // The depth sort of the Gaussians does not depend on that count, so it is queued BEHIND the copy and the host waits on an
+    // event recorded between the two: the GPU sorts while the host reads the counters, allocates and launches stage 2.
+    static thread_local cudaEvent_t ev_read = nullptr;
     if (host_counters) {
+        if (!ev_read && cudaEventCreateWithFlags(&ev_read, cudaEventDisableTiming) != cudaSuccess) { check_launch("rast_forward_stage1 event"); return -1; }
         if (cudaMemcpyAsync(host_counters, g.counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
-            cudaStreamSynchronize(stream) != cudaSuccess) {
+            cudaEventRecord(ev_read, stream) != cudaSuccess) {
             check_launch("rast_forward_stage1 readback");
             return -1;
         }
+    }
+    // depth order of the Gaussians (stable; culled ones carry key 0xFFFFFFFF and sink); which side holds the result depends
+    // on P only (stage 2 recomputes it)
+    {
+        ProfScope prof(PROF_DEPTH_SORT, stream);
+        if (radix_sort_pairs(g.depth_key, g.order_iota, g.gkeys_b, g.gvals_b, (size_t)P, 0, 32, g.sort_temp, g.sort_temp_bytes, stream) < 0) return -1;
+    }
+    if (host_counters) {
+        if (cudaEventSynchronize(ev_read) != cudaSuccess) { check_launch("rast_forward_stage1 readback"); return -1; }
         if (host_counters[0] >= (1ull << 30)) { set_error("rast_forward: %llu instances exceed the 2^30 limit", host_counters[0]); return -1; }
     }
     return 0;
@@ -648,13 +664,13 @@ int rast_forward_stage2(int P, long long R, long long n_visible, int W, int H, c
     cudaMemsetAsync(img.ranges, 0, d.tiles * sizeof(uint2), stream);
     const u32* sorted_list = b.ivals_a;
     if (P > 0 && R > 0) {
-        // 1. depth order of the Gaussians (stable; culled ones carry key 0xFFFFFFFF and sink)
-        int side = radix_sort_pairs(g.depth_key, g.order_iota, b.gkeys_b, b.gvals_b, (size_t)P, 0, 32,
-                                    b.sort_temp, b.sort_temp_bytes, stream);
-        if (side < 0) return -1;
-        const u32* sorted_gid = side ? b.gvals_b : g.order_iota;
+        // 1. depth order of the Gaussians: sorted by stage 1 (queued behind its counter read-back)
+        int side = radix_plan((size_t)P, 0, 32).passes & 1;
+        const u32* sorted_gid = side ? g.gvals_b : g.order_iota;
         // 2. (tile, gaussian) instances in depth order
         const u32 nblk = (u32)((n_visible + 255) / 256);
+        {
+        ProfScope prof(PROF_EMIT, stream);
         cudaMemsetAsync(b.emit_status, 0, ((size_t)nblk + 1) * sizeof(u64), stream);
         cudaMemsetAsync(b.emit_ticket, 0, 64 * sizeof(u32), stream);
         if (g_opt_lookback_parallel != 0)
@@ -663,15 +679,21 @@ int rast_forward_stage2(int P, long long R, long long n_visible, int W, int H, c
         else
             emit_instances_kernel<false><<<nblk, 256, 0, stream>>>(sorted_gid, (u32)n_visible, g.tiles_touched, g.rect,
                                                                    d.grid_x, b.ikeys_a, b.ivals_a, b.emit_status, b.emit_ticket);
+        }
         // 3. stable sort by tile id => (tile, depth, index) order
-        side = radix_sort_pairs(b.ikeys_a, b.ivals_a, b.ikeys_b, b.ivals_b, (size_t)R, 0, d.tile_bits,
-                                b.sort_temp, b.sort_temp_bytes, stream);
+        {
+            ProfScope prof(PROF_TILE_SORT, stream);
+            side = radix_sort_pairs(b.ikeys_a, b.ivals_a, b.ikeys_b, b.ivals_b, (size_t)R, 0, d.tile_bits,
+                                    b.sort_temp, b.sort_temp_bytes, stream);
+        }
         if (side < 0) return -1;
         const u32* sorted_tile = side ? b.ikeys_b : b.ikeys_a;
         sorted_list = side ? b.ivals_b : b.ivals_a;
         // 4. per-tile ranges
+        ProfScope prof(PROF_TILE_RANGES, stream);
         tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(sorted_tile, (u32)R, img.ranges);
     }
+    ProfScope prof(PROF_COMPOSITE_FWD, stream);
     // 5. compositing (runs for empty scenes too: background only)
     composite_fwd_kernel<<<(unsigned)d.tiles, TILE_PIXELS, 0, stream>>>(
         img.ranges, sorted_list, W, H, d.grid_x, g.recA, g.recB, g.recC, bg, img.final_T, img.n_contrib,

@@ -22,6 +22,9 @@ struct GeomState {
     float*  cov3D;         // [6P]
     unsigned char* clamped;// [P] bit c set <=> channel c was clamped at 0
     unsigned long long* counters; // [4]: num_rendered, num_visible, -, -
+    u32*    gkeys_b;       // [P] ping-pong of the depth sort (stage 1 queues the sort behind the counter read-back)
+    u32*    gvals_b;       // [P]
+    void*   sort_temp; size_t sort_temp_bytes;     // histograms / look-back state of the depth sort
     static GeomState carve(void* buf, size_t P, size_t* bytes) {
         Carver c(buf);
         GeomState g;
@@ -35,14 +38,16 @@ struct GeomState {
         g.cov3D = c.take<float>(6 * P);
         g.clamped = c.take<unsigned char>(P);
         g.counters = c.take<unsigned long long>(4);
+        g.gkeys_b = c.take<u32>(P);
+        g.gvals_b = c.take<u32>(P);
+        g.sort_temp_bytes = radix_plan(P, 0, 32).temp_bytes;
+        g.sort_temp = c.take<char>(g.sort_temp_bytes);
         if (bytes) *bytes = c.used();
         return g;
     }
 };
 
 struct BinState {
-    u32* gkeys_b;          // [P] ping-pong for the depth sort
-    u32* gvals_b;          // [P]
     u32* ikeys_a;          // [R] tile id per instance (unsorted, depth order)
     u32* ivals_a;          // [R] gaussian id per instance
     u32* ikeys_b;          // [R]
@@ -54,17 +59,13 @@ struct BinState {
     static BinState carve(void* buf, size_t P, size_t R, int tile_bits, size_t* bytes) {
         Carver c(buf);
         BinState b;
-        b.gkeys_b = c.take<u32>(P);
-        b.gvals_b = c.take<u32>(P);
         b.ikeys_a = c.take<u32>(R);
         b.ivals_a = c.take<u32>(R);
         b.ikeys_b = c.take<u32>(R);
         b.ivals_b = c.take<u32>(R);
         b.emit_status = c.take<u64>((P + 255) / 256 + 1);
         b.emit_ticket = c.take<u32>(64);
-        size_t t1 = radix_plan(P, 0, 32).temp_bytes;
-        size_t t2 = radix_plan(R, 0, tile_bits).temp_bytes;
-        b.sort_temp_bytes = t1 > t2 ? t1 : t2;
+        b.sort_temp_bytes = radix_plan(R, 0, tile_bits).temp_bytes;
         b.sort_temp = c.take<char>(b.sort_temp_bytes);
         if (bytes) *bytes = c.used();
         return b;

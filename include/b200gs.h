@@ -53,6 +53,14 @@ int b200gs_version(void);
 int b200gs_set_option(const char* name, int value);
 int b200gs_get_option(const char* name);
 
+/* Opt-in phase timing for the multi-kernel rasterizer entry points (what bench.py's per-kernel roofline rows are measured with):
+ * while enabled, every call records CUDA events on the launching stream around each phase -- "preprocess_fwd", "depth_sort",
+ * "emit_instances", "tile_sort", "tile_ranges", "composite_fwd", "composite_bwd", "preprocess_bwd".  enable(1) / enable(0) both
+ * clear the record; read() synchronises on the recorded events and returns how many calls were recorded and their summed
+ * duration in milliseconds.  Process-wide, not thread-safe, off by default (no events are created or recorded then). */
+int b200gs_profile_enable(int enable);
+int b200gs_profile_read(const char* phase, int* calls, float* total_ms);
+
 /* ---------------------------------------------------------------------------------------
  * Rasterizer — replaces _C.rasterize_gaussians / rasterize_gaussians_backward / mark_visible
  * (RAST/ext.cpp:15-19; RAST/rasterize_points.cu:35-117, :119-202, :204-223) and underneath
@@ -170,6 +178,12 @@ typedef struct {
 } b200gs_adam_tensor;
 int b200gs_adam_multi(int n_tensors, const b200gs_adam_tensor* tensors /* host */, double beta1, double beta2,
                       double eps, b200gs_stream_t stream);
+
+/* The same step for the two SH tensors of scene/gaussian_model.py:136-140 (_features_dc [P,1,3], _features_rest [P,M-1,3]) with
+ * their gradient read from ONE [P,M,3] buffer -- the layout the rasterizer backward writes (RAST/cuda_rasterizer/backward.cu:20-139)
+ * -- so the per-step split of that gradient into two tensors never happens.  `grad` of the two descriptors is ignored. */
+int b200gs_adam_sh(long long P, int M, const b200gs_adam_tensor* dc, const b200gs_adam_tensor* rest, const float* grad_pm3,
+                   double beta1, double beta2, double eps, b200gs_stream_t stream);
 
 /* Densify / prune bookkeeping — replaces the per-tensor boolean-mask indexing and torch.cat
  * chains of scene/gaussian_model.py:424-482 (_prune_optimizer, cat_tensors_to_optimizer):
@@ -299,6 +313,11 @@ int b200gs_activations_backward(long long P, const float* scales_out, const floa
  * per-view share of train_4DGS.py:205-210's batch-mean L1. loss_accum is a device float the caller zeroes. */
 int b200gs_l1_loss_fwd_bwd(long long n, const float* render, const float* target, float scale, float* loss_accum, float* d_render,
                            b200gs_stream_t stream);
+/* The same against the ground truth as the dataset holds it -- uint8 [H,W,3] (scene/dataset_readers.py:1041), converted on the
+ * device the way utils/general_utils.py:PILtoTorch does on the host (float(u8) / 255.0f): 3 B/pixel cross PCIe instead of 12.
+ * render / d_render are [3,H,W]. */
+int b200gs_l1_loss_fwd_bwd_u8(int H, int W, const float* render_chw, const unsigned char* target_hwc, float scale, float* loss_accum,
+                              float* d_render_chw, b200gs_stream_t stream);
 
 /* to8b of render_4DGS.py:49 / train_4DGS.py:335 on the device: out_hwc[y][x][c] = (uint8)(255 * clip(image_chw[c][y][x], 0, 1)),
  * truncating like numpy's astype; [3,H,W] FP32 -> [H,W,3] bytes (the frame leaves the GPU as 3 B/pixel). */

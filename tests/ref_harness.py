@@ -114,6 +114,18 @@ def ref_backward(cam, bg, R, radii, dL_dcolor, dL_ddepth, means3D, shs=None, col
     return g
 
 
+def ref_mark_visible(cam, means3D):
+    """CudaRasterizer::Rasterizer::markVisible (rasterizer_impl.cu:141-153) -> bool[P]."""
+    L = rast()
+    P = means3D.shape[0]
+    out = torch.zeros(P, dtype=torch.bool, device=means3D.device)
+    torch.cuda.synchronize()
+    assert L.ref_mark_visible(P, means3D.contiguous().data_ptr(), cam.viewmatrix.data_ptr(), cam.projmatrix.data_ptr(),
+                              out.data_ptr()) == 0, L.ref_last_error()
+    torch.cuda.synchronize()
+    return out
+
+
 def ref_dist2(points):
     out = torch.zeros(points.shape[0], device=points.device)
     torch.cuda.synchronize()

@@ -106,9 +106,11 @@ def _run_sh(rank, world, port, ret, overlap):
                                         {"params": list(model._deformation.parameters()), "lr": 1e-3}], lr=0.0, eps=1e-15)
     tr = ViewParallelTrainer(model, torch.tensor([0.1, 0.2, 0.3]), stage="fine", world_size=world, rank=rank,
                              render_fn=fake_render_shs, shared_shs=True, overlap_sh_reduce=overlap)
-    assert tr.overlap_sh_reduce == (overlap and world > 1)
-    if tr.overlap_sh_reduce:      # SH slices at the end of the arena, outside the post-loop all-reduce
-        assert tr._reduce_end < tr.arena.numel() and model._features_rest in tr.trainable[-1:]
+    # shared SH tensor: the two SH parameters live outside the flat arena, their gradient is ONE [P,16,3] buffer reduced by its
+    # own collective (the "SH tail"; on CUDA it runs on a side stream from inside the last view's backward, on CPU after the loop)
+    assert not tr.overlap_sh_reduce                      # CPU: no side stream
+    assert len(tr.sh_params) == 2 and all(not any(p is q for q in tr.arena_params) for p in tr.sh_params)
+    assert sum(p.numel() for p in tr.arena_params) + 3 * 50 <= tr.arena.numel()
     cams = [0.5 + 0.25 * b for b in range(4)]
     g = torch.Generator().manual_seed(1)
     gts = [torch.rand(3, 5, 6, generator=g) for _ in range(4)]
@@ -123,8 +125,8 @@ def _run_sh(rank, world, port, ret, overlap):
 
 
 def test_overlapped_sh_reduce_equals_single_process():
-    """Opt-in path: the SH gradient reduced by its own (early, asynchronous) all-reduce and the rest of the arena by the
-    post-loop one give the same parameters as the single-process run and as the one-collective path."""
+    """The SH gradient reduced by its own all-reduce and the rest of the arena by the post-loop one give the same parameters
+    as the single-process run, whatever the overlap flag asks for."""
     mgr = mp.Manager()
     ret = mgr.dict()
     _run_sh(0, 1, 0, ret, False)

@@ -53,10 +53,8 @@ def _scene(P, W, H, mu, device="cuda"):
     return act, cam
 
 
-import os
-# BASELINE.json's full sizes: C3 (1M, 1280x720) always; C4 / C5 (1920x1080, 5M at 3840x2160) with B200GS_FULLSIZE=1
-_FULL = [(1000000, 1280, 720, 0.010)] + ([(1000000, 1920, 1080, 0.004), (5000000, 3840, 2160, 0.004)]
-                                         if os.environ.get("B200GS_FULLSIZE") else [])
+# BASELINE.json's full sizes: C3 (1M, 1280x720), C4 (1920x1080), C5 (5M at 3840x2160)
+_FULL = [(1000000, 1280, 720, 0.010), (1000000, 1920, 1080, 0.004), (5000000, 3840, 2160, 0.004)]
 
 
 @pytest.mark.parametrize("P,W,H,mu", [(2000, 64, 48, 0.02), (20000, 200, 120, 0.01), (200000, 512, 512, 0.004),
