@@ -11,6 +11,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200gs.so")
 
 _lib = None
+# cheap host-side event counts (what ran, how often): read by b200gs.launcher's exit summary and by tests
+import collections
+COUNTERS = collections.Counter()
 
 
 class B200GSError(RuntimeError):

@@ -143,6 +143,7 @@ class FusedAdam(Optimizer):
             from . import field as _field
             _field.drop_shared()
             torch.autograd.graph.increment_version(touched)
+        _lib.COUNTERS["adam_steps"] += 1
         for (beta1, beta2, eps), items in buckets.items():
             arr = (_AdamTensor * len(items))()
             for i, it in enumerate(items):

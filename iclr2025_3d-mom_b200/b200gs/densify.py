@@ -47,6 +47,7 @@ def gather_rows(tensors, index, n_out, out_rows=None):
 
 def prune_optimizer(optimizer, mask):
     """gaussian_model.py:424-442."""
+    _lib.COUNTERS["prune_events"] += 1
     index = torch.nonzero(mask, as_tuple=False).reshape(-1).contiguous()          # int64 rows to keep, ascending
     n_out = int(index.numel())
     jobs = []
@@ -78,6 +79,7 @@ def prune_optimizer(optimizer, mask):
 
 def cat_tensors_to_optimizer(optimizer, tensors_dict):
     """gaussian_model.py:461-482."""
+    _lib.COUNTERS["densify_cat_events"] += 1
     jobs = []
     for group in optimizer.param_groups:
         if len(group["params"]) > 1:

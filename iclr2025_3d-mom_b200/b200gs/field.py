@@ -149,15 +149,42 @@ def _check_cuda_f32(*ts):
             raise RuntimeError(f"expected float32, got {t.dtype}")
 
 
-def _times_arg(times, P):
-    """times_sel is a [P,1] tensor in the reference (gaussian_renderer/__init__.py:56)."""
+_lib.register("b200gs_uniform_value", ctypes.c_int, [ctypes.c_longlong, _P, _P, _P, _P])
+# The reference's render() repeats the camera's ONE timestamp into a [P,1] tensor (gaussian_renderer/__init__.py:56).  With this
+# switch on (default) a tensor timestamp is checked on the device -- one tiny kernel + an 8-byte read-back, i.e. a host sync a few
+# hundred microseconds before the one the rasterizer forward performs anyway -- and a uniform one takes the same one-timestamp
+# path as a Python float: time planes served from shared memory, their gradient reduced through 1-D rows.
+DETECT_UNIFORM_TIME = os.environ.get("B200GS_DETECT_UNIFORM_TIME", "1") != "0"
+_UNIFORM_BUF = {}
+
+
+def _uniform_time(t):
+    """t: contiguous float32 CUDA tensor -> its single value as a Python float if every element is bit-identical, else None."""
+    import struct
+    buf = _UNIFORM_BUF.get(t.device)
+    if buf is None:
+        buf = (torch.empty(2, dtype=torch.int32, device=t.device), torch.empty(2, dtype=torch.int32).pin_memory())
+        _UNIFORM_BUF[t.device] = buf
+    check(_lib.lib().b200gs_uniform_value(t.numel(), t.data_ptr(), buf[0].data_ptr(), buf[1].data_ptr(), current_stream()), "uniform_value")
+    if int(buf[1][0]) != 1:
+        return None
+    return struct.unpack("<f", struct.pack("<I", int(buf[1][1]) & 0xFFFFFFFF))[0]
+
+
+def _times_arg(times, P, detect=True):
+    """times_sel is a [P,1] tensor in the reference (gaussian_renderer/__init__.py:56).  Returns (per-point tensor or None, scalar)."""
     if torch.is_tensor(times):
         t = times.reshape(-1)
         if t.numel() == 1 and P != 1:
             t = t.expand(P)
         if t.numel() != P:
             raise RuntimeError("timestamps must have one entry per point")
-        return t.to(torch.float32).contiguous(), 0.0
+        t = t.to(torch.float32).contiguous()
+        if detect and DETECT_UNIFORM_TIME and t.is_cuda and P > 0:
+            v = _uniform_time(t)
+            if v is not None:
+                return None, v
+        return t, 0.0
     return None, float(times)
 
 
@@ -238,6 +265,7 @@ def begin_shared_step(net, xyz_param, inference=False):
     order = _cell_order(xyz, grid.aabb)
     check(_lib.lib().b200gs_hexplane_forward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(order), None, 0.0, MASK_SPATIAL, None,
                                                     S.data_ptr(), current_stream()), "hexplane_forward(spatial)")
+    _lib.COUNTERS["spatial_product_evaluations"] += 1
     _SHARED = {"key": _shared_key(xyz, xyz_param._version, P, grid.aabb, planes), "S": S, "A": None if inference else torch.zeros_like(S),
                "xyz_param": xyz_param, "grid": grid, "order": order, "used": False}
 
@@ -301,9 +329,10 @@ def _shared_for(xyz, P, aabb, planes):
 
 def drop_shared():
     """Forget the per-step / per-sequence spatial product (called by FusedAdam.step and by the trainer's error path)."""
-    global _SHARED, _INFER
+    global _SHARED, _INFER, _AUTO
     _SHARED = None
     _INFER = None
+    _AUTO = None
 
 
 # Opt-in (B200GS_INFERENCE_SPATIAL_CACHE=1 or field.INFERENCE_SPATIAL_CACHE = True; not yet run on a GPU): what
@@ -330,21 +359,90 @@ def _inference_shared(xyz, P, aabb, planes, levels, res, order):
         d = _hex_desc(aabb, planes, levels, res)
         check(_lib.lib().b200gs_hexplane_forward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(order), None, 0.0, MASK_SPATIAL, None,
                                                         S.data_ptr(), current_stream()), "hexplane_forward(spatial, inference cache)")
+        _lib.COUNTERS["spatial_product_evaluations"] += 1
         _INFER = {"key": key, "S": S, "A": None, "used": False, "order": order}
     return _INFER
+
+
+# ---- the same split under plain autograd (the reference's own training loop through the launcher) ---------------------------
+# train_4DGS.py:172-229 renders the views of a batch one after the other and calls loss.backward() ONCE.  The product of the
+# three spatial planes is an ordinary differentiable tensor S = _SpatialFn(xyz, planes): it is evaluated once per set of
+# parameter versions, every view's field call takes it as an input (time planes from shared memory, hexplane_time_*), autograd
+# sums the views' dL/dS and runs the spatial backward once.  The cached S dies with the backward pass that consumes it.
+AUTOGRAD_SPATIAL_SHARING = os.environ.get("B200GS_AUTOGRAD_SPATIAL_SHARING", "1") != "0"
+_AUTO = None
+
+
+def _drop_auto(*_):
+    global _AUTO
+    _AUTO = None
+
+
+class _SpatialFn(torch.autograd.Function):
+    """S[P, 32 levels] = product over the three spatial planes (xy, xz, yz) of the bilinear samples at xyz, per level."""
+
+    @staticmethod
+    def forward(ctx, xyz, aabb, levels, res, *planes):
+        xyz = xyz.contiguous()
+        _check_cuda_f32(xyz, aabb, *planes)
+        P = int(xyz.shape[0])
+        S = torch.empty((P, 32 * levels), dtype=torch.float32, device=xyz.device)
+        d = _hex_desc(aabb, planes, levels, res)
+        order = _cell_order(xyz, aabb)
+        check(_lib.lib().b200gs_hexplane_forward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(order), None, 0.0, MASK_SPATIAL, None,
+                                                        S.data_ptr(), current_stream()), "hexplane_forward(spatial)")
+        _lib.COUNTERS["spatial_product_evaluations"] += 1
+        ctx.save_for_backward(xyz, aabb, *planes)
+        ctx.meta = (levels, res)
+        ctx.order = order
+        ctx.params = planes
+        return S
+
+    @staticmethod
+    def backward(ctx, dS):
+        xyz, aabb, *planes = ctx.saved_tensors
+        levels, res = ctx.meta
+        P = int(xyz.shape[0])
+        dS = dS.contiguous()
+        direct = [_grad_target(q) if (k % 6) in (0, 1, 3) else None for k, q in enumerate(ctx.params)]
+        grads = [(dp if dp is not None else torch.zeros_like(p, memory_format=torch.preserve_format)) if (k % 6) in (0, 1, 3) else None
+                 for k, (p, dp) in enumerate(zip(planes, direct))]
+        d = _hex_desc(aabb, planes, levels, res, grads)
+        d_xyz = torch.empty_like(xyz)
+        check(_lib.lib().b200gs_hexplane_backward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(ctx.order), None, 0.0, MASK_SPATIAL,
+                                                         None, None, dS.data_ptr(), d_xyz.data_ptr(), None, 0, current_stream()),
+              "hexplane_backward(spatial)")
+        return (d_xyz, None, None, None, *[None if dp is not None else g for g, dp in zip(grads, direct)])
+
+
+def _auto_spatial(xyz, grid):
+    """The differentiable spatial product for this (xyz, planes, aabb) state: cached until a backward pass consumes it or any
+    of those tensors changes."""
+    global _AUTO
+    planes = grid._planes()
+    key = _shared_key(xyz, xyz._version, int(xyz.shape[0]), grid.aabb, planes)
+    if _AUTO is not None and _AUTO["key"] == key:
+        return _AUTO["S"]
+    S = _SpatialFn.apply(xyz, grid.aabb, len(grid.grids), tuple(grid._res), *planes)
+    if S.requires_grad:
+        S.register_hook(_drop_auto)          # its gradient is being produced: the graph below it is about to be freed
+    _AUTO = {"key": key, "S": S}
+    return S
 
 
 class _DeformFn(torch.autograd.Function):
     """(pts, scales, rot) = field(xyz, scales, rot, t, scene_flow, frame_num, delta_scale).
 
-    inputs: xyz, scales, rot, times, scene_flow, frame_num, delta_scale, aabb, levels, res, heads,
+    inputs: xyz, scales, rot, times, scene_flow, frame_num, delta_scale, aabb, levels, res, heads, S_in,
             w1, b1, (w2,b2,w3,b3) x 3 heads, *planes
+    S_in: None, or the differentiable spatial product of _SpatialFn (then only the time planes are sampled here and
+    dL/dS_in is returned for autograd to sum over the views of a batch).
     """
-    N_FIXED = 11
+    N_FIXED = 12
     N_W = 14
 
     @staticmethod
-    def forward(ctx, xyz, scales, rot, times, scene_flow, frame_num, delta_scale, aabb, levels, res, heads, *rest):
+    def forward(ctx, xyz, scales, rot, times, scene_flow, frame_num, delta_scale, aabb, levels, res, heads, S_in, *rest):
         weights, planes = rest[:_DeformFn.N_W], rest[_DeformFn.N_W:]
         xyz = xyz.contiguous(); scales = scales.contiguous(); rot = rot.contiguous(); scene_flow = scene_flow.contiguous()
         _check_cuda_f32(xyz, scales, rot, scene_flow, aabb, *planes, *[w for w in weights if w is not None])
@@ -352,12 +450,14 @@ class _DeformFn(torch.autograd.Function):
         P = int(xyz.shape[0])
         dev = xyz.device
         stream = current_stream()
-        tt, ts = _times_arg(times, P)
+        tt, ts = _times_arg(times, P, detect=False)          # (the caller has already looked for a uniform tensor)
         feat = torch.empty((P, 32 * levels), dtype=torch.float32, device=dev)
         d = _hex_desc(aabb, planes, levels, res)
         order = _cell_order(xyz, aabb)
         ctx.order = order
         sh = _shared_for(xyz, P, aabb, planes)
+        if sh is None and S_in is not None:
+            sh = {"S": S_in.contiguous(), "A": None, "used": False, "auto": True}
         if sh is None:
             sh = _inference_shared(xyz, P, aabb, planes, levels, res, order)
         ctx.shared = sh
@@ -375,6 +475,7 @@ class _DeformFn(torch.autograd.Function):
                 feat = torch.empty(((P + 127) // 128 * 128, 32 * levels), dtype=torch.float32, device=dev)
             check(L.b200gs_hexplane_time_forward(ctypes.byref(d), P, xyz.data_ptr(), None, ts, sh["S"].data_ptr(),
                                                  feat.data_ptr(), int(ctx.feat_tiled), stream), "hexplane_time_forward")
+            _lib.COUNTERS["time_row_forward_calls"] += 1
         elif sh is not None:      # spatial product from begin_shared_step; only the time planes are sampled per view
             sh["used"] = True
             check(L.b200gs_hexplane_forward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(order),
@@ -445,14 +546,21 @@ class _DeformFn(torch.autograd.Function):
         check(L.b200gs_deform_mlp_backward(ctypes.byref(mw), ctypes.byref(mg), P, feat.data_ptr(), saved.data_ptr(),
                                            cp(d_pts) if heads[0] else None, cp(d_scales) if heads[1] else None,
                                            cp(d_rot) if heads[2] else None, d_feat.data_ptr(), stream), "deform_mlp_backward")
-        gplanes = [dp if dp is not None else torch.zeros_like(p, memory_format=torch.preserve_format) for p, dp in zip(planes, direct_p)]
+        sh = ctx.shared
+        # the spatial planes receive nothing here when only the time planes were sampled (their share goes through S)
+        time_only = sh is not None
+        gplanes = [dp if dp is not None else (None if (time_only and (k % 6) in (0, 1, 3)) else torch.zeros_like(p, memory_format=torch.preserve_format))
+                   for k, (p, dp) in enumerate(zip(planes, direct_p))]
         d_xyz_grid = torch.empty_like(xyz)
         d = _hex_desc(aabb, planes, levels, res, gplanes)
-        sh = ctx.shared
+        d_S = None
         if ctx.time_rows:
             scratch, nbytes = _time_row_scratch(d, xyz.device)
+            if sh.get("auto"):
+                d_S = torch.zeros_like(sh["S"])          # this view's dL/dS; autograd sums the views and runs _SpatialFn.backward once
+            A = d_S if d_S is not None else sh["A"]
             check(L.b200gs_hexplane_time_backward(ctypes.byref(d), P, xyz.data_ptr(), None, ts, sh["S"].data_ptr(),
-                                                  sh["A"].data_ptr(), d_feat.data_ptr(), d_xyz_grid.data_ptr(), scratch.data_ptr(),
+                                                  A.data_ptr(), d_feat.data_ptr(), d_xyz_grid.data_ptr(), scratch.data_ptr(),
                                                   nbytes, int(ctx.feat_tiled), stream), "hexplane_time_backward")
         elif sh is not None or not has_t:
             # shared step: time planes now, the spatial planes' share is accumulated for finish_shared_step.
@@ -476,7 +584,7 @@ class _DeformFn(torch.autograd.Function):
                 for i in range(2 + 4 * h, 6 + 4 * h):
                     gw_out[i] = None
         gp_out = [None if dp is not None else g for g, dp in zip(gplanes, direct_p)]
-        return (d_xyz, d_scales, d_rot, None, None, None, None, None, None, None, None, *gw_out, *gp_out)
+        return (d_xyz, d_scales, d_rot, None, None, None, None, None, None, None, None, d_S, *gw_out, *gp_out)
 
 
 def _regulation_launch(field, weights, loss_accum, grads):
@@ -589,6 +697,13 @@ class HexPlaneField(nn.Module):
                 out.append(p)
         return out
 
+    def _time_rows_supported(self):
+        """Can the one-timestamp kernels (time planes pre-blended in shared memory) serve this configuration?"""
+        if self.aabb.is_cuda:
+            d = _hex_desc(self.aabb, self._planes(), len(self.grids), tuple(self._res))
+            return bool(_lib.lib().b200gs_hexplane_time_supported(ctypes.byref(d)))
+        return False
+
     def get_density(self, pts, timestamps=None):
         if timestamps is None:
             raise NotImplementedError("static (time-free) HexPlane queries are not on the reference's path")
@@ -677,9 +792,17 @@ class Deformation(nn.Module):
             delta_scale = 0.0
         # time_emb: the reference's [P,1] tensor (gaussian_renderer/__init__.py:56), or one Python float for the whole call
         t_arg = time_emb[:, :1] if torch.is_tensor(time_emb) else float(time_emb)
+        S_in = None
+        if torch.is_tensor(t_arg) and xyz.is_cuda:
+            # the reference's render() hands over the camera's ONE timestamp as a [P,1] tensor (gaussian_renderer/__init__.py:56)
+            tt, ts = _times_arg(t_arg, int(xyz.shape[0]))
+            t_arg = ts if tt is None else tt
+        if (AUTOGRAD_SPATIAL_SHARING and not torch.is_tensor(t_arg) and xyz.is_cuda and torch.is_grad_enabled() and _SHARED is None
+                and self.grid._time_rows_supported() and (xyz.requires_grad or self.grid.grids[0][0].requires_grad)):
+            S_in = _auto_spatial(xyz, self.grid)
         pts, scales, rotations = _DeformFn.apply(xyz, scales_emb[:, :3], rotations_emb[:, :4], t_arg, scene_flow,
                                                  frame_num, delta_scale, self.grid.aabb, len(self.grid.grids),
-                                                 tuple(self.grid._res), heads, *weights, *self.grid._planes())
+                                                 tuple(self.grid._res), heads, S_in, *weights, *self.grid._planes())
         opacity = opacity_emb[:, :1]
         shs = shs_emb
         return pts, scales, rotations, opacity, shs

@@ -67,6 +67,7 @@ class _CModule:
         if means3D.ndimension() != 2 or means3D.size(1) != 3:
             raise RuntimeError("means3D must have dimensions (num_points, 3)")
         L = _lib.lib()
+        _lib.COUNTERS["raster_forward_calls"] += 1
         P = int(means3D.size(0))
         H, W = int(image_height), int(image_width)
         dev = means3D.device

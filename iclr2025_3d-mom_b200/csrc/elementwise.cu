@@ -120,6 +120,17 @@ __global__ void __launch_bounds__(256) l1_fwd_bwd_u8_kernel(int H, int W, const 
     }
 }
 
+// Is every element of x bit-identical to x[0]?  out[0] = 1 / 0, out[1] = bits of x[0].  (gaussian_renderer/__init__.py:56 repeats
+// the camera's one timestamp into a [P,1] tensor; knowing that lets the field serve the time planes from shared memory.)
+__global__ void __launch_bounds__(256) uniform_check_kernel(long long n, const unsigned int* __restrict__ x, unsigned int* __restrict__ out)
+{
+    const unsigned int first = __ldg(x);
+    bool same = true;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) same &= __ldg(x + i) == first;
+    if (!__all_sync(0xffffffffu, same) && (threadIdx.x & 31) == 0) out[0] = 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[1] = first;
+}
+
 // to8b of render_4DGS.py:49 / train_4DGS.py:335 on the device: out[y][x][c] = (uint8)(255 * clip(img[c][y][x], 0, 1))
 // (truncation, like numpy's astype), CHW float -> HWC bytes; 12 B read + 3 B written per pixel.
 __global__ void __launch_bounds__(256) to8b_hwc_kernel(int H, int W, const float* __restrict__ img, unsigned char* __restrict__ out)
@@ -184,6 +195,23 @@ int b200gs_l1_loss_fwd_bwd_u8(int H, int W, const float* render_chw, const unsig
     if (blocks > (long long)NUM_SMS * 8) blocks = (long long)NUM_SMS * 8;
     l1_fwd_bwd_u8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(H, W, render_chw, target_hwc, scale, loss_accum, d_render_chw);
     return check_launch("l1_loss_u8");
+}
+
+int b200gs_uniform_value(long long n, const float* x, unsigned int* scratch_dev2, unsigned int* host_pinned2, b200gs_stream_t stream)
+{
+    if (n <= 0 || !x || !scratch_dev2 || !host_pinned2) { set_error("uniform_value: empty input or null pointer"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned int init[2] = {1u, 0u};
+    host_pinned2[0] = init[0]; host_pinned2[1] = init[1];
+    if (cudaMemcpyAsync(scratch_dev2, host_pinned2, 8, cudaMemcpyHostToDevice, st) != cudaSuccess) return check_launch("uniform_value") ? -1 : -1;
+    long long blocks = (n + 255) / 256;
+    if (blocks > (long long)NUM_SMS * 8) blocks = (long long)NUM_SMS * 8;
+    uniform_check_kernel<<<(unsigned)blocks, 256, 0, st>>>(n, reinterpret_cast<const unsigned int*>(x), scratch_dev2);
+    if (cudaMemcpyAsync(host_pinned2, scratch_dev2, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        check_launch("uniform_value");
+        return -1;
+    }
+    return check_launch("uniform_value");
 }
 
 int b200gs_to8b_hwc(int H, int W, const float* image_chw, unsigned char* out_hwc, b200gs_stream_t stream)

@@ -319,6 +319,12 @@ int b200gs_l1_loss_fwd_bwd(long long n, const float* render, const float* target
 int b200gs_l1_loss_fwd_bwd_u8(int H, int W, const float* render_chw, const unsigned char* target_hwc, float scale, float* loss_accum,
                               float* d_render_chw, b200gs_stream_t stream);
 
+/* Is the [n] float tensor x one value repeated?  gaussian_renderer/__init__.py:56 hands the field the camera's single timestamp as
+ * a materialised [P,1] tensor; when it is uniform the field takes its one-timestamp fast path (time planes from shared memory).
+ * scratch_dev2: 8 bytes of device memory; host_pinned2: 8 bytes of PINNED host memory, on return [0] = 1 if uniform else 0,
+ * [1] = the bits of x[0].  HOST SYNC: waits for the stream (the second documented one next to b200gs_rast_forward_stage1). */
+int b200gs_uniform_value(long long n, const float* x, unsigned int* scratch_dev2, unsigned int* host_pinned2, b200gs_stream_t stream);
+
 /* to8b of render_4DGS.py:49 / train_4DGS.py:335 on the device: out_hwc[y][x][c] = (uint8)(255 * clip(image_chw[c][y][x], 0, 1)),
  * truncating like numpy's astype; [3,H,W] FP32 -> [H,W,3] bytes (the frame leaves the GPU as 3 B/pixel). */
 int b200gs_to8b_hwc(int H, int W, const float* image_chw, unsigned char* out_hwc, b200gs_stream_t stream);

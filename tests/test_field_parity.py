@@ -55,12 +55,16 @@ _FULL = [([1, 2], 50, 1000000)]      # BASELINE.json C3 point count (always on: 
 
 
 @pytest.mark.parametrize("multires,T,P", [([1, 2], 50, 5000), ([1, 2], 50, 64), ([1, 2], 50, 1), ([1, 2, 4, 8], 25, 3001),
-                                          ([1, 2], 50, 40003)] + _FULL)   # >= 16384 points: cell-ordered traversal
+                                          ([1, 2], 50, 40003), ([1, 2], 50, -5000), ([1, 2], 50, -40003)] + _FULL)   # >= 16384 points: cell-ordered traversal
 def test_deform_network_forward_backward(multires, T, P):
+    # P < 0: |P| points with a DIFFERENT timestamp per point (the general [P,1] tensor of gaussian_renderer/__init__.py:56);
+    # otherwise the camera's one timestamp repeated, which field.DETECT_UNIFORM_TIME routes to the one-timestamp kernels
+    per_point_time = P < 0
+    P = abs(P)
     net = _model(multires, T)
     levels = len(multires)
     xyz, scales, rot, opacity, shs, flow = _inputs(P)
-    time = torch.full((P, 1), 0.37, device="cuda")
+    time = torch.rand(P, 1, generator=torch.Generator().manual_seed(9)).cuda() if per_point_time else torch.full((P, 1), 0.37, device="cuda")
     frame_num = torch.tensor(22, device="cuda")
     sd = {k: v.detach().clone().contiguous().requires_grad_(v.dtype.is_floating_point) for k, v in net.state_dict().items()}
 
