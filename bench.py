@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--render-frames", type=int, default=60, help="frames per camera path of the render block (0 = skip)")
     ap.add_argument("--no-raster-only", action="store_true", help="skip the config-2 rasterizer-only block")
+    ap.add_argument("--no-launcher-path", action="store_true", help="skip the block that runs the reference's unchanged train_4DGS.py through the launcher")
     ap.add_argument("--no-shared-spatial", action="store_true",
                     help="render every frame with the full six-plane HexPlane pass instead of sharing the spatial product over a sequence")
     ap.add_argument("--cpu-points", type=int, default=0, help="override the cpu_baseline sample size")
@@ -446,6 +447,49 @@ def raster_only_block(args, device, impl):
         del raw, act
         torch.cuda.empty_cache()
     return out
+
+
+# ---- the reference's own scripts through the launcher --------------------------------------------------
+def launcher_path_block(args):
+    """The boundary on hardware: the reference's UNCHANGED train_4DGS.py (baseline/_ref, installed by tools/install_reference.sh
+    where /root/reference exists) run by `python -m b200gs.launcher` on the synthetic stage-1 stand-in (tools/make_synthetic_mom.py):
+    210k initial Gaussians, 320x192, batch_size 2, 40 coarse + 120 fine iterations with densification and pruning.  iters/s is
+    measured between the first and the last optimizer.step() of the run (so it includes everything the script does per
+    iteration: its Python, the loss, densify / prune, tqdm), not the process start-up or data loading."""
+    import re
+    import shutil
+    import tempfile
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "scene")):
+        return {"unavailable": "baseline/_ref not installed"}
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_synthetic_mom as mm
+    tmp = tempfile.mkdtemp(prefix="b200gs_launcher_")
+    try:
+        out = os.path.join(tmp, "scene")
+        mm.write(out, points=210000, width=320, height=192, views=5, video_frames=60)
+        cfg = mm.write_config(os.path.join(tmp, "short.py"), coarse_iterations=40, iterations=120, batch_size=2)
+        env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "iclr2025_3d-mom_b200") + os.pathsep + os.environ.get("PYTHONPATH", ""),
+                   B200GS_LAUNCHER_LOG="1")
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        t0 = time.perf_counter()
+        r = subprocess.run([sys.executable, "-m", "b200gs.launcher", "--reference", ref, "train_4DGS.py", "--input_dir", out, "--configs", cfg,
+                            "--expname", "synthetic", "--model_path", out, "--port", "6124", "--save_iterations", "120", "--test_iterations", "100000",
+                            "--video_iterations", "100000", "--quiet"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+        wall = time.perf_counter() - t0
+        m = re.search(r"\[b200gs\] launcher summary: (.*)", r.stdout + r.stderr)
+        if r.returncode != 0 or not m:
+            return {"failed": (r.stdout + r.stderr)[-600:]}
+        summary = dict(kv.split("=") for kv in m.group(1).split())
+        return {"script": "train_4DGS.py (unchanged, baseline/_ref) via b200gs.launcher", "iters_per_s": float(summary["iters_per_s"]),
+                "view_iters_per_s": 2 * float(summary["iters_per_s"]), "iterations": int(summary["adam_steps"]), "batch_size": 2,
+                "points_initial": 210000, "image": "320x192", "process_wall_s": round(wall, 2),
+                "densify_cat_events": int(summary["densify_cat_events"]), "prune_events": int(summary["prune_events"]),
+                "time_row_forward_calls": int(summary["time_row_forward_calls"]),
+                "spatial_product_evaluations": int(summary["spatial_product_evaluations"])}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 # ---- cpu baselines ---------------------------------------------------------------------------------
@@ -943,6 +987,12 @@ def _main():
             res["raster_only"] = raster_only_block(args, device, impl)
         except Exception as ex:
             res["raster_only"] = {"failed": f"{type(ex).__name__}: {ex}"}
+    if impl == "b200" and world == 1 and not args.no_launcher_path:
+        torch.cuda.empty_cache()
+        try:
+            res["launcher_path"] = launcher_path_block(args)
+        except Exception as ex:
+            res["launcher_path"] = {"failed": f"{type(ex).__name__}: {ex}"}
     if impl != "b200":
         res["impl"] = "reference"
         res["reference_stack"] = "reference CUDA rasterizer (oracle/_ref, unmodified) + PyTorch port of HexPlane/deformation + torch.optim.Adam, on GPU"

@@ -14,6 +14,7 @@ _lib = None
 # cheap host-side event counts (what ran, how often): read by b200gs.launcher's exit summary and by tests
 import collections
 COUNTERS = collections.Counter()
+TIMES = {}
 
 
 class B200GSError(RuntimeError):

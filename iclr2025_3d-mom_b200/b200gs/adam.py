@@ -122,7 +122,13 @@ class FusedAdam(Optimizer):
                     state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 m, v = state["exp_avg"], state["exp_avg_sq"]
                 if not _dense(p):
-                    raise RuntimeError("FusedAdam needs dense (contiguous or channels_last) parameters")
+                    # e.g. the reference's _xyz right after create_from_pcd: torch.tensor(pcd_points.T) keeps numpy's
+                    # column-major strides (scene/gaussian_model.py:153) until the first densify / prune re-builds it.
+                    # Same Parameter object, same values, row-major storage from here on (moments follow below).
+                    p.data = p.data.contiguous()
+                    if g is not None and not _same_layout(g, p):
+                        g = g.contiguous()
+                        p.grad = g
                 if not _same_layout(m, p):
                     m = torch.empty_like(p).copy_(m); state["exp_avg"] = m
                 if not _same_layout(v, p):
@@ -144,6 +150,10 @@ class FusedAdam(Optimizer):
             _field.drop_shared()
             torch.autograd.graph.increment_version(touched)
         _lib.COUNTERS["adam_steps"] += 1
+        import time as _time
+        now = _time.perf_counter()
+        _lib.TIMES.setdefault("first_adam_step", now)
+        _lib.TIMES["last_adam_step"] = now
         for (beta1, beta2, eps), items in buckets.items():
             arr = (_AdamTensor * len(items))()
             for i, it in enumerate(items):

@@ -111,9 +111,11 @@ def _print_summary(gm):
     from . import _lib
     c = _lib.COUNTERS
     print("[b200gs] launcher summary: field=%s optimizer=%s adam_steps=%d densify_cat_events=%d prune_events=%d raster_forward_calls=%d "
-          "time_row_forward_calls=%d spatial_product_evaluations=%d"
+          "time_row_forward_calls=%d spatial_product_evaluations=%d iters_per_s=%.3f"
           % (_print_summary.field, _print_summary.optimizer, c["adam_steps"], c["densify_cat_events"], c["prune_events"],
-             c["raster_forward_calls"], c["time_row_forward_calls"], c["spatial_product_evaluations"]), file=sys.stderr, flush=True)
+             c["raster_forward_calls"], c["time_row_forward_calls"], c["spatial_product_evaluations"],
+             (c["adam_steps"] - 1) / max(_lib.TIMES.get("last_adam_step", 0.0) - _lib.TIMES.get("first_adam_step", 0.0), 1e-9)
+             if c["adam_steps"] > 1 else 0.0), file=sys.stderr, flush=True)
 
 
 _print_summary.field = "none"

@@ -36,7 +36,7 @@ def test_unchanged_train_and_render_scripts_run_through_the_launcher(tmp_path):
     for rel, want in sums.items():
         assert hashlib.sha256(open(os.path.join(REF, rel), "rb").read()).hexdigest() == want, rel
     out = str(tmp_path / "scene")
-    mm.write(out, points=210000, width=320, height=192, views=5, video_frames=8)
+    mm.write(out, points=210000, width=320, height=192, views=5, video_frames=60)
     cfg = mm.write_config(str(tmp_path / "short.py"), coarse_iterations=60, iterations=160, batch_size=2)
     r = _run("train_4DGS.py", ["--input_dir", out, "--configs", cfg, "--expname", "synthetic", "--model_path", out, "--port", "6123",
                                "--save_iterations", "160", "--test_iterations", "100000", "--video_iterations", "100000"], None)

@@ -8,7 +8,7 @@ so that the reference's own scripts can be run, unchanged, on a box without the 
 The images are procedural (smooth colour fields + blobs that drift with the frame index): enough for the optimisation to have
 something to fit and for densify / prune to fire; they are not meant to look like anything.
 
-    python tools/make_synthetic_mom.py <out_dir> [--points 210000] [--width 320] [--height 192] [--views 5] [--video-frames 8]
+    python tools/make_synthetic_mom.py <out_dir> [--points 210000] [--width 320] [--height 192] [--views 5] [--video-frames 60]
 """
 import argparse
 import math
@@ -48,7 +48,7 @@ def _c2w_opengl(angle_y, offset, distance):
     return m
 
 
-def write(out_dir, points=210000, width=320, height=192, views=5, video_frames=8, seed=6666, distance=4.5):
+def write(out_dir, points=210000, width=320, height=192, views=5, video_frames=60, seed=6666, distance=4.5):
     mom = os.path.join(out_dir, "MOM")
     os.makedirs(os.path.join(mom, "video"), exist_ok=True)
     rng = np.random.default_rng(seed)
@@ -94,6 +94,6 @@ if __name__ == "__main__":
     ap.add_argument("--width", type=int, default=320)
     ap.add_argument("--height", type=int, default=192)
     ap.add_argument("--views", type=int, default=5)
-    ap.add_argument("--video-frames", type=int, default=8)
+    ap.add_argument("--video-frames", type=int, default=60)
     a = ap.parse_args()
     print(write(a.out_dir, a.points, a.width, a.height, a.views, a.video_frames))
