@@ -422,6 +422,8 @@ class ViewParallelTrainer:
             for vi, (cam, gt) in enumerate(zip(cams, gts)):
                 pkg = self.render_fn(cam, m, self.bg, self.stage, shs) if self.shared_shs else \
                     self.render_fn(cam, m, self.bg, self.stage)
+                # (before the backward: the SH tail, which reduces max_radii over the ranks, starts from inside the LAST one)
+                torch.maximum(self.max_radii, pkg["radii"], out=self.max_radii)
                 _field.ACCUMULATE_INTO_GRAD = self.shared_shs     # p.grad are arena views: let the field kernels add into them
                 on_gpu = shs is not None and shs.is_cuda
                 _rast.SH_GRAD_ACCUMULATOR = self.sh_grad if on_gpu else None
@@ -450,7 +452,6 @@ class ViewParallelTrainer:
                 vg = pkg["viewspace_points"].grad
                 if vg is not None:
                     self.viewspace_grad += vg
-                torch.maximum(self.max_radii, pkg["radii"], out=self.max_radii)
                 if loss is not None:
                     total = loss.detach() if total is None else total + loss.detach()
         except BaseException:

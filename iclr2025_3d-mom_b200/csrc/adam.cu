@@ -124,8 +124,61 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const __grid_constant_
         const unsigned long long local = e - tab.first_elem[ti];
         const unsigned long long row = local / (unsigned)T.row_floats;
         const unsigned int col = (unsigned int)(local - row * (unsigned)T.row_floats);
+        if (T.zero_tail_rows > 0 && (long long)row >= tab.n_out - T.zero_tail_rows) { T.dst[local] = 0.f; continue; }     // new rows of an Adam moment
         const long long src_row = tab.index ? tab.index[row] : (long long)row;
         T.dst[local] = __ldg(T.src + (size_t)src_row * T.row_floats + col);
+    }
+}
+
+// ---- densify / prune decisions (scene/gaussian_model.py:681-698, :511-523, :541-565, :713-715, :362-365) ----------------------
+// One pass over the Gaussians each; the arithmetic follows the torch expressions of the reference operator for operator
+// (accurate expf / logf / division, no fast-math), so the same Gaussians are selected.
+__global__ void __launch_bounds__(256) densify_select_kernel(long long N, const float* __restrict__ accum, const float* __restrict__ denom,
+                                                             const float* __restrict__ scaling, float thr, float dense_extent,
+                                                             unsigned char* __restrict__ clone_flag, unsigned char* __restrict__ split_flag)
+{
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < N; i += (long long)gridDim.x * 256) {
+        float g = __fdiv_rn(__ldg(accum + i), __ldg(denom + i));          // grads = xyz_gradient_accum / denom
+        if (g != g) g = 0.f;                                              // grads[grads.isnan()] = 0.0
+        const float smax = fmaxf(fmaxf(__ldg(scaling + 3 * i), __ldg(scaling + 3 * i + 1)), __ldg(scaling + 3 * i + 2));
+        const float world = expf(smax);                                   // max(get_scaling): exp is monotone, max commutes with it
+        clone_flag[i] = (fabsf(g) >= thr) && (world <= dense_extent);     // torch.norm(grads, dim=-1) >= thr  &  max scale <= percent_dense * extent
+        split_flag[i] = (g >= thr) && (world > dense_extent);             // padded_grad >= thr  &  max scale > percent_dense * extent
+    }
+}
+
+__global__ void __launch_bounds__(256) prune_select_kernel(long long N, const float* __restrict__ opacity, const float* __restrict__ scaling,
+                                                           const float* __restrict__ max_radii2D, float min_opacity, float max_screen_size,
+                                                           float max_world, unsigned char* __restrict__ prune_flag)
+{
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < N; i += (long long)gridDim.x * 256) {
+        const float o = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-__ldg(opacity + i))));      // torch.sigmoid
+        bool p = o < min_opacity;
+        if (max_screen_size > 0.f) {
+            const float smax = fmaxf(fmaxf(__ldg(scaling + 3 * i), __ldg(scaling + 3 * i + 1)), __ldg(scaling + 3 * i + 2));
+            p = p || (__ldg(max_radii2D + i) > max_screen_size) || (expf(smax) > max_world);
+        }
+        prune_flag[i] = p;
+    }
+}
+
+__global__ void __launch_bounds__(256) densification_stats_kernel(long long N, const float* __restrict__ vgrad, const unsigned char* __restrict__ filter,
+                                                                  float* __restrict__ accum, float* __restrict__ denom)
+{
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < N; i += (long long)gridDim.x * 256) {
+        if (!filter[i]) continue;
+        const float x = __ldg(vgrad + 3 * i), y = __ldg(vgrad + 3 * i + 1);
+        accum[i] = __fadd_rn(accum[i], __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))));     // += norm(grad[:, :2])
+        denom[i] = __fadd_rn(denom[i], 1.f);
+    }
+}
+
+__global__ void __launch_bounds__(256) reset_opacity_kernel(long long N, const float* __restrict__ opacity, float* __restrict__ out)
+{
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < N; i += (long long)gridDim.x * 256) {
+        const float o = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-__ldg(opacity + i))));
+        const float c = fminf(o, 0.01f);                                  // torch.min(get_opacity, ones * 0.01)
+        out[i] = logf(__fdiv_rn(c, __fsub_rn(1.f, c)));                   // inverse_sigmoid
     }
 }
 
@@ -216,6 +269,48 @@ int b200gs_gather_rows_multi(int n_tensors, const b200gs_gather_tensor* tensors,
         done += n;
     }
     return check_launch("gather_rows_multi");
+}
+
+static unsigned blocks_for(long long n)
+{
+    long long b = (n + 255) / 256;
+    if (b > (long long)NUM_SMS * 16) b = (long long)NUM_SMS * 16;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+int b200gs_densify_select(long long N, const float* grad_accum, const float* denom, const float* scaling_raw, float grad_threshold,
+                          float dense_extent, unsigned char* clone_flag, unsigned char* split_flag, b200gs_stream_t stream)
+{
+    if (N <= 0) return 0;
+    if (!grad_accum || !denom || !scaling_raw || !clone_flag || !split_flag) { set_error("densify_select: null pointer"); return -1; }
+    densify_select_kernel<<<blocks_for(N), 256, 0, (cudaStream_t)stream>>>(N, grad_accum, denom, scaling_raw, grad_threshold, dense_extent, clone_flag, split_flag);
+    return check_launch("densify_select");
+}
+
+int b200gs_prune_select(long long N, const float* opacity_raw, const float* scaling_raw, const float* max_radii2D, float min_opacity,
+                        float max_screen_size, float max_world_extent, unsigned char* prune_flag, b200gs_stream_t stream)
+{
+    if (N <= 0) return 0;
+    if (!opacity_raw || !prune_flag || (max_screen_size > 0.f && (!scaling_raw || !max_radii2D))) { set_error("prune_select: null pointer"); return -1; }
+    prune_select_kernel<<<blocks_for(N), 256, 0, (cudaStream_t)stream>>>(N, opacity_raw, scaling_raw, max_radii2D, min_opacity, max_screen_size, max_world_extent, prune_flag);
+    return check_launch("prune_select");
+}
+
+int b200gs_densification_stats(long long N, const float* viewspace_grad, const unsigned char* update_filter, float* grad_accum, float* denom,
+                               b200gs_stream_t stream)
+{
+    if (N <= 0) return 0;
+    if (!viewspace_grad || !update_filter || !grad_accum || !denom) { set_error("densification_stats: null pointer"); return -1; }
+    densification_stats_kernel<<<blocks_for(N), 256, 0, (cudaStream_t)stream>>>(N, viewspace_grad, update_filter, grad_accum, denom);
+    return check_launch("densification_stats");
+}
+
+int b200gs_reset_opacity(long long N, const float* opacity_raw, float* out, b200gs_stream_t stream)
+{
+    if (N <= 0) return 0;
+    if (!opacity_raw || !out) { set_error("reset_opacity: null pointer"); return -1; }
+    reset_opacity_kernel<<<blocks_for(N), 256, 0, (cudaStream_t)stream>>>(N, opacity_raw, out);
+    return check_launch("reset_opacity");
 }
 
 }  // extern "C"

@@ -190,9 +190,27 @@ int b200gs_adam_sh(long long P, int M, const b200gs_adam_tensor* dc, const b200g
  * for every listed tensor, dst[i, :] = src[index[i], :], i < n_out, rows of row_floats floats.
  * index = int64 row ids on the device (null = identity, i.e. a plain multi-tensor copy). */
 #define B200GS_GATHER_MAX_TENSORS 64
-typedef struct { const float* src; float* dst; int row_floats; int reserved; } b200gs_gather_tensor;
+typedef struct { const float* src; float* dst; int row_floats; int zero_tail_rows; /* the last zero_tail_rows of the n_out rows are set to 0
+                 instead of gathered: the fresh rows of exp_avg / exp_avg_sq (gaussian_model.py:470-471) */ } b200gs_gather_tensor;
 int b200gs_gather_rows_multi(int n_tensors, const b200gs_gather_tensor* tensors /* host */,
                              const long long* index, long long n_out, b200gs_stream_t stream);
+
+/* The DECISIONS of a densification / pruning event, one pass over the Gaussians each (the moves are b200gs_gather_rows_multi):
+ *   densify_select  GaussianModel.densify -> densify_and_clone / densify_and_split (scene/gaussian_model.py:693-698, :541-565, :511-523):
+ *                   g = grad_accum / denom (NaN -> 0); clone_flag = |g| >= thr and max(exp(scaling)) <= dense_extent;
+ *                   split_flag = g >= thr and max(exp(scaling)) > dense_extent   (dense_extent = percent_dense * scene_extent)
+ *   prune_select    GaussianModel.prune (:681-690): sigmoid(opacity) < min_opacity, or -- when max_screen_size > 0 -- max_radii2D >
+ *                   max_screen_size or max(exp(scaling)) > max_world_extent (= 0.1 * extent)
+ *   densification_stats  add_densification_stats (:713-715): for update_filter[i] != 0: grad_accum[i] += |viewspace_grad[i, :2]|, denom[i] += 1
+ *   reset_opacity   (:362-365): out = inverse_sigmoid(min(sigmoid(opacity), 0.01))
+ * flags are bytes (0 / 1; a torch.bool tensor's storage).  Same float operations as the torch expressions they replace. */
+int b200gs_densify_select(long long N, const float* grad_accum, const float* denom, const float* scaling_raw, float grad_threshold,
+                          float dense_extent, unsigned char* clone_flag, unsigned char* split_flag, b200gs_stream_t stream);
+int b200gs_prune_select(long long N, const float* opacity_raw, const float* scaling_raw, const float* max_radii2D, float min_opacity,
+                        float max_screen_size, float max_world_extent, unsigned char* prune_flag, b200gs_stream_t stream);
+int b200gs_densification_stats(long long N, const float* viewspace_grad /* [N,3] */, const unsigned char* update_filter, float* grad_accum,
+                               float* denom, b200gs_stream_t stream);
+int b200gs_reset_opacity(long long N, const float* opacity_raw, float* out, b200gs_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Deformation field — replaces the PyTorch operator chains behind
