@@ -16,7 +16,7 @@ static thread_local char g_err[512] = "";
 // on a B200 (bit-identical outputs; gradients equal up to float-atomic order); 0 selects the first-generation kernels. The
 // environment (B200GS_MLP_BWD_V2 / B200GS_MLP_FWD_ELECT = integer) overrides the initial value.
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : dflt; }
-int g_opt_mlp_bwd_v2 = env_int("B200GS_MLP_BWD_V2", 55);
+int g_opt_mlp_bwd_v2 = env_int("B200GS_MLP_BWD_V2", 87);
 int g_opt_mlp_fwd_elect = env_int("B200GS_MLP_FWD_ELECT", 2);
 int g_opt_hexplane_time_bwd = env_int("B200GS_HEXPLANE_TIME_BWD", 2);    // 0.417 -> 0.354 ms (profiles/r2a_hexplane_time_check.txt)
 int g_opt_lookback_parallel = env_int("B200GS_LOOKBACK_PARALLEL", 1);    // 111 -> 103 us per 1M-pair sort (profiles/r2a_sort_check.txt)
@@ -130,7 +130,7 @@ int b200gs_version(void) { return 100; }
 int b200gs_set_option(const char* name, int value)
 {
     if (name && !strcmp(name, "mlp_bwd_v2")) {
-        if (value != 0 && value != 1 && value != 3 && value != 5 && value != 7 && value != 55) { set_error("b200gs_set_option: mlp_bwd_v2 = %d is not built (0, 1, 3, 5, 7, 55)", value); return -1; }
+        if (value != 0 && value != 1 && value != 3 && value != 5 && value != 7 && value != 55 && value != 87) { set_error("b200gs_set_option: mlp_bwd_v2 = %d is not built (0, 1, 3, 5, 7, 55, 87)", value); return -1; }
         b200gs::g_opt_mlp_bwd_v2 = value;
         return 0;
     }

@@ -79,7 +79,11 @@ __device__ __forceinline__ float4 lds128(u32 addr)
 // chain reads its A operand dY from the MN-major SWIZZLE_128B_BASE32B image of the weight-gradient MMAs, re-described as a
 // K-major operand (rows = points, 128-byte rows of 32 out-features, 8-row group stride BwdArgs::dy_sbo = 512 B -- the one
 // combination that reproduces the product exactly on hardware, tools/probe/umma_probe2.cu), so dY is stored to shared
-// memory twice (hi, lo) instead of four times: 0.744 -> 0.686 ms per 1M points (profiles/r2a_mlp_variant_check.txt).
+// memory twice (hi, lo) instead of four times: 0.744 -> 0.686 ms per 1M points (profiles/r2a_mlp_variant_check.txt);
+// bit 5 = TMA: the 66 KB of shared memory that frees become two 32 KB staging slots, and the stash / feature rows of a phase
+// (one contiguous 32 KB tile each, tc5_common.cuh) arrive by ONE bulk copy (cp.async.bulk -> UBLKCP, the TMA engine) requested two
+// phases ahead by the MMA-issuing thread and counted on the slot's mbarrier, instead of 8 LDG.128 per thread held in registers
+// across a phase: 0.686 -> 0.597 ms (profiles/r2i_mlp_variant_check.txt; d_out in registers on top of it lost: 0.648).
 // ABL (timing experiments only, WRONG RESULTS, option "mlp_bwd_ablate"): what the kernel costs without one of its parts --
 // 1: d_out read from constants instead of global memory, 2: no operand stores to shared memory, 4: no MMAs (and no waits for
 // them), 8: no gradient math (dz / dW3 / bias sums), 16: no d_feature stores, 32: stash / feature rows from constants.
@@ -88,8 +92,9 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
 {
     constexpr bool A_NODIN = (ABL & 1) != 0, A_NOSTS = (ABL & 2) != 0, A_NOMMA = (ABL & 4) != 0, A_NOMATH = (ABL & 8) != 0,
                    A_NODFEAT = (ABL & 16) != 0, A_NOLOAD = (ABL & 32) != 0;
-    constexpr bool V2 = (VER & 1) != 0, DIN_AHEAD = ((VER >> 1) & 3) == 1, DIN_PREFETCH = ((VER >> 1) & 3) >= 2, SINGLE_DY = ((VER >> 4) & 1) != 0;
+    constexpr bool V2 = (VER & 1) != 0, DIN_AHEAD = ((VER >> 1) & 3) == 1, DIN_PREFETCH = ((VER >> 1) & 3) >= 2, SINGLE_DY = ((VER >> 4) & 1) != 0, TMA = ((VER >> 5) & 1) != 0;
     static_assert(!SINGLE_DY || V2, "the single dY image is built on the V2 kernel");
+    static_assert(!TMA || (SINGLE_DY && ABL == 0), "the TMA-staged rows live in the shared memory the single dY image frees");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* W2B = reinterpret_cast<float*>(smem_raw);                 // current head: hi [16 k-chunks][64 n][4] | lo  (32 KB)
     float* W1B = W2B + 2 * MW * MW;                                  // hi | lo                                      (32 KB)
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
     unsigned char* XH = DYM + 65536;                                 // 32 KB, MN-major swizzled  [in 64][p 128]
     unsigned char* DYK = XH + 32768;              // 2 planes x 16 chunks x 2064 B, K-major  [p 128][out 64]
     u64* bar = reinterpret_cast<u64*>(DYK + 2 * KPLANE);
-    u32* tmem_slot = reinterpret_cast<u32*>(bar + 1);
+    u32* tmem_slot = reinterpret_cast<u32*>(bar + 3);          // bar[0]: MMA groups; bar[1], bar[2]: the two TMA staging slots
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // SIMT mapping: columns 32 c + 4 q + e, points 32 pg + 4 i + sub (i = 0..7)
     const int q = lane & 7, sub = lane >> 3, c = warp & 1, pg = warp >> 1;
@@ -124,6 +129,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
     if (tid == 0) {
         if (smem_u32(DYM) & 1023u) __trap();                          // the swizzle below assumes 1 KB aligned tiles
         mbar_init(bar, 1);
+        if constexpr (TMA) { mbar_init(bar + 1, 1); mbar_init(bar + 2, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
     // every thread right after the block barrier, so warp 0 is converged; elect.sync picks the same lane every time, which
     // tcgen05.commit needs (it tracks the MMAs of the executing thread).  Descriptor start addresses are 14-bit fields of
     // (address >> 4) and shared memory ends below 256 KB, so adding (offset >> 4) to a hoisted base cannot carry out.
-    auto issue_group = [&](u32 sW, u32 d_col, bool d_accumulate, u32 w_col) {
+    auto issue_group = [&](u32 sW, u32 d_col, bool d_accumulate, u32 w_col, bool tma_go = false, const float* tma_src = nullptr, u32 tma_slot = 0) {
         if (!A_NOMMA && warp == 0) {
             if (elect_one()) {
                 tc_fence_after();
@@ -170,6 +176,16 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
                 for (int j = 0; j < 16; ++j)           // K = 128 points, 8 per instruction (two 4-row atoms)
                     mma_ss(tbase + w_col, dM + (u64)((j * 1024) >> 4), dX + (u64)((j * 1024) >> 4), id_mn, (first_tile && j == 0) ? 0u : 1u);
                 tc_commit(bar);
+                if constexpr (TMA) {
+                    // the 32 KB tile of stash / feature rows that the phase after next will read: one bulk copy (TMA engine)
+                    // into the staging slot this phase has just finished with, completion counted on the slot's mbarrier
+                    if (tma_go) {
+                        const u32 mb = smem_u32(bar + 1 + tma_slot), dst = sDYK + tma_slot * KPLANE;
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(32768u) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     :: "r"(dst), "l"(tma_src), "r"(32768u), "r"(mb) : "memory");
+                    }
+                }
             }
             __syncwarp();
         }
@@ -215,6 +231,29 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
     // MMA drain + shared-memory stores of the phase before.
     const bool en0 = a.w.w2[0] != nullptr, en1 = a.w.w2[1] != nullptr, en2 = a.w.w2[2] != nullptr;
     auto next_phase = [&](int ph) { return (ph < 0 && en0) ? 0 : (ph < 1 && en1) ? 1 : (ph < 2 && en2) ? 2 : 3; };
+    // TMA staging (TMA): the rows of phase n + 2 are requested at the end of phase n into slot (n & 1); every thread tracks the
+    // (uniform) schedule: n_cons rows-tiles consumed so far, (iss_tile, iss_ph) = the next tile / phase to request
+    u32 n_cons = 0, n_iss = 0;
+    long long iss_tile = blockIdx.x;
+    int iss_ph = next_phase(-1);
+    auto tma_src_of = [&](long long tile, int ph) -> const float* {
+        return (ph >= 3 ? a.feat : a.saved + (size_t)(1 + ph) * stash_plane_floats(a.P)) + (size_t)tile * (ROWS * MW);
+    };
+    auto iss_advance = [&]() {
+        if (iss_ph >= 3) { iss_tile += gridDim.x; iss_ph = next_phase(-1); } else iss_ph = next_phase(iss_ph);
+        ++n_iss;
+    };
+    auto stage_read = [&](float4* x, long long r0) {                         // this phase's rows out of its staging slot
+        const u32 slot = n_cons & 1u;
+        mbar_wait(bar + 1 + slot, (n_cons >> 1) & 1u);
+        const u32 base = sDYK + slot * KPLANE + (u32)(((p0 >> 2) * 256 + (col0 >> 2) * 16 + (p0 & 3) * 4) * 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = lds128(base + (u32)i * 1024u);
+            x[i] = r0 + 4 * i < a.P ? v : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        ++n_cons;
+    };
     auto load_rows = [&](float4* x, const float* src, long long r0) {          // features: row-major [P][64] or stash-style tiles
         const float* base = src + (a.w.feat_tiled ? stash_off(r0, col0) : (size_t)r0 * MW + col0);
         const size_t step = a.w.feat_tiled ? 256 : 4 * MW;                       // rows r0 + 4 i
@@ -261,7 +300,18 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
     float4 hrow[8], xin[8];
     if ((long long)blockIdx.x < nblocks) {
         load_stash(hrow, 0, (long long)blockIdx.x * ROWS + p0);
-        load_phase_rows(next_phase(-1), xin, (long long)blockIdx.x * ROWS + p0);
+        if constexpr (!TMA) load_phase_rows(next_phase(-1), xin, (long long)blockIdx.x * ROWS + p0);
+    }
+    if constexpr (TMA) {              // the first two row-tiles of this CTA's schedule -> slots 0 and 1
+        for (int k = 0; k < 2; ++k) {
+            if (iss_tile < nblocks && tid == 0) {
+                const u32 mb = smem_u32(bar + 1 + (n_iss & 1u)), dst = sDYK + (n_iss & 1u) * KPLANE;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(32768u) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(dst), "l"(tma_src_of(iss_tile, iss_ph)), "r"(32768u), "r"(mb) : "memory");
+            }
+            iss_advance();
+        }
     }
     if constexpr (V2) copy_image_pair(W2B, next_phase(-1));            // group 0's weights -> slot 0 (waited for before its MMAs)
     float din_next[8][4];
@@ -279,6 +329,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
         for (int h = 0; h < 3; ++h) {
             if (!a.w.w2[h]) continue;
             const int kd = kdim[h];
+            if constexpr (TMA) stage_read(xin, row0);
             float4 w3[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) w3[k] = k < kd ? __ldg(reinterpret_cast<const float4*>(a.w.w3[h] + k * MW + col0)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -315,7 +366,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
                     for (int k = 0; k < 4; ++k) gB3[h][k] += din[i][k];
                 }
             }
-            load_phase_rows(next_phase(h), xin, row0);          // next head's rows, or the feature rows
+            if constexpr (!TMA) load_phase_rows(next_phase(h), xin, row0);          // next head's rows, or the feature rows
             if constexpr (DIN_AHEAD) load_phase_dout(next_phase(h), din_next, row0);        // (nothing for the feature phase)
             if constexpr (DIN_PREFETCH) prefetch_phase_dout(next_phase(h), blk);
             drain(false);            // the previous MMA group still reads DYK / DYM / XH and the W2 slot
@@ -344,7 +395,9 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
             tc_fence_before();
             __syncthreads();
             if constexpr (V2) {
-                issue_group((ngroup & 1u) ? sW1 : sW2, C_RH, rh_started, C_W2 + 64 * h);
+                const bool go = TMA && iss_tile < nblocks;
+                issue_group((ngroup & 1u) ? sW1 : sW2, C_RH, rh_started, C_W2 + 64 * h, go, go ? tma_src_of(iss_tile, iss_ph) : nullptr, n_iss & 1u);
+                if constexpr (TMA) iss_advance();
                 ++ngroup;
             } else if (tid == 0) {
                 tc_fence_after();
@@ -365,13 +418,14 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
             rh_started = true;
         }
         // ---- dh = d relu(hidden) masked ; d feature = dh W1 ; dW1 += dh^T feature ----
-        if (next_phase(-1) == 3) load_rows(xin, a.feat, row0);        // every head disabled: nothing was prefetched
+        if constexpr (TMA) stage_read(xin, row0);
+        else if (next_phase(-1) == 3) load_rows(xin, a.feat, row0);        // every head disabled: nothing was prefetched
         float4 frow[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) frow[i] = xin[i];
         if (blk + gridDim.x < nblocks) {                              // next tile: relu(hidden) rows and the first phase's inputs
             load_stash(hrow, 0, (blk + gridDim.x) * ROWS + p0);
-            load_phase_rows(next_phase(-1), xin, (blk + gridDim.x) * ROWS + p0);
+            if constexpr (!TMA) load_phase_rows(next_phase(-1), xin, (blk + gridDim.x) * ROWS + p0);
             if constexpr (DIN_AHEAD) load_phase_dout(next_phase(-1), din_next, (blk + gridDim.x) * ROWS + p0);
             if constexpr (DIN_PREFETCH) prefetch_phase_dout(next_phase(-1), blk + gridDim.x);
         }
@@ -380,6 +434,10 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
             if (blk + gridDim.x < nblocks) copy_image_pair((ngroup & 1u) ? W2B : W1B, next_phase(-1));
             else cp_async_commit();
         }
+        // TMA: the bounce goes through the staging slot the feature rows were just read from (every thread has them in registers
+        // once the barrier below has been passed); the next request for that slot is issued after this phase's last barrier
+        const u32 sBounce = TMA ? sDYK + ((n_cons - 1u) & 1u) * KPLANE : sDYK;
+        if constexpr (TMA) __syncthreads();
         {   // D_RH comes out of TMEM as (lane = point, 32 columns); bounce it through the DYK hi plane to reach the SIMT mapping
             u32 v[32];
             if (rh_started) {
@@ -391,7 +449,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                sts128(sDYK + (u32)(8 * cT + j) * KCH + (u32)pT * 16u,
+                sts128(sBounce + (u32)(8 * cT + j) * KCH + (u32)pT * 16u,
                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
         }
         tc_fence_before();
@@ -399,7 +457,7 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const u32 pp = (u32)(p0 + 4 * i);
-            const float4 r4 = lds128(sDYK + k_off + pp * 16u);
+            const float4 r4 = lds128(sBounce + k_off + pp * 16u);
             float x[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -422,7 +480,9 @@ __global__ void __launch_bounds__(BT, 1) deform_mlp_bwd_tc5_kernel(const __grid_
         tc_fence_before();
         __syncthreads();
         if constexpr (V2) {
-            issue_group((ngroup & 1u) ? sW1 : sW2, C_FE, false, C_W1);
+            const bool go = TMA && iss_tile < nblocks;
+            issue_group((ngroup & 1u) ? sW1 : sW2, C_FE, false, C_W1, go, go ? tma_src_of(iss_tile, iss_ph) : nullptr, n_iss & 1u);
+            if constexpr (TMA) iss_advance();
             ++ngroup;
         } else if (tid == 0) {
             tc_fence_after();
@@ -567,7 +627,10 @@ int deform_mlp_backward_tc5(const b200gs_mlp_weights* w, const b200gs_mlp_grads*
             // MMAs re-described as a K-major operand with a 512-byte 8-row group stride (exact on hardware: tools/probe/umma_probe2.cu,
             // profiles/r2a_umma_probe2.txt; the 1024-byte stride is NOT and was removed)
             case 55: kern = tc5::deform_mlp_bwd_tc5_kernel<23>; break;
-            default: set_error("deform_mlp_backward: mlp_bwd_v2 = %d is not built (0, 1, 3, 5, 7, 55)", g_opt_mlp_bwd_v2); return -1;
+            // 87 = 55 + the stash / feature rows of a phase staged by ONE 32 KB bulk copy (TMA engine) two phases ahead instead
+            // of 8 LDG.128 per thread one phase ahead; needs the tiled feature layout (falls back to 55 otherwise)
+            case 87: kern = w->feat_tiled ? tc5::deform_mlp_bwd_tc5_kernel<55> : tc5::deform_mlp_bwd_tc5_kernel<23>; break;
+            default: set_error("deform_mlp_backward: mlp_bwd_v2 = %d is not built (0, 1, 3, 5, 7, 55, 87)", g_opt_mlp_bwd_v2); return -1;
             case 1: break;
         }
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

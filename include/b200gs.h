@@ -32,10 +32,11 @@ int b200gs_version(void);
 /* Kernel variants, process-wide. The defaults are the fastest variants that have passed tools/native/mlp_variant_check.cu on
  * a B200 (bit-identical outputs, gradients equal up to float-atomic order); 0 selects the first-generation kernel, the
  * environment variable B200GS_<NAME>=<integer> overrides the initial value:
- *   "mlp_bwd_v2"     deformation-MLP backward (default 55): bit 0 = alternating weight slots + elected MMA issuer + coalesced
+ *   "mlp_bwd_v2"     deformation-MLP backward (default 87): bit 0 = alternating weight slots + elected MMA issuer + coalesced
  *                    gradient flush; bits 1-2 = how d_out reaches a phase (3 = prefetched into L2 one phase ahead); 55 = 7 +
- *                    ONE dY image in shared memory, read K-major by the dX chain and MN-major by the weight-gradient MMAs
- *                    (deform_mlp_bwd_tc5.cu).  Built values: 0, 1, 3, 5, 7, 55; anything else is refused
+ *                    ONE dY image in shared memory, read K-major by the dX chain and MN-major by the weight-gradient MMAs;
+ *                    87 = 55 + stash / feature rows staged by 32 KB TMA bulk copies two phases ahead (tiled feature layout;
+ *                    55 otherwise) (deform_mlp_bwd_tc5.cu).  Built values: 0, 1, 3, 5, 7, 55, 87; anything else is refused
  *   "mlp_fwd_elect"  deformation-MLP forward (default 2): 1 = elected MMA issuer, 2 = plus activation-stash stores deferred
  *                    past the next layer's MMA issue (deform_mlp_tc5.cu)
  *   "hexplane_time_fwd" time-row HexPlane forward (default 2): 1 / 2 = both levels' factor rows requested up front,

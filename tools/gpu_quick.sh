@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 make -s -C tools/native >/dev/null 2>&1
 run() { name=$1; shift; timeout 90 "$@" > gpurun_out/${name}_$TAG.log 2>&1; echo "== $name rc=$?"; }
 run umma_probe2 tools/probe/umma_probe2;                                   cat gpurun_out/umma_probe2_$TAG.log
-run mlp_variant_check tools/native/mlp_variant_check 1000000 1,7,55; grep -v '^    ' gpurun_out/mlp_variant_check_$TAG.log | head -60
+run mlp_variant_check tools/native/mlp_variant_check 1000000 7,55,87; grep -v '^    ' gpurun_out/mlp_variant_check_$TAG.log | head -60
 run mlp_bwd_ablate tools/native/mlp_variant_check 1000000 ablate;          cat gpurun_out/mlp_bwd_ablate_$TAG.log
 run sort_check tools/native/sort_check 1000000 32;                         tail -9 gpurun_out/sort_check_$TAG.log
 run sort_check12 tools/native/sort_check 5100000 12;                       tail -9 gpurun_out/sort_check12_$TAG.log

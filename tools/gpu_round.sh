@@ -6,7 +6,7 @@ KRE=${2:-deform_mlp_bwd}
 mkdir -p gpurun_out
 # seconds each, no Python: kernel-variant parity + timing, rasterizer checksums + timing (diff two builds / option values)
 tools/probe/umma_probe2 > gpurun_out/umma_probe2_$TAG.log 2>&1; cat gpurun_out/umma_probe2_$TAG.log
-make -s -C tools/native >/dev/null 2>&1; tools/native/mlp_variant_check 1000000 1,7,55 > gpurun_out/mlp_variant_check_$TAG.log 2>&1; grep -v '^    ' gpurun_out/mlp_variant_check_$TAG.log | head -40
+make -s -C tools/native >/dev/null 2>&1; tools/native/mlp_variant_check 1000000 7,55,87 > gpurun_out/mlp_variant_check_$TAG.log 2>&1; grep -v '^    ' gpurun_out/mlp_variant_check_$TAG.log | head -40
 tools/native/mlp_variant_check 1000000 ablate > gpurun_out/mlp_bwd_ablate_$TAG.log 2>&1; cat gpurun_out/mlp_bwd_ablate_$TAG.log
 tools/native/sort_check 1000000 32 > gpurun_out/sort_check_$TAG.log 2>&1; tail -9 gpurun_out/sort_check_$TAG.log
 tools/native/sort_check 5100000 12 > gpurun_out/sort_check12_$TAG.log 2>&1; tail -9 gpurun_out/sort_check12_$TAG.log
