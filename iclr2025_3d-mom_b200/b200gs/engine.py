@@ -429,8 +429,16 @@ class ViewParallelTrainer:
                 _rast.SH_GRAD_ACCUMULATOR = self.sh_grad if on_gpu else None
                 _rast.SH_GRAD_OVERWRITE = first_sh
                 if on_gpu and self.overlap_sh_reduce and vi == len(cams) - 1:
-                    # called by the rasterizer backward right after it has queued the kernel that adds this view's SH gradient
-                    _rast.AFTER_SH_ACCUMULATE = self._sh_tail
+                    # The SH tail starts from inside the LAST view's backward.  The SH gradient is complete as soon as the
+                    # rasterizer backward has been queued, but the deformation-MLP backward that follows is a persistent kernel
+                    # with one 230 KB CTA per SM and a static tile schedule: a collective that holds a few SMs while it runs
+                    # delays those CTAs by the collective's whole duration (measured at N = 8: 0.60 -> 1.22 ms).  So the tail
+                    # is started right AFTER the MLP backward has been queued and overlaps the time-plane / spatial HexPlane
+                    # backward, the arena all-reduce and the regulariser instead -- ordinary kernels that share SMs gracefully.
+                    if self.stage == "fine" and hasattr(_field, "AFTER_MLP_BACKWARD"):
+                        _field.AFTER_MLP_BACKWARD = self._sh_tail
+                    else:
+                        _rast.AFTER_SH_ACCUMULATE = self._sh_tail
                 try:
                     if self.shared_shs and gt.is_cuda:
                         # fused L1 (utils/loss_utils.py:23-24) + its gradient, then backward from the image
@@ -448,6 +456,7 @@ class ViewParallelTrainer:
                     _rast.SH_GRAD_ACCUMULATOR = None
                     _rast.SH_GRAD_OVERWRITE = False
                     _rast.AFTER_SH_ACCUMULATE = None
+                    _field.AFTER_MLP_BACKWARD = None
                 first_sh = False
                 vg = pkg["viewspace_points"].grad
                 if vg is not None:
@@ -475,8 +484,9 @@ class ViewParallelTrainer:
         self._mark("arena_reduced")
         if self.regulation is not None:
             # plane-only term, identical on every rank: added once, after the reduce
+            # (its VALUE goes into rank 0's share of the loss only, so that the shares still sum to the global loss)
             _field.accumulate_regulation(m._deformation.deformation_net.grid, *self.regulation,
-                                         loss_accum=total if (total is not None and total.numel() == 1 and total.dim() == 1) else None)
+                                         loss_accum=total if (self.rank == 0 and total is not None and total.numel() == 1 and total.dim() == 1) else None)
         if self.regulation_fn is not None:
             reg = self.regulation_fn()
             reg.backward()

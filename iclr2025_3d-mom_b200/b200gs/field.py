@@ -230,6 +230,9 @@ class _HexPlaneFn(torch.autograd.Function):
 # anyway) and autograd gets None for them: per view this saves a zero-fill plus an accumulation pass for each of
 # the 26 field parameters. Off by default, so under the reference's own scripts autograd sees ordinary gradients.
 ACCUMULATE_INTO_GRAD = False
+# Optional callable invoked right after the deformation-MLP backward kernel of a view has been queued (the trainer starts the SH
+# gradient's side-stream all-reduce + Adam there on the last view of a step); None = nothing.
+AFTER_MLP_BACKWARD = None
 
 
 def _grad_target(param):
@@ -546,6 +549,8 @@ class _DeformFn(torch.autograd.Function):
         check(L.b200gs_deform_mlp_backward(ctypes.byref(mw), ctypes.byref(mg), P, feat.data_ptr(), saved.data_ptr(),
                                            cp(d_pts) if heads[0] else None, cp(d_scales) if heads[1] else None,
                                            cp(d_rot) if heads[2] else None, d_feat.data_ptr(), stream), "deform_mlp_backward")
+        if AFTER_MLP_BACKWARD is not None:
+            AFTER_MLP_BACKWARD()
         sh = ctx.shared
         # the spatial planes receive nothing here when only the time planes were sampled (their share goes through S)
         time_only = sh is not None

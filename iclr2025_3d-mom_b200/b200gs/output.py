@@ -66,3 +66,70 @@ class FrameRing:
         self.count -= 1
         frame = self.host[slot].numpy()
         return frame.copy() if copy else frame
+
+
+class FrameWriter:
+    """PNG / MP4 encoding off the critical path.  render_4DGS.py:58-76 calls
+    `torchvision.utils.save_image` per frame INSIDE its render loop and `imageio.mimwrite` after it, so its "FPS" is PNG-encode
+    bound; here the render loop only hands finished uint8 [H,W,3] frames (what `FrameRing.pop()` returns) to a queue and a few
+    worker threads encode them (OpenCV releases the GIL while encoding): PNG files named `{index:05d}.png` like the reference's,
+    and, on `close()`, one MP4 of all frames in index order.  Host-only code: nothing here touches the GPU."""
+
+    def __init__(self, png_dir=None, video_path=None, fps=30, workers=4, max_pending=64):
+        import queue
+        import threading
+        self.png_dir, self.video_path, self.fps = png_dir, video_path, fps
+        if png_dir is not None:
+            import os
+            os.makedirs(png_dir, exist_ok=True)
+        self.q = queue.Queue(maxsize=max_pending)          # back-pressure: rendering stalls only if encoding falls this far behind
+        self.frames = {} if video_path is not None else None
+        self.errors = []
+        self.threads = [threading.Thread(target=self._work, daemon=True) for _ in range(max(1, workers))]
+        for t in self.threads:
+            t.start()
+
+    def _work(self):
+        import os
+        import cv2
+        while True:
+            item = self.q.get()
+            if item is None:
+                self.q.task_done()
+                return
+            idx, frame = item
+            try:
+                if self.png_dir is not None:
+                    cv2.imwrite(os.path.join(self.png_dir, "{0:05d}.png".format(idx)), cv2.cvtColor(frame, cv2.COLOR_RGB2BGR))
+                if self.frames is not None:
+                    self.frames[idx] = frame
+            except Exception as ex:                        # reported by close()
+                self.errors.append((idx, ex))
+            self.q.task_done()
+
+    def put(self, index, frame):
+        """frame: uint8 [H,W,3] numpy array that the caller will not modify (FrameRing.pop() hands out a copy)."""
+        self.q.put((int(index), frame))
+
+    def close(self):
+        """Waits for the queue to drain, writes the video, re-raises the first encoding error."""
+        for _ in self.threads:
+            self.q.put(None)
+        for t in self.threads:
+            t.join()
+        if self.errors:
+            raise RuntimeError(f"FrameWriter: frame {self.errors[0][0]} failed: {self.errors[0][1]}")
+        if self.frames:
+            import cv2
+            order = sorted(self.frames)
+            h, w = self.frames[order[0]].shape[:2]
+            vw = cv2.VideoWriter(self.video_path, cv2.VideoWriter_fourcc(*"mp4v"), self.fps, (w, h))
+            for i in order:
+                vw.write(cv2.cvtColor(self.frames[i], cv2.COLOR_RGB2BGR))
+            vw.release()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

@@ -564,6 +564,7 @@ hexplane_time_bwd2_kernel(const __grid_constant__ b200gs_hexplane_desc d, const 
         const long long i = base + slot;
         const bool valid = i < end;
         const size_t g = valid ? (order ? (size_t)__ldg(order + i) : (size_t)i) : 0;
+        // (prefetching the next iteration's rows into L1 was measured: 0.365 vs 0.353 ms, not kept)
         float4 gout[L], fac[L], old[L];
         if (valid) {
 #pragma unroll
