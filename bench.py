@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--render-frames", type=int, default=60, help="frames per camera path of the render block (0 = skip)")
     ap.add_argument("--no-raster-only", action="store_true", help="skip the config-2 rasterizer-only block")
+    ap.add_argument("--no-c5", action="store_true", help="skip the config-5 stress block (5M Gaussians at 3840x2160, N = 1 only)")
     ap.add_argument("--no-launcher-path", action="store_true", help="skip the block that runs the reference's unchanged train_4DGS.py through the launcher")
     ap.add_argument("--no-shared-spatial", action="store_true",
                     help="render every frame with the full six-plane HexPlane pass instead of sharing the spatial product over a sequence")
@@ -446,6 +447,70 @@ def raster_only_block(args, device, impl):
                     "instances": int(R), "scene": f"scale_mu={mu}"}
         del raw, act
         torch.cuda.empty_cache()
+    return out
+
+
+# ---- stress (BASELINE.json config 5) -------------------------------------------------------------------
+def stress_c5_block(args, device):
+    """5M Gaussians at 3840x2160: `distCUDA2` initialisation (scene/gaussian_model.py:160-161), then training iterations of 2 views
+    with a densification + pruning EVENT (GaussianModel.densify + prune through b200gs.densify: decision kernel + one gather)
+    every 10 iterations, statistics accumulated every iteration (add_densification_stats, max_radii2D).  Reports the kNN time,
+    the steady iteration time and every event's duration including the FIRST one (allocator growth included)."""
+    from b200gs import engine, synthetic as syn
+    from b200gs.knn import distCUDA2
+    P, W, H, iters = 5_000_000, 3840, 2160, 31
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    raw = syn.make_gaussians(P, scale_mu=0.004, device="cpu")
+    xyz = raw["xyz"].to(device)
+    distCUDA2(xyz[:100000])                                    # library / allocator warm-up
+    a, b = ev(), ev(); a.record()
+    d2 = distCUDA2(xyz)
+    b.record(); torch.cuda.synchronize()
+    knn_ms = a.elapsed_time(b)
+    raw["log_scale"] = torch.log(torch.sqrt(torch.clamp_min(d2, 1e-7)))[..., None].repeat(1, 3).cpu()
+    torch.manual_seed(6666)
+    model = engine.GaussianState({k: v.to(device) for k, v in raw.items()}, hyper=engine.default_hyper()).to(device)
+    with torch.no_grad():
+        model._deformation.deformation_net.set_aabb(xyz.max(0).values.tolist(), xyz.min(0).values.tolist())
+    model.training_setup()
+    model.densification_setup(percent_dense=0.01)
+    h = engine.default_hyper()
+    tr = engine.ViewParallelTrainer(model, torch.zeros(3, device=device), stage="fine",
+                                    regulation=(h.time_smoothness_weight, h.l1_time_planes, h.plane_tv_weight))
+    cams = syn.orbit_cameras(2, W, H, device=device)
+    g = torch.Generator().manual_seed(99)
+    gts = [(torch.rand(H, W, 3, generator=g) * 255.999).to(torch.uint8).to(device) for _ in cams]
+    extent = 1.0
+    step_ms, events = [], []
+    n0 = P
+    for it in range(1, iters + 1):
+        a, b = ev(), ev(); a.record()
+        loss = tr.step(cams, gts)
+        with torch.no_grad():                                   # train_4DGS.py:264-267
+            vis = tr.max_radii > 0
+            model.max_radii2D = torch.maximum(model.max_radii2D, tr.max_radii.to(torch.float32))
+            model.add_densification_stats(tr.viewspace_grad, vis)
+        b.record()
+        if it % 10 == 0:
+            c, d = ev(), ev(); c.record()
+            with torch.no_grad():
+                before = model._xyz.shape[0]
+                model.densify(0.0002, 0.005, extent, None)
+                mid = model._xyz.shape[0]
+                model.prune(0.0002, 0.005, extent, None)
+            tr.rebuild()
+            d.record(); torch.cuda.synchronize()
+            events.append({"iteration": it, "ms": round(c.elapsed_time(d), 3), "points_before": before, "after_densify": mid, "after_prune": int(model._xyz.shape[0])})
+        torch.cuda.synchronize()
+        if not bool(torch.isfinite(loss).all()):
+            raise RuntimeError("C5: non-finite loss")
+        step_ms.append(a.elapsed_time(b))
+    steady = sorted(step_ms[2:9])[3]
+    out = {"config": "C5: 5,000,000 Gaussians, 3840x2160, 2 views per iteration, densify + prune event every 10 iterations", "distCUDA2_ms": round(knn_ms, 2),
+           "iteration_ms_median_before_first_event": round(steady, 2), "view_iters_per_s": 2e3 / steady, "events": events,
+           "max_memory_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1), "points_final": int(model._xyz.shape[0])}
+    del tr, model
+    torch.cuda.empty_cache()
     return out
 
 
@@ -987,6 +1052,13 @@ def _main():
             res["raster_only"] = raster_only_block(args, device, impl)
         except Exception as ex:
             res["raster_only"] = {"failed": f"{type(ex).__name__}: {ex}"}
+    if impl == "b200" and world == 1 and not args.no_c5:
+        trainer = model = None                              # free the C3 model before the 5M-Gaussian one is built
+        torch.cuda.empty_cache()
+        try:
+            res["stress_c5"] = stress_c5_block(args, device)
+        except Exception as ex:
+            res["stress_c5"] = {"failed": f"{type(ex).__name__}: {ex}"}
     if impl == "b200" and world == 1 and not args.no_launcher_path:
         torch.cuda.empty_cache()
         try:

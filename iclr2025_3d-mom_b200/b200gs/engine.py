@@ -118,6 +118,32 @@ class GaussianState(nn.Module):
         self._lr_max_steps = opt.position_lr_max_steps
         return self.optimizer
 
+    # ---- densification bookkeeping, names and semantics of scene/gaussian_model.py:190-196, :681-715 ----
+    def densification_setup(self, percent_dense=0.01):
+        N, dev = self._xyz.shape[0], self._xyz.device
+        self.percent_dense = percent_dense
+        self.xyz_gradient_accum = torch.zeros((N, 1), device=dev)
+        self.denom = torch.zeros((N, 1), device=dev)
+        self.max_radii2D = torch.zeros((N,), device=dev)
+        self._deformation_accum = torch.zeros((N, 3), device=dev)
+        self._deformation_table = torch.ones((N,), dtype=torch.bool, device=dev)
+
+    def add_densification_stats(self, viewspace_point_tensor, update_filter):
+        from . import densify as _d
+        _d.add_densification_stats(self, viewspace_point_tensor, update_filter)
+
+    def densify(self, max_grad, min_opacity, extent, max_screen_size, *a, **k):
+        from . import densify as _d
+        _d.densify(self, max_grad, min_opacity, extent, max_screen_size)
+
+    def prune(self, max_grad, min_opacity, extent, max_screen_size):
+        from . import densify as _d
+        _d.prune(self, max_grad, min_opacity, extent, max_screen_size)
+
+    def reset_opacity(self):
+        from . import densify as _d
+        _d.reset_opacity(self)
+
     def update_learning_rate(self, iteration):
         """scene/gaussian_model.py:284-298: per-iteration schedule of the xyz / grid / deformation groups (all three decay
         over position_lr_max_steps; the other groups keep their constant rates)."""
@@ -277,10 +303,10 @@ class ViewParallelTrainer:
         `[xyz | MLP | planes | opacity | scaling | rotation | screen-space xy]`; the SH gradient -- 192 of the 260 bytes a
         Gaussian contributes -- lives in one `[P,16,3]` buffer that the rasterizer backward of every view adds into (the
         first view of a step overwrites it, so it is never zero-filled);
-      * as soon as the LAST view's rasterizer backward has queued that addition, the SH tail starts on a side stream:
-        `ncclAllReduce(sum)` of the SH buffer (+ the `max` of the radii), then the Adam step of the two SH tensors straight
-        from that buffer (`FusedAdam.step_sh`) -- all of it overlapping the last view's field backward, the deferred spatial
-        HexPlane backward and the plane regulariser on the main stream;
+      * from inside the LAST view's backward -- right after its deformation-MLP backward has been queued (see step()) -- the SH
+        tail starts on a side stream: `ncclAllReduce(sum)` of the SH buffer (+ the `max` of the radii), then the Adam step of
+        the two SH tensors straight from that buffer (`FusedAdam.step_sh`) -- overlapping the time-plane / spatial HexPlane
+        backward, the arena all-reduce and the plane regulariser on the main stream;
       * the main stream then reduces the (4x smaller) arena, adds the regulariser and takes the Adam step of everything
         else; the step ends by joining the side stream.
     Same sums, same Adam arithmetic as one collective + one optimiser launch (tests/test_dist_gloo.py, tests/test_dist_nccl.py)."""
@@ -309,6 +335,13 @@ class ViewParallelTrainer:
         self._sh_started = False
         self._sh_done = None
         self.timeline = None                           # bench.py: dict of CUDA events around the phases of the last step
+        self._build_arena()
+
+    def _build_arena(self):
+        """(Re)creates the flat gradient arena for the model's CURRENT parameter tensors -- at construction and after every
+        densification / pruning event (the per-Gaussian parameters are new, differently sized tensors then)."""
+        model, stage = self.model, self.stage
+        dev = model.get_xyz.device
         P = model.get_xyz.shape[0]
         # flat gradient arena: [every parameter the loss reaches except (shared_shs) the SH tensors | screen-space xy per
         # Gaussian]; p.grad are views into it, so autograd accumulates in place and ONE collective (fp32 sum over
@@ -338,6 +371,11 @@ class ViewParallelTrainer:
         self.viewspace_grad = self.arena[off:off + 3 * P].view(P, 3)
         self.max_radii = torch.zeros(P, dtype=torch.int32, device=dev)
         self.sh_grad = None                            # [P,M,3], allocated with the first step's SH tensor
+
+
+    def rebuild(self):
+        """Call after model.densify() / model.prune(): new arena, new SH gradient buffer."""
+        self._build_arena()
 
     def _bind(self):
         self.arena.zero_()

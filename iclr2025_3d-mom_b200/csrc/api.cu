@@ -21,6 +21,7 @@ int g_opt_mlp_fwd_elect = env_int("B200GS_MLP_FWD_ELECT", 2);
 int g_opt_hexplane_time_bwd = env_int("B200GS_HEXPLANE_TIME_BWD", 2);    // 0.417 -> 0.354 ms (profiles/r2a_hexplane_time_check.txt)
 int g_opt_lookback_parallel = env_int("B200GS_LOOKBACK_PARALLEL", 1);    // 111 -> 103 us per 1M-pair sort (profiles/r2a_sort_check.txt)
 int g_opt_hexplane_time_fwd = env_int("B200GS_HEXPLANE_TIME_FWD", 2);    // 0.134 -> 0.112 ms, bit-identical
+int g_opt_composite_pairs = env_int("B200GS_COMPOSITE_PAIRS", 1);      // two pixels per lane + packed FP32 pairs in the compositing backward
 int g_opt_mlp_bwd_ablate = 0;                                             // timing experiments only (wrong results); never from the environment
 
 // ---- opt-in phase timing ---------------------------------------------------------------------------------------------
@@ -144,6 +145,7 @@ int b200gs_set_option(const char* name, int value)
     }
     if (name && !strcmp(name, "lookback_parallel")) { b200gs::g_opt_lookback_parallel = value; return 0; }
     if (name && !strcmp(name, "hexplane_time_fwd")) { b200gs::g_opt_hexplane_time_fwd = value; return 0; }
+    if (name && !strcmp(name, "composite_pairs")) { b200gs::g_opt_composite_pairs = value; return 0; }
     set_error("b200gs_set_option: unknown option '%s'", name ? name : "(null)");
     return -1;
 }
@@ -155,6 +157,7 @@ int b200gs_get_option(const char* name)
     if (name && !strcmp(name, "mlp_bwd_ablate")) return b200gs::g_opt_mlp_bwd_ablate;
     if (name && !strcmp(name, "lookback_parallel")) return b200gs::g_opt_lookback_parallel;
     if (name && !strcmp(name, "hexplane_time_fwd")) return b200gs::g_opt_hexplane_time_fwd;
+    if (name && !strcmp(name, "composite_pairs")) return b200gs::g_opt_composite_pairs;
     return -1;
 }
 

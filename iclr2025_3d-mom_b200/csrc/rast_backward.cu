@@ -9,6 +9,7 @@
 // (14 shuffles), accumulated per batch slot in shared memory, and leave the SM as three
 // 128-bit vector reductions per (tile, splat) instance.
 #include "rast_state.cuh"
+#include "f32x2.cuh"
 
 namespace b200gs {
 
@@ -194,6 +195,211 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ l
             if (a2.x != 0.f || a2.y != 0.f || a2.z != 0.f) red_add_v4(dst + 8, a2.x, a2.y, a2.z, 0.f);
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             sa[0] = z; sa[1] = z; sa[2] = z;
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+}
+
+
+// ---- the same kernel with TWO pixels per lane and packed FP32 pairs (option "composite_pairs", default on) -------------------
+// The kernel above is issue-slot bound (ncu: 75 % of issue slots busy, FMA pipe 34 %; 88 instructions per (warp, splat) of which
+// ~44 are the butterfly).  Here a warp covers an 8x8 patch: lane (lx, ly) owns pixels (lx, ly) and (lx, ly + 4) and carries their
+// state as f32x2 pairs, so the per-pixel arithmetic is issued once for both (FFMA2 / FMUL2 / FADD2, splat constants as
+// scalar-broadcast operands) and the 10-value butterfly is paid once per 64 pixels instead of once per 32.
+//   * A pixel for which the splat is inactive takes part with alpha = G = 0: T / (1 - 0), w = 0 and every partial gradient are
+//     exact no-ops, and the "previous colour" recurrence  rec = la * lc + (1 - la) * rec  evaluated one splat early gives the same
+//     value one splat later (0 * C + 1 * rec), so no per-pixel selects are needed and the previous colour is warp-uniform.
+//   * 1 / (1 - alpha) uses MUFU.RCP (relative error ~1e-7 per pair, 1e-5 over a chain of 100 contributors; the bar for these
+//     gradients is 1e-3); exp stays the accurate sequence (see below).
+constexpr int CB2_THREADS = 128;
+
+__global__ void __launch_bounds__(CB2_THREADS)
+composite_bwd2_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ list, int W, int H, int grid_x,
+                      const float4* __restrict__ recA, const float4* __restrict__ recB,
+                      const float4* __restrict__ recC, const float* __restrict__ bg,
+                      const float* __restrict__ final_T, const u32* __restrict__ n_contrib,
+                      const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_depth,
+                      float* __restrict__ acc)
+{
+    __shared__ BStage stage[2];
+    __shared__ __align__(16) float s_acc[CB * ACC];
+    __shared__ u32 s_max[4];
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 tile = blockIdx.x;
+    const u32 tx = tile % (u32)grid_x, ty = tile / (u32)grid_x;
+    const u32 px = tx * TILE_X + (warp & 1) * 8 + (lane & 7);
+    const u32 pyA = ty * TILE_Y + (warp >> 1) * 8 + (lane >> 3), pyB = pyA + 4;
+    const bool inA = px < (u32)W && pyA < (u32)H, inB = px < (u32)W && pyB < (u32)H;
+    const float fxp = (float)px;
+    const f2 fyp = pk((float)pyA, (float)pyB);
+    const uint2 range = ranges[tile];
+    const size_t pidA = (size_t)pyA * W + px, pidB = (size_t)pyB * W + px;
+    const size_t HW = (size_t)H * W;
+    const u32 lastA = inA ? n_contrib[pidA] : 0, lastB = inB ? n_contrib[pidB] : 0;
+    const float patch_x = (float)(tx * TILE_X + (warp & 1) * 8), patch_y = (float)(ty * TILE_Y + (warp >> 1) * 8);
+    u32 m = max(lastA, lastB);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const u32 warp_last = m;
+    if (lane == 0) s_max[warp] = m;
+    for (u32 i = tid; i < CB * ACC; i += CB2_THREADS) s_acc[i] = 0.f;
+    __syncthreads();
+    u32 n_eff = max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3]));
+    n_eff = min(n_eff, range.y - range.x);
+    if (n_eff == 0) return;
+    const int rounds = (int)((n_eff + CB - 1) / CB);
+
+    const f2 T_final = pk(inA ? final_T[pidA] : 0.f, inB ? final_T[pidB] : 0.f);
+    f2 T = T_final;
+    const f2 dLp0 = pk(inA ? dL_dpix[pidA] : 0.f, inB ? dL_dpix[pidB] : 0.f);
+    const f2 dLp1 = pk(inA ? dL_dpix[HW + pidA] : 0.f, inB ? dL_dpix[HW + pidB] : 0.f);
+    const f2 dLp2 = pk(inA ? dL_dpix[2 * HW + pidA] : 0.f, inB ? dL_dpix[2 * HW + pidB] : 0.f);
+    const f2 dLd = pk((inA && dL_dpix_depth) ? dL_dpix_depth[pidA] : 0.f, (inB && dL_dpix_depth) ? dL_dpix_depth[pidB] : 0.f);
+    // -T_final * (bg . dL_dpixel): the background term of dL_dalpha before its 1 / (1 - alpha)
+    const f2 nTb = mul2(sub2(pk1(0.f), T_final), fma2(pk1(bg[2]), dLp2, fma2(pk1(bg[1]), dLp1, mul2(pk1(bg[0]), dLp0))));
+    f2 rec0 = pk1(0.f), rec1 = pk1(0.f), rec2 = pk1(0.f), recd = pk1(0.f), last_alpha = pk1(0.f);
+    float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ld = 0.f;          // colour / depth of the previous splat this warp processed
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+    auto fill = [&](BStage& st, u32 first) {
+#pragma unroll
+        for (int h = 0; h < CB / CB2_THREADS; ++h) {
+            const u32 t = tid + h * CB2_THREADS, pos = first + t;
+            if (pos < n_eff) {
+                const u32 g = __ldg(list + (range.x + n_eff - 1 - pos));
+                st.gid[t] = g;
+                cp_async16(&st.A[t], recA + g);
+                cp_async16(&st.B[t], recB + g);
+                cp_async16(&st.C[t], recC + g);
+            }
+        }
+    };
+    fill(stage[0], 0);
+    cp_async_commit();
+    for (int r = 0; r < rounds; ++r) {
+        if (r + 1 < rounds) fill(stage[(r + 1) & 1], (u32)(r + 1) * CB);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const BStage& st = stage[r & 1];
+        const int cnt = (int)min((u32)CB, n_eff - (u32)r * CB);
+        u32 masks[CB / 32];
+#pragma unroll
+        for (int q = 0; q < CB / 32; ++q) {
+            const int j = q * 32 + (int)lane;
+            const u32 p = n_eff - 1u - ((u32)r * CB + (u32)j);
+            const bool keep = j < cnt && p < warp_last && splat_may_touch_patch(st.A[j], st.B[j], patch_x, patch_y, 7.f);
+            masks[q] = __ballot_sync(0xffffffffu, keep);
+        }
+#pragma unroll
+        for (int q = 0; q < CB / 32; ++q) {
+          u32 mq = masks[q];
+          while (mq != 0) {
+            const int j = q * 32 + __ffs(mq) - 1;
+            mq &= mq - 1;
+            const u32 contributor = n_eff - 1u - ((u32)r * CB + (u32)j);
+            const float4 A = st.A[j];
+            const float4 B = st.B[j];
+            const float dx = A.x - fxp;
+            const f2 dy = sub2(pk1(A.y), fyp);
+            // power = -0.5 (a dx^2 + c dy^2) - b dx dy
+            const float adx2 = A.z * dx * dx, bdx = A.w * dx;
+            const f2 quad = fma2(mul2(pk1(B.x), dy), dy, pk1(adx2));
+            const f2 power = fma2(quad, pk1(-0.5f), mul2(pk1(-bdx), dy));
+            const float pwA = lo(power), pwB = hi(power);
+            bool actA = contributor < lastA && !(pwA > 0.0f) && !(pwA < B.w);
+            bool actB = contributor < lastB && !(pwB > 0.0f) && !(pwB < B.w);
+            // the accurate expf, as in the forward and in the reference's backward: T is recovered as T_final / prod (1 - alpha), so
+            // an alpha that differs from the forward's by 3e-7 (ex2.approx) is amplified by 1 / (1 - alpha) along the chain
+            const float GA = expf(pwA), GB = expf(pwB);
+            float aA = fminf(0.99f, B.y * GA), aB = fminf(0.99f, B.y * GB);
+            actA = actA && !(aA < 1.0f / 255.0f);
+            actB = actB && !(aB < 1.0f / 255.0f);
+            if (!__any_sync(0xffffffffu, actA || actB)) continue;
+            // an inactive pixel takes part with alpha = G = 0 (see the kernel comment)
+            const f2 G = pk(actA ? GA : 0.f, actB ? GB : 0.f);
+            const f2 alpha = pk(actA ? aA : 0.f, actB ? aB : 0.f);
+            const float4 Cc = st.C[j];
+            const f2 oma = sub2(pk1(1.f), alpha);
+            float qA, qB;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(qA) : "f"(lo(oma)));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(qB) : "f"(hi(oma)));
+            const f2 q1 = pk(qA, qB);                     // 1 / (1 - alpha)
+            T = mul2(T, q1);
+            const f2 w = mul2(alpha, T);
+            const f2 omla = sub2(pk1(1.f), last_alpha);
+            rec0 = fma2(last_alpha, pk1(lc0), mul2(omla, rec0));
+            rec1 = fma2(last_alpha, pk1(lc1), mul2(omla, rec1));
+            rec2 = fma2(last_alpha, pk1(lc2), mul2(omla, rec2));
+            recd = fma2(last_alpha, pk1(ld), mul2(omla, recd));
+            lc0 = Cc.x; lc1 = Cc.y; lc2 = Cc.z; ld = B.z;
+            last_alpha = alpha;
+            f2 dLa = mul2(sub2(pk1(Cc.x), rec0), dLp0);
+            dLa = fma2(sub2(pk1(Cc.y), rec1), dLp1, dLa);
+            dLa = fma2(sub2(pk1(Cc.z), rec2), dLp2, dLa);
+            dLa = fma2(sub2(pk1(B.z), recd), dLd, dLa);
+            dLa = fma2(nTb, q1, mul2(dLa, T));            // * T  +  (-T_final / (1 - alpha)) * (bg . dL_dpixel)
+            const f2 dL_dG = mul2(pk1(B.y), dLa);
+            const f2 gdx = mul2(G, pk1(dx)), gdy = mul2(G, dy);
+            const f2 dGx = fma2(gdy, pk1(-A.w), mul2(gdx, pk1(-A.z)));
+            const f2 dGy = fma2(gdx, pk1(-A.w), mul2(gdy, pk1(-B.x)));
+            const f2 hx = mul2(gdx, dL_dG), hy = mul2(gdy, dL_dG);
+            const f2 mhdy = mul2(dy, pk1(-0.5f));
+            const f2 p0 = mul2(mul2(dL_dG, dGx), pk1(ddelx_dx));      // d mean2D.x
+            const f2 p1 = mul2(mul2(dL_dG, dGy), pk1(ddely_dy));      // d mean2D.y
+            const f2 p2 = mul2(hx, pk1(-0.5f * dx));                  // d conic.a
+            const f2 p3 = mul2(hx, mhdy);                             // d conic.b
+            const f2 p4 = mul2(hy, mhdy);                             // d conic.c
+            const f2 p5 = mul2(G, dLa);                               // d opacity
+            const f2 p6 = mul2(w, dLd);                               // d depth
+            const f2 p7 = mul2(w, dLp0), p8 = mul2(w, dLp1), p9 = mul2(w, dLp2);   // d colour
+            const float v0 = lo(p0) + hi(p0), v1 = lo(p1) + hi(p1), v2 = lo(p2) + hi(p2), v3 = lo(p3) + hi(p3), v4 = lo(p4) + hi(p4),
+                        v5 = lo(p5) + hi(p5), v6 = lo(p6) + hi(p6), v7 = lo(p7) + hi(p7), v8 = lo(p8) + hi(p8), v9 = lo(p9) + hi(p9);
+            // transposed butterfly: 8 values (v0..v7) -> lane>>2 owns value (lane>>2); v8,v9 -> lanes 0/16
+            {
+                const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+                float u0 = (h16 ? v4 : v0) + __shfl_xor_sync(0xffffffffu, h16 ? v0 : v4, 16);
+                float u1 = (h16 ? v5 : v1) + __shfl_xor_sync(0xffffffffu, h16 ? v1 : v5, 16);
+                float u2 = (h16 ? v6 : v2) + __shfl_xor_sync(0xffffffffu, h16 ? v2 : v6, 16);
+                float u3 = (h16 ? v7 : v3) + __shfl_xor_sync(0xffffffffu, h16 ? v3 : v7, 16);
+                float y = (h16 ? v9 : v8) + __shfl_xor_sync(0xffffffffu, h16 ? v8 : v9, 16);
+                float w0 = (h8 ? u2 : u0) + __shfl_xor_sync(0xffffffffu, h8 ? u0 : u2, 8);
+                float w1 = (h8 ? u3 : u1) + __shfl_xor_sync(0xffffffffu, h8 ? u1 : u3, 8);
+                y += __shfl_xor_sync(0xffffffffu, y, 8);
+                float x = (h4 ? w1 : w0) + __shfl_xor_sync(0xffffffffu, h4 ? w0 : w1, 4);
+                y += __shfl_xor_sync(0xffffffffu, y, 4);
+                x += __shfl_xor_sync(0xffffffffu, x, 2);
+                y += __shfl_xor_sync(0xffffffffu, y, 2);
+                x += __shfl_xor_sync(0xffffffffu, x, 1);
+                y += __shfl_xor_sync(0xffffffffu, y, 1);
+                if ((lane & 3) == 0) {
+                    const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                    const int slot = (k == 7) ? 8 : k;
+                    if (x != 0.f) atomicAdd(&s_acc[j * ACC + slot], x);
+                }
+                if ((lane & 15) == 0) {
+                    const int slot = (lane & 16) ? 10 : 9;
+                    if (y != 0.f) atomicAdd(&s_acc[j * ACC + slot], y);
+                }
+            }
+          }
+        }
+        __syncthreads();
+        // flush this batch: one thread per instance, three 128-bit reductions
+#pragma unroll
+        for (int h = 0; h < CB / CB2_THREADS; ++h) {
+            const int t = (int)tid + h * CB2_THREADS;
+            if (t < cnt) {
+                float4* sa = reinterpret_cast<float4*>(&s_acc[t * ACC]);
+                const float4 a0 = sa[0], a1 = sa[1], a2 = sa[2];
+                float* dst = acc + (size_t)st.gid[t] * ACC;
+                if (a0.x != 0.f || a0.y != 0.f || a0.z != 0.f || a0.w != 0.f) red_add_v4(dst, a0.x, a0.y, a0.z, a0.w);
+                if (a1.x != 0.f || a1.y != 0.f || a1.z != 0.f) red_add_v4(dst + 4, a1.x, a1.y, a1.z, 0.f);
+                if (a2.x != 0.f || a2.y != 0.f || a2.z != 0.f) red_add_v4(dst + 8, a2.x, a2.y, a2.z, 0.f);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                sa[0] = z; sa[1] = z; sa[2] = z;
+            }
         }
         __syncthreads();
     }
@@ -533,7 +739,11 @@ int rast_backward(int P, int D, int M, long long R, int W, int H, const float* b
     {
         ProfScope prof(PROF_COMPOSITE_BWD, stream);
         cudaMemsetAsync(grad_arena, 0, (size_t)P * ACC * sizeof(float), stream);
-        if (R > 0)
+        if (R > 0 && g_opt_composite_pairs != 0)
+            composite_bwd2_kernel<<<(unsigned)tiles, CB2_THREADS, 0, stream>>>(
+                img.ranges, sorted_list, W, H, grid_x, g.recA, g.recB, g.recC, bg, img.final_T, img.n_contrib,
+                dL_dpix, dL_dpix_depth, grad_arena);
+        else if (R > 0)
             composite_bwd_kernel<<<(unsigned)tiles, TILE_PIXELS, 0, stream>>>(
                 img.ranges, sorted_list, W, H, grid_x, g.recA, g.recB, g.recC, bg, img.final_T, img.n_contrib,
                 dL_dpix, dL_dpix_depth, grad_arena);

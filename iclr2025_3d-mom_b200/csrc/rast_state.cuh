@@ -97,12 +97,12 @@ struct ImgState {
 // attained at the box point closest to the centre along one of the two facing edges, so two
 // candidates suffice.  Anything doubtful (non-PD conic, NaNs) is kept; survivors still run the exact
 // per-pixel test, so results are unchanged.
-__device__ __forceinline__ bool splat_may_touch_patch(const float4 A, const float4 B, float bx, float by)
+__device__ __forceinline__ bool splat_may_touch_patch(const float4 A, const float4 B, float bx, float by, float patch_h = 3.f)
 {
     const float a = A.z, b = A.w, c = B.x;
     if (!(a > 0.f) || !(c > 0.f)) return true;
     const float dx_hi = A.x - bx, dx_lo = dx_hi - 7.f;          // d.x range over the patch
-    const float dy_hi = A.y - by, dy_lo = dy_hi - 3.f;
+    const float dy_hi = A.y - by, dy_lo = dy_hi - patch_h;          // patch_h = rows - 1 (8x4 patch: 3, 8x8 patch: 7)
     const float cx = fminf(fmaxf(0.f, dx_lo), dx_hi), cy = fminf(fmaxf(0.f, dy_lo), dy_hi);
     const float y1 = fminf(fmaxf(__fdividef(-b * cx, c), dy_lo), dy_hi);
     const float x2 = fminf(fmaxf(__fdividef(-b * cy, a), dx_lo), dx_hi);
