@@ -127,6 +127,9 @@ class GaussianState(nn.Module):
         self.max_radii2D = torch.zeros((N,), device=dev)
         self._deformation_accum = torch.zeros((N, 3), device=dev)
         self._deformation_table = torch.ones((N,), dtype=torch.bool, device=dev)
+        if self.optimizer is not None:
+            from . import densify as _d
+            _d.warmup(self)                  # first-use costs and allocator growth paid here, not inside the first event
 
     def add_densification_stats(self, viewspace_point_tensor, update_filter):
         from . import densify as _d

@@ -441,11 +441,11 @@ class _DeformFn(torch.autograd.Function):
     S_in: None, or the differentiable spatial product of _SpatialFn (then only the time planes are sampled here and
     dL/dS_in is returned for autograd to sum over the views of a batch).
     """
-    N_FIXED = 12
+    N_FIXED = 13
     N_W = 14
 
     @staticmethod
-    def forward(ctx, xyz, scales, rot, times, scene_flow, frame_num, delta_scale, aabb, levels, res, heads, S_in, *rest):
+    def forward(ctx, xyz, scales, rot, times, scene_flow, frame_num, delta_scale, aabb, levels, res, heads, S_in, need_backward, *rest):
         weights, planes = rest[:_DeformFn.N_W], rest[_DeformFn.N_W:]
         xyz = xyz.contiguous(); scales = scales.contiguous(); rot = rot.contiguous(); scene_flow = scene_flow.contiguous()
         _check_cuda_f32(xyz, scales, rot, scene_flow, aabb, *planes, *[w for w in weights if w is not None])
@@ -490,7 +490,9 @@ class _DeformFn(torch.autograd.Function):
                   "hexplane_forward")
         mw = _DeformFn._weights_struct(weights, heads, 32 * levels)
         mw.feat_tiled = int(ctx.feat_tiled)
-        saved = torch.empty((L.b200gs_deform_mlp_saved_floats(P),), dtype=torch.float32, device=dev)
+        # inference (the caller knows no backward will follow: torch.no_grad() or nothing requires grad): no activation stash
+        stash = need_backward or not all(heads)
+        saved = torch.empty((L.b200gs_deform_mlp_saved_floats(P),), dtype=torch.float32, device=dev) if stash else None
         pts_o = torch.empty_like(xyz); scales_o = torch.empty_like(scales); rot_o = torch.empty_like(rot)
         if torch.is_tensor(frame_num):
             fn_dev = frame_num.to(device=dev, dtype=torch.float32).reshape(-1)[:1].contiguous()
@@ -499,8 +501,10 @@ class _DeformFn(torch.autograd.Function):
             fn_dev, fn_val, fn_ptr = None, float(frame_num), None
         check(L.b200gs_deform_mlp_forward(ctypes.byref(mw), P, feat.data_ptr(), xyz.data_ptr(), scales.data_ptr(),
                                           rot.data_ptr(), scene_flow.data_ptr(), fn_val, fn_ptr, float(delta_scale),
-                                          pts_o.data_ptr(), scales_o.data_ptr(), rot_o.data_ptr(), saved.data_ptr(), stream),
+                                          pts_o.data_ptr(), scales_o.data_ptr(), rot_o.data_ptr(), saved.data_ptr() if saved is not None else None, stream),
               "deform_mlp_forward")
+        if saved is None:
+            saved = torch.empty(0, device=dev)
         ctx.save_for_backward(xyz, tt if tt is not None else torch.empty(0), aabb, feat, saved,
                               *[w if w is not None else torch.empty(0) for w in weights], *planes)
         ctx.meta = (levels, res, heads, ts, tt is not None)
@@ -527,6 +531,8 @@ class _DeformFn(torch.autograd.Function):
         xyz, tt, aabb, feat, saved, *rest = ctx.saved_tensors
         weights, planes = rest[:_DeformFn.N_W], rest[_DeformFn.N_W:]
         levels, res, heads, ts, has_t = ctx.meta
+        if saved.numel() == 0:
+            raise RuntimeError("deform_network: backward through a forward that ran in inference mode (no activation stash)")
         L = _lib.lib()
         P = int(xyz.shape[0])
         stream = current_stream()
@@ -589,7 +595,7 @@ class _DeformFn(torch.autograd.Function):
                 for i in range(2 + 4 * h, 6 + 4 * h):
                     gw_out[i] = None
         gp_out = [None if dp is not None else g for g, dp in zip(gplanes, direct_p)]
-        return (d_xyz, d_scales, d_rot, None, None, None, None, None, None, None, None, d_S, *gw_out, *gp_out)
+        return (d_xyz, d_scales, d_rot, None, None, None, None, None, None, None, None, d_S, None, *gw_out, *gp_out)
 
 
 def _regulation_launch(field, weights, loss_accum, grads):
@@ -798,6 +804,8 @@ class Deformation(nn.Module):
         # time_emb: the reference's [P,1] tensor (gaussian_renderer/__init__.py:56), or one Python float for the whole call
         t_arg = time_emb[:, :1] if torch.is_tensor(time_emb) else float(time_emb)
         S_in = None
+        need_backward = torch.is_grad_enabled() and (any(t.requires_grad for t in (rays_pts_emb, scales_emb, rotations_emb))
+                                                     or any(w.requires_grad for w in weights) or self.grid.grids[0][0].requires_grad)
         if torch.is_tensor(t_arg) and xyz.is_cuda:
             # the reference's render() hands over the camera's ONE timestamp as a [P,1] tensor (gaussian_renderer/__init__.py:56)
             tt, ts = _times_arg(t_arg, int(xyz.shape[0]))
@@ -807,7 +815,7 @@ class Deformation(nn.Module):
             S_in = _auto_spatial(xyz, self.grid)
         pts, scales, rotations = _DeformFn.apply(xyz, scales_emb[:, :3], rotations_emb[:, :4], t_arg, scene_flow,
                                                  frame_num, delta_scale, self.grid.aabb, len(self.grid.grids),
-                                                 tuple(self.grid._res), heads, S_in, *weights, *self.grid._planes())
+                                                 tuple(self.grid._res), heads, S_in, need_backward, *weights, *self.grid._planes())
         opacity = opacity_emb[:, :1]
         shs = shs_emb
         return pts, scales, rotations, opacity, shs

@@ -92,6 +92,8 @@ def install(reference_root):
                 groups = [{kk: vv for kk, vv in g.items() if kk in ("params", "lr", "name")} for g in self.optimizer.param_groups]
                 self.optimizer = FusedAdam(groups, lr=0.0, eps=1e-15)
                 _print_summary.optimizer = type(self.optimizer).__name__
+                if os.environ.get("B200GS_FUSED_DENSIFY", "1") != "0" and self._xyz.is_cuda:
+                    densify.warmup(self)         # first-use kernel loading + allocator growth outside the first densification event
                 return out
             setattr(gm.GaussianModel, name, wrapped)
         orig_reg = gm.GaussianModel.compute_regulation

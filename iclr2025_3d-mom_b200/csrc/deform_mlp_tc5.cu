@@ -308,7 +308,9 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
         for (int i = tid; i < MW; i += NT2) bias[MW + h * MW + i] = __ldg(a.w.b2[h] + i);
         if (tid < 16) bias[4 * MW + h * 16 + tid] = tid < kdim[h] ? __ldg(a.w.b3[h] + tid) : 0.f;
     }
-    if (F == 64 && blockIdx.x == 0) {           // transposed TF32 weight images for the tcgen05 backward (see tc5_common.cuh)
+    // a.saved == nullptr: inference (no backward will follow) -- nothing is stashed, 1 KB per point less HBM traffic
+    const bool stash_on = a.saved != nullptr;
+    if (F == 64 && blockIdx.x == 0 && stash_on) {           // transposed TF32 weight images for the tcgen05 backward (see tc5_common.cuh)
         float* images = a.saved + 4 * stash_plane_floats(a.P);
         for (int h = 0; h < 3; ++h) write_bwd_weight_image(images, h, a.w.w2[h], NT2);
         write_bwd_weight_image(images, 3, a.w.w1, NT2);
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
         tmem_wait_ld();
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(fmaxf(__uint_as_float(v[e]) + b[32 * cT + e], 0.f));
-        if (valid && !DEFER_STASH) {
+        if (valid && !DEFER_STASH && stash_on) {
             float* dst = stash_plane + stash_off(row, 32 * cT);          // this thread's 8 chunks are 16 floats apart
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(NT2, 1) deform_mlp_fwd_tc5v2_kernel(const __gr
         for (int e = 0; e < 32; ++e) lo[e] = __float_as_uint(tf32_lo(__uint_as_float(v[e])));      // hi = the raw value (hardware truncates)
     };
     auto deferred_stash = [&](float* stash_plane, long long row, bool valid, const u32* v) {
-        if (DEFER_STASH && valid) {
+        if (DEFER_STASH && valid && stash_on) {
             float* dst = stash_plane + stash_off(row, 32 * cT);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -512,6 +514,10 @@ int deform_mlp_forward_tc5(const b200gs_mlp_weights* w, long long P, const float
     const long long nblocks = (P + tc5::ROWS - 1) / tc5::ROWS;
     const int grid = (int)(nblocks < NUM_SMS ? nblocks : NUM_SMS);
     const size_t smem = tc5::fwd_smem(w->feat_dim);
+    if (!saved && !(w->w2[0] && w->w2[1] && w->w2[2])) {
+        set_error("deform_mlp_forward: saved == NULL (inference, nothing stashed) needs all three heads enabled");
+        return -1;
+    }
     if (w->w2[0] && w->w2[1] && w->w2[2]) {          // all heads on (the reference's configuration): pipelined kernel
         // experimental issue idiom (see the kernel's comment): opt-in until it has been measured on the GPU
         if (g_opt_mlp_fwd_elect != 0 && w->feat_dim == 64) {

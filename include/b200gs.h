@@ -46,6 +46,9 @@ int b200gs_version(void);
  *   "lookback_parallel" chained scans of the radix sort passes and of the instance emission (default 1):
  *                    predecessors' states are read 8 (per digit) / 32 (per warp) at a time instead of one dependent L2 round
  *                    trip each; identical results
+ *   "composite_pairs" compositing backward (default 1): a lane owns TWO pixels of an 8x8 warp patch and carries their state as
+ *                    packed FP32 pairs (FFMA2 / FMUL2 / FADD2), the gradient butterfly is paid once per 64 pixels: 0.765 -> 0.608 ms
+ *                    per 1M-Gaussian 1280x720 view; 0 = the one-pixel-per-lane kernel (rast_backward.cu)
  * Measured on a B200 in round 2 (profiles/r2a_*.txt); the variants that lost ("sort_small_tiles", "sort_balanced_digits", the
  * resident-weight and double-buffered MLP backward kernels) were deleted.
  * Same arithmetic in every variant.  ("mlp_bwd_ablate" is a profiling aid, not a variant: it removes one part of the MLP
@@ -265,7 +268,9 @@ size_t b200gs_deform_mlp_saved_floats(long long P);
 /* pts_out = xyz + pos_head + delta_scale*(frame_num*scene_flow); scales_out = scales + scale_head;
  * rot_out = rot + rot_head (deformation.py:113-135). frame_num_dev (device float, may be null)
  * overrides frame_num: the reference hands frame_num over as a 0-d CUDA tensor (scene/dataset.py:39)
- * and reading it on the host would cost a device sync per view. */
+ * and reading it on the host would cost a device sync per view.
+ * saved: the activation stash the backward reads (b200gs_deform_mlp_saved_floats(P) floats), or NULL for INFERENCE
+ * (render_4DGS.py, torch.no_grad()): nothing is stashed, 1 KB per point less HBM traffic (needs all three heads enabled). */
 int b200gs_deform_mlp_forward(const b200gs_mlp_weights* w /* host */, long long P, const float* features,
                               const float* xyz, const float* scales, const float* rot, const float* scene_flow,
                               float frame_num, const float* frame_num_dev, float delta_scale, float* pts_out, float* scales_out, float* rot_out,

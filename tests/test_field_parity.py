@@ -159,3 +159,28 @@ def test_hexplane_field_standalone_and_state_dict():
               "timenet.2.bias", "time_poc", "pos_poc", "rotation_scaling_poc", "opacity_poc"]:
         assert k in keys, k
     assert len(net.get_grid_parameters()) == 13 and all("grid" not in n for n, _ in net.named_parameters() if False)
+
+
+def test_inference_forward_without_stash_is_bit_identical():
+    """Under torch.no_grad() the MLP forward is told that no backward follows (saved = NULL): nothing is stashed, the outputs
+    are the same bits; a backward through such a forward is refused."""
+    net = _model([1, 2], 50)
+    P = 20011
+    xyz, scales, rot, opacity, shs, flow = _inputs(P)
+    time = torch.full((P, 1), 0.61, device="cuda")
+    fn = torch.tensor(7, device="cuda")
+    from b200gs import field
+    a = [t.clone().requires_grad_(True) for t in (xyz, scales, rot)]
+    keep = field.AUTOGRAD_SPATIAL_SHARING
+    field.AUTOGRAD_SPATIAL_SHARING = False          # same HexPlane kernels on both sides: only the stash differs
+    try:
+        pts, sc, rt, _, _ = net(a[0], a[1], a[2], opacity, shs, time, flow, fn, 1)
+    finally:
+        field.AUTOGRAD_SPATIAL_SHARING = keep
+    with torch.no_grad():
+        p2, s2, r2, _, _ = net(xyz, scales, rot, opacity, shs, time, flow, fn, 1)
+    assert torch.equal(pts.detach(), p2) and torch.equal(sc.detach(), s2) and torch.equal(rt.detach(), r2)
+    assert not p2.requires_grad
+    # with the spatial product shared under autograd (the default) the field re-associates the six-plane product: FP32 rounding only
+    p3, s3, r3, _, _ = net(a[0], a[1], a[2], opacity, shs, time, flow, fn, 1)
+    assert _rel(p3.detach(), p2) < 2e-6 and _rel(s3.detach(), s2) < 2e-6 and _rel(r3.detach(), r2) < 2e-6
