@@ -71,3 +71,44 @@ def test_to8b_and_frame_ring():
     while ring.count:
         got.append(ring.pop().copy())
     assert len(got) == 6 and all(np.array_equal(a, to8b(f).transpose(1, 2, 0)) for a, f in zip(got, frames))
+
+
+def test_l1_against_uint8_target_equals_the_float_path():
+    """The dataset's own uint8 HWC image as the L1 target (converted on the device as utils/general_utils.py:PILtoTorch converts
+    it on the host: u8 / 255.0) gives the same gradient bits and the same loss as the float CHW target."""
+    from b200gs import fusedops
+    g = torch.Generator().manual_seed(5)
+    H, W = 75, 130
+    u8 = (torch.rand(H, W, 3, generator=g) * 255.999).to(torch.uint8)
+    target = (u8.float() / 255.0).permute(2, 0, 1).contiguous().cuda()
+    render = torch.rand(3, H, W, generator=g).cuda()
+    render[0, :4, :4] = target[0, :4, :4]                     # exact hits: sign(0) = 0
+    la, lb = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    da = fusedops.l1_loss_and_grad(render, target, 0.125 / render.numel(), la)
+    db = fusedops.l1_loss_and_grad(render, u8.cuda(), 0.125 / render.numel(), lb)
+    assert torch.equal(da, db)
+    assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(la))
+    ref = 0.125 * (render - target).abs().mean()
+    assert abs(float(lb) - float(ref)) <= 2e-6 * float(ref)
+
+
+def test_host_image_feeder_and_loss_ring():
+    """engine.HostImageFeeder (ground truth uploaded one step ahead on a side stream) hands every step the right images;
+    engine.LossRing returns the value pushed `lag` steps ago without a per-step device sync."""
+    from b200gs import engine
+    dev = torch.device("cuda", 0)
+    steps = [[(torch.full((8, 9, 3), 10 * s + v, dtype=torch.uint8)).pin_memory() for v in range(2)] for s in range(5)]
+    feeder = engine.HostImageFeeder(steps[0], dev)
+    ring = engine.LossRing(depth=4)
+    feeder.prefetch(steps[0])
+    for s in range(5):
+        imgs = feeder.take()
+        if s + 1 < 5:
+            feeder.prefetch(steps[s + 1])
+        got = [int(t.float().mean().item()) for t in imgs]
+        assert got == [10 * s, 10 * s + 1], (s, got)
+        torch.cuda._sleep(200000)                       # the step's work
+        feeder.release()
+        ring.push(torch.tensor([float(s)], device=dev))
+        assert ring.read(lag=1) == (None if s == 0 else float(s - 1))
+    assert ring.read(lag=0) == 4.0
