@@ -830,7 +830,9 @@ def _main():
         model.optimizer.step = timed_opt_step
 
     W_ = max(args.warmup, 3)
-    for _ in range(W_):
+    # (N > 1: three more untimed steps -- NCCL sets up its channels / algorithms for the two message sizes lazily, on two
+    #  streams, and a straggling rank in the first timed steps showed up as a 15 % slower N = 4 line once)
+    for _ in range(W_ + (3 if world > 1 else 0)):
         trainer.step(cams, gts_dev, global_batch=n_global)
     adam_ms.clear()
     timeline = None

@@ -16,9 +16,15 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$KR
 tail -3 gpurun_out/ncu_full_$TAG.log
 # summaries are extracted HERE (the report itself can exceed what gpurun copies back: it is dropped if larger than 45 MB)
 python tools/ncu_summary.py gpurun_out/prof_$TAG.ncu-rep --json gpurun_out/ncu_dram_bytes_$TAG.json > gpurun_out/ncu_full_$TAG.csv 2> gpurun_out/ncu_summary_$TAG.err
-for k in deform_mlp_bwd deform_mlp_fwd composite_bwd composite_fwd rs_onesweep_pass hexplane_time_bwd2 hexplane_bwd_kernel; do
+for k in deform_mlp_bwd deform_mlp_fwd composite_bwd2 composite_fwd rs_onesweep_pass hexplane_time_bwd2 hexplane_bwd_kernel; do
     python tools/ncu_stalls.py gpurun_out/prof_$TAG.ncu-rep $k > gpurun_out/stalls_${k}_$TAG.txt 2>&1
 done
+# 3. the launch list of bench.py itself (the command whose `kernels` shares it must agree with): training steps only
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_bench_$TAG.csv \
+    python bench.py --steps 2 --warmup 3 --render-frames 0 --no-raster-only --no-c5 --no-launcher-path --no-cpu-baseline > gpurun_out/ncu_bench_$TAG.json 2> gpurun_out/ncu_bench_$TAG.err; echo "bench launch list rc=$?"
+python tools/ncu_launch_shares.py gpurun_out/launches_bench_$TAG.csv > gpurun_out/launch_shares_bench_$TAG.txt 2>&1
+python tools/ncu_launch_shares.py gpurun_out/launches_$TAG.csv > gpurun_out/launch_shares_view_$TAG.txt 2>&1
+gzip -f gpurun_out/launches_bench_$TAG.csv
 ls -la gpurun_out/prof_$TAG.ncu-rep
 [ $(stat -c %s gpurun_out/prof_$TAG.ncu-rep) -gt 45000000 ] && rm -f gpurun_out/prof_$TAG.ncu-rep
 du -sh gpurun_out
