@@ -269,8 +269,8 @@ def begin_shared_step(net, xyz_param, inference=False):
     check(_lib.lib().b200gs_hexplane_forward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(order), None, 0.0, MASK_SPATIAL, None,
                                                     S.data_ptr(), current_stream()), "hexplane_forward(spatial)")
     _lib.COUNTERS["spatial_product_evaluations"] += 1
-    _SHARED = {"key": _shared_key(xyz, xyz_param._version, P, grid.aabb, planes), "S": S, "A": None if inference else torch.zeros_like(S),
-               "xyz_param": xyz_param, "grid": grid, "order": order, "used": False}
+    _SHARED = {"key": _shared_key(xyz, xyz_param._version, P, grid.aabb, planes), "S": S, "A": None if inference else torch.empty_like(S), "A_written": False,
+               "xyz_param": xyz_param, "grid": grid, "order": order, "used": False}      # A: written by the first view's backward, added to by the others
 
 
 @contextlib.contextmanager
@@ -292,8 +292,8 @@ def finish_shared_step():
     """The deferred spatial backward: plane gradients into the planes' .grad, xyz gradient into xyz_param.grad."""
     global _SHARED
     sh, _SHARED = _SHARED, None
-    if sh is None or not sh["used"]:
-        return
+    if sh is None or not sh["used"] or not sh.get("A_written", False):
+        return          # no view's backward contributed
     grid, xyz_param = sh["grid"], sh["xyz_param"]
     planes = grid._planes()
     grads = []
@@ -568,15 +568,19 @@ class _DeformFn(torch.autograd.Function):
         if ctx.time_rows:
             scratch, nbytes = _time_row_scratch(d, xyz.device)
             if sh.get("auto"):
-                d_S = torch.zeros_like(sh["S"])          # this view's dL/dS; autograd sums the views and runs _SpatialFn.backward once
+                d_S = torch.empty_like(sh["S"])          # this view's dL/dS (WRITTEN by the kernel: flag bit 1); autograd sums the views
             A = d_S if d_S is not None else sh["A"]
+            overwrite = d_S is not None or not sh.get("A_written", True)
             check(L.b200gs_hexplane_time_backward(ctypes.byref(d), P, xyz.data_ptr(), None, ts, sh["S"].data_ptr(),
                                                   A.data_ptr(), d_feat.data_ptr(), d_xyz_grid.data_ptr(), scratch.data_ptr(),
-                                                  nbytes, int(ctx.feat_tiled), stream), "hexplane_time_backward")
+                                                  nbytes, int(ctx.feat_tiled) | (2 if overwrite else 0), stream), "hexplane_time_backward")
+            sh["A_written"] = True
         elif sh is not None or not has_t:
             # shared step: time planes now, the spatial planes' share is accumulated for finish_shared_step.
             # One timestamp for the whole launch (scalar time): the time planes' gradient goes through replicated 1-D rows.
             scratch, nbytes = _time_row_scratch(d, xyz.device) if not has_t else (None, 0)
+            if sh is not None and not sh.get("A_written", True):
+                sh["A"].zero_(); sh["A_written"] = True          # this kernel only accumulates
             check(L.b200gs_hexplane_backward_masked(ctypes.byref(d), P, xyz.data_ptr(), _optr(ctx.order),
                                                     tt.data_ptr() if has_t else None, ts, MASK_TIME if sh is not None else MASK_ALL,
                                                     sh["S"].data_ptr() if sh is not None else None,

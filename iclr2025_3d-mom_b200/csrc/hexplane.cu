@@ -474,8 +474,10 @@ hexplane_time_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const _
                          const float* __restrict__ pts, const unsigned int* __restrict__ order, float t,
                          const float* __restrict__ factor, float* __restrict__ dfactor, const float* __restrict__ dfeat,
                          float* __restrict__ dpts, float* __restrict__ time_rows /* [replicas][ts.total], zeroed */, int replicas,
-                         int tiled)
+                         int tiled_flags)
 {
+    const int tiled = tiled_flags & 1;
+    const bool overwrite = (tiled_flags & 2) != 0;
     extern __shared__ float R[];
     float* rows = time_rows + (size_t)(blockIdx.x % replicas) * ts.total;      // row gradients: this CTA's replica
     time_rows_prepare(d, t, R, ts);
@@ -503,7 +505,7 @@ hexplane_time_bwd_kernel(const __grid_constant__ b200gs_hexplane_desc d, const _
                 const float4 go = mul4(gout, fac);
                 if (dfactor) {                       // d S += d feature * T
                     float4* da = reinterpret_cast<float4*>(dfactor + g * F + l * HP_C + cg * 4);
-                    const float4 T = mul4(mul4(r[0].v, r[1].v), r[2].v), old = *da;
+                    const float4 T = mul4(mul4(r[0].v, r[1].v), r[2].v), old = overwrite ? make_float4(0.f, 0.f, 0.f, 0.f) : *da;
                     *da = make_float4(old.x + gout.x * T.x, old.y + gout.y * T.y, old.z + gout.z * T.z, old.w + gout.w * T.w);
                 }
                 if (go.x != 0.f || go.y != 0.f || go.z != 0.f || go.w != 0.f) {
@@ -548,9 +550,11 @@ __global__ void __launch_bounds__(256, MINB)
 hexplane_time_bwd2_kernel(const __grid_constant__ b200gs_hexplane_desc d, const __grid_constant__ TimeRowSetup ts, long long P,
                           const float* __restrict__ pts, const unsigned int* __restrict__ order, float t,
                           const float* __restrict__ factor, float* __restrict__ dfactor, const float* __restrict__ dfeat,
-                          float* __restrict__ dpts, float* __restrict__ time_rows, int replicas, int tiled)
+                          float* __restrict__ dpts, float* __restrict__ time_rows, int replicas, int tiled_flags)
 {
     constexpr int L = 2, F = L * HP_C;
+    const int tiled = tiled_flags & 1;
+    const bool overwrite = (tiled_flags & 2) != 0;          // d_factor is WRITTEN, not accumulated (a fresh buffer: no read, no memset)
     extern __shared__ float R[];
     float* rows = time_rows + (size_t)(blockIdx.x % replicas) * ts.total;
     time_rows_prepare(d, t, R, ts);
@@ -571,7 +575,7 @@ hexplane_time_bwd2_kernel(const __grid_constant__ b200gs_hexplane_desc d, const 
             for (int l = 0; l < L; ++l) {
                 gout[l] = __ldg(reinterpret_cast<const float4*>(dfeat + (tiled ? tc5::stash_off((long long)g, l * HP_C + cg * 4) : g * F + l * HP_C + cg * 4)));
                 fac[l] = factor ? __ldg(reinterpret_cast<const float4*>(factor + g * F + l * HP_C + cg * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
-                old[l] = dfactor ? *reinterpret_cast<const float4*>(dfactor + g * F + l * HP_C + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                old[l] = (dfactor && !overwrite) ? *reinterpret_cast<const float4*>(dfactor + g * F + l * HP_C + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         float c[4], scale[3];
@@ -881,7 +885,7 @@ int b200gs_hexplane_time_backward(const b200gs_hexplane_desc* desc, long long P,
                                   b200gs_stream_t stream)
 {
     if (validate(desc)) return -1;
-    if (d_features_tiled && desc->levels != 2) { set_error("hexplane_time_backward: tiled d_features need 2 levels (64 columns)"); return -1; }
+    if ((d_features_tiled & 1) && desc->levels != 2) { set_error("hexplane_time_backward: tiled d_features need 2 levels (64 columns)"); return -1; }
     TimeRowSetup ts;
     if (!time_rows_setup(*desc, ts)) { set_error("hexplane_time_backward: time rows do not fit shared memory"); return -1; }
     if (P <= 0) return 0;

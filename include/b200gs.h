@@ -304,7 +304,9 @@ size_t b200gs_hexplane_time_row_scratch_bytes(const b200gs_hexplane_desc* desc, 
  * touched time rows of each (x,t) / (y,t) / (z,t) plane into a 1-D row, samples become 1-D lerps without global texel traffic,
  * and the backward reduces the row gradients into replicated 1-D rows (time_row_scratch, as for the _masked variant; required). Same contract as the
  * _masked variants with plane_mask = 0x34 and times = null (results differ from them by FP32 re-association only).
- * b200gs_hexplane_time_supported: 1 when the rows of this descriptor fit one CTA's shared memory (2 levels at 64 / 128). */
+ * b200gs_hexplane_time_supported: 1 when the rows of this descriptor fit one CTA's shared memory (2 levels at 64 / 128).
+ * d_features_tiled of the backward is a flag word: bit 0 = d_features in the MLP kernels' tiled layout, bit 1 = d_factor_accum is
+ * WRITTEN instead of accumulated (a fresh per-view buffer under autograd: saves its zero fill and the read). */
 int b200gs_hexplane_time_supported(const b200gs_hexplane_desc* desc);
 int b200gs_hexplane_time_forward(const b200gs_hexplane_desc* desc, long long P, const float* pts, const unsigned int* order,
                                  float time_scalar, const float* factor, float* features, int features_tiled, b200gs_stream_t stream);

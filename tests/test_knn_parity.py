@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 
 import os
-# BASELINE.json C5 initialises 5M points: run at that size with B200GS_FULLSIZE=1 (the reference kernel needs seconds there)
+# BASELINE.json C5 initialises 5M points: always run at that size too (the reference kernel needs a few seconds there)
 _FULL = [1000000, 5000000]          # BASELINE.json C3 / C5 point counts
 
 
