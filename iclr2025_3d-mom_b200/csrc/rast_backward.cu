@@ -213,8 +213,12 @@ composite_bwd_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ l
 //   * 1 / (1 - alpha) uses MUFU.RCP (relative error ~1e-7 per pair, 1e-5 over a chain of 100 contributors; the bar for these
 //     gradients is 1e-3); exp stays the accurate sequence (see below).
 constexpr int CB2_THREADS = 128;
+// CB2 = splats per batch, MINB = CTAs per SM the register budget is set for: 256 / 5 (39 KB of shared memory per CTA), 224 / 6
+// (34 KB, <= 85 registers), 192 / 7 (29 KB, <= 73 registers)
+template <int CB2> struct __align__(16) BStage2 { float4 A[CB2]; float4 B[CB2]; float4 C[CB2]; u32 gid[CB2]; };
 
-__global__ void __launch_bounds__(CB2_THREADS)
+template <int CB2, int MINB>
+__global__ void __launch_bounds__(CB2_THREADS, MINB)
 composite_bwd2_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ list, int W, int H, int grid_x,
                       const float4* __restrict__ recA, const float4* __restrict__ recB,
                       const float4* __restrict__ recC, const float* __restrict__ bg,
@@ -222,8 +226,8 @@ composite_bwd2_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ 
                       const float* __restrict__ dL_dpix, const float* __restrict__ dL_dpix_depth,
                       float* __restrict__ acc)
 {
-    __shared__ BStage stage[2];
-    __shared__ __align__(16) float s_acc[CB * ACC];
+    __shared__ BStage2<CB2> stage[2];
+    __shared__ __align__(16) float s_acc[CB2 * ACC];
     __shared__ u32 s_max[4];
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 tile = blockIdx.x;
@@ -243,12 +247,12 @@ composite_bwd2_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ 
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     const u32 warp_last = m;
     if (lane == 0) s_max[warp] = m;
-    for (u32 i = tid; i < CB * ACC; i += CB2_THREADS) s_acc[i] = 0.f;
+    for (u32 i = tid; i < CB2 * ACC; i += CB2_THREADS) s_acc[i] = 0.f;
     __syncthreads();
     u32 n_eff = max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3]));
     n_eff = min(n_eff, range.y - range.x);
     if (n_eff == 0) return;
-    const int rounds = (int)((n_eff + CB - 1) / CB);
+    const int rounds = (int)((n_eff + CB2 - 1) / CB2);
 
     const f2 T_final = pk(inA ? final_T[pidA] : 0.f, inB ? final_T[pidB] : 0.f);
     f2 T = T_final;
@@ -262,11 +266,11 @@ composite_bwd2_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ 
     float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ld = 0.f;          // colour / depth of the previous splat this warp processed
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
-    auto fill = [&](BStage& st, u32 first) {
+    auto fill = [&](BStage2<CB2>& st, u32 first) {
 #pragma unroll
-        for (int h = 0; h < CB / CB2_THREADS; ++h) {
+        for (int h = 0; h < (CB2 + CB2_THREADS - 1) / CB2_THREADS; ++h) {
             const u32 t = tid + h * CB2_THREADS, pos = first + t;
-            if (pos < n_eff) {
+            if (t < (u32)CB2 && pos < n_eff) {
                 const u32 g = __ldg(list + (range.x + n_eff - 1 - pos));
                 st.gid[t] = g;
                 cp_async16(&st.A[t], recA + g);
@@ -278,27 +282,27 @@ composite_bwd2_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ 
     fill(stage[0], 0);
     cp_async_commit();
     for (int r = 0; r < rounds; ++r) {
-        if (r + 1 < rounds) fill(stage[(r + 1) & 1], (u32)(r + 1) * CB);
+        if (r + 1 < rounds) fill(stage[(r + 1) & 1], (u32)(r + 1) * CB2);
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        const BStage& st = stage[r & 1];
-        const int cnt = (int)min((u32)CB, n_eff - (u32)r * CB);
-        u32 masks[CB / 32];
+        const BStage2<CB2>& st = stage[r & 1];
+        const int cnt = (int)min((u32)CB2, n_eff - (u32)r * CB2);
+        u32 masks[CB2 / 32];
 #pragma unroll
-        for (int q = 0; q < CB / 32; ++q) {
+        for (int q = 0; q < CB2 / 32; ++q) {
             const int j = q * 32 + (int)lane;
-            const u32 p = n_eff - 1u - ((u32)r * CB + (u32)j);
+            const u32 p = n_eff - 1u - ((u32)r * CB2 + (u32)j);
             const bool keep = j < cnt && p < warp_last && splat_may_touch_patch(st.A[j], st.B[j], patch_x, patch_y, 7.f);
             masks[q] = __ballot_sync(0xffffffffu, keep);
         }
 #pragma unroll
-        for (int q = 0; q < CB / 32; ++q) {
+        for (int q = 0; q < CB2 / 32; ++q) {
           u32 mq = masks[q];
           while (mq != 0) {
             const int j = q * 32 + __ffs(mq) - 1;
             mq &= mq - 1;
-            const u32 contributor = n_eff - 1u - ((u32)r * CB + (u32)j);
+            const u32 contributor = n_eff - 1u - ((u32)r * CB2 + (u32)j);
             const float4 A = st.A[j];
             const float4 B = st.B[j];
             const float dx = A.x - fxp;
@@ -388,7 +392,7 @@ composite_bwd2_kernel(const uint2* __restrict__ ranges, const u32* __restrict__ 
         __syncthreads();
         // flush this batch: one thread per instance, three 128-bit reductions
 #pragma unroll
-        for (int h = 0; h < CB / CB2_THREADS; ++h) {
+        for (int h = 0; h < (CB2 + CB2_THREADS - 1) / CB2_THREADS; ++h) {
             const int t = (int)tid + h * CB2_THREADS;
             if (t < cnt) {
                 float4* sa = reinterpret_cast<float4*>(&s_acc[t * ACC]);
@@ -739,10 +743,14 @@ int rast_backward(int P, int D, int M, long long R, int W, int H, const float* b
     {
         ProfScope prof(PROF_COMPOSITE_BWD, stream);
         cudaMemsetAsync(grad_arena, 0, (size_t)P * ACC * sizeof(float), stream);
-        if (R > 0 && g_opt_composite_pairs != 0)
-            composite_bwd2_kernel<<<(unsigned)tiles, CB2_THREADS, 0, stream>>>(
+        if (R > 0 && g_opt_composite_pairs != 0) {
+            // measured at 1M / 1280x720 and 200k / 512^2 (profiles/r2y_composite_pairs_occupancy.txt): 256 / 5: 0.612 / 0.322 ms,
+            // 224 / 6: 0.594 / 0.298 ms, 192 / 7: 0.582 / 0.321 ms for the whole rasterizer backward
+            auto kern = composite_bwd2_kernel<224, 6>;
+            kern<<<(unsigned)tiles, CB2_THREADS, 0, stream>>>(
                 img.ranges, sorted_list, W, H, grid_x, g.recA, g.recB, g.recC, bg, img.final_T, img.n_contrib,
                 dL_dpix, dL_dpix_depth, grad_arena);
+        }
         else if (R > 0)
             composite_bwd_kernel<<<(unsigned)tiles, TILE_PIXELS, 0, stream>>>(
                 img.ranges, sorted_list, W, H, grid_x, g.recA, g.recB, g.recC, bg, img.final_T, img.n_contrib,
