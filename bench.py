@@ -69,8 +69,10 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], False
+    def __init__(self, index, enabled=True):
+        # rank 0 only at N > 1: eight processes forking nvidia-smi ten times a second contend for the driver and showed up as
+        # straggling ranks (the timed value is the MAX over ranks); one sampler at 4 Hz sees the same clocks
+        self.index, self.rows, self.stop, self.enabled = index, [], False, enabled
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
@@ -82,15 +84,17 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.25)
 
     def __enter__(self):
-        self.t.start()
+        if self.enabled:
+            self.t.start()
         return self
 
     def __exit__(self, *a):
         self.stop = True
-        self.t.join(timeout=6)
+        if self.enabled:
+            self.t.join(timeout=6)
 
     def summary(self):
         if not self.rows:
@@ -836,7 +840,7 @@ def _main():
         trainer.step(cams, gts_dev, global_batch=n_global)
     adam_ms.clear()
     timeline = None
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, enabled=(rank == 0)) as clk:
         # headline: EXACTLY K un-instrumented steps between barriers, device time, max over ranks
         ms = run_steps(trainer, cams, gts_dev, n_global, args.steps, barrier, max_over_ranks)
         # the same K steps again with every entry point / rasterizer phase bracketed by CUDA events: the per-kernel durations
