@@ -526,8 +526,12 @@ class ViewParallelTrainer:
         if self.regulation is not None:
             # plane-only term, identical on every rank: added once, after the reduce
             # (its VALUE goes into rank 0's share of the loss only, so that the shares still sum to the global loss)
+            fused_total = total is not None and total.numel() == 1 and total.dim() == 1
+            acc = total if fused_total else (torch.zeros(1, device=self.arena.device) if total is not None else None)
             _field.accumulate_regulation(m._deformation.deformation_net.grid, *self.regulation,
-                                         loss_accum=total if (self.rank == 0 and total is not None and total.numel() == 1 and total.dim() == 1) else None)
+                                         loss_accum=acc if self.rank == 0 else None)
+            if not fused_total and acc is not None and self.rank == 0:
+                total = total + acc.reshape(())
         if self.regulation_fn is not None:
             reg = self.regulation_fn()
             reg.backward()
