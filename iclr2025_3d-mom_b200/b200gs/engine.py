@@ -147,6 +147,23 @@ class GaussianState(nn.Module):
         from . import densify as _d
         _d.reset_opacity(self)
 
+    # model files (scene/gaussian_model.py:321-360, 367-407): same bytes on disk, see b200gs/modelio.py
+    def save_ply(self, path):
+        from . import modelio
+        modelio.save_ply(self, path)
+
+    def load_ply(self, path):
+        from . import modelio
+        modelio.load_ply(self, path)
+
+    def save_deformation(self, path):
+        from . import modelio
+        modelio.save_deformation(self, path)
+
+    def load_model(self, path):
+        from . import modelio
+        modelio.load_model(self, path)
+
     def update_learning_rate(self, iteration):
         """scene/gaussian_model.py:284-298: per-iteration schedule of the xyz / grid / deformation groups (all three decay
         over position_lr_max_steps; the other groups keep their constant rates)."""
@@ -337,6 +354,7 @@ class ViewParallelTrainer:
         self.side = torch.cuda.Stream(device=dev) if self.overlap_sh_reduce else None
         self._sh_started = False
         self._sh_done = None
+        self._sse, self._sse_numel = None, 0
         self.timeline = None                           # bench.py: dict of CUDA events around the phases of the last step
         self._build_arena()
 
@@ -431,6 +449,13 @@ class ViewParallelTrainer:
             self._sh_done = torch.cuda.Event()
             self._sh_done.record(self.side)
 
+    def psnr(self):
+        """utils/image_utils.py:psnr of the last step's LOCAL views, averaged (what train_4DGS.py:212 logs): a device tensor built
+        from the squared-error sums the L1 kernel accumulated on the side; reading it is the caller's sync."""
+        if self._sse is None:
+            raise RuntimeError("psnr(): no step with views has run on this rank")
+        return fusedops.psnr_from_sse(self._sse, self._sse_numel).mean()
+
     def step(self, cams, gts, global_batch=None):
         """cams / gts: THIS rank's views; a ground-truth image is a float32 [3,H,W] tensor or the dataset's own uint8 [H,W,3]
         image (GPU path). Loss = mean over the GLOBAL batch of per-view L1 means (train_4DGS.py:205-210: l1 over the
@@ -439,6 +464,8 @@ class ViewParallelTrainer:
         self._bind()
         self._mark("step_start")
         total = None
+        sse_plain = []
+        self._sse = None
         shs = None
         m = self.model
         self._sh_started, self._sh_done, self._sh_stepped = False, None, False
@@ -483,14 +510,19 @@ class ViewParallelTrainer:
                 try:
                     if self.shared_shs and gt.is_cuda:
                         # fused L1 (utils/loss_utils.py:23-24) + its gradient, then backward from the image
-                        if total is None:
-                            total = torch.zeros(1, device=gt.device)
+                        if total is None:          # [loss | one squared-error sum per local view] zeroed by one fill
+                            acc_buf = torch.zeros(1 + len(cams), device=gt.device)
+                            total, self._sse = acc_buf[:1], acc_buf[1:]
                         img = pkg["render"]
-                        d_img = fusedops.l1_loss_and_grad(img, gt, 1.0 / (img.numel() * B), total)
+                        self._sse_numel = img.numel()
+                        d_img = fusedops.l1_loss_and_grad(img, gt, 1.0 / (img.numel() * B), total, self._sse[vi:])
                         img.backward(d_img)
                         loss = None
                     else:
-                        loss = (pkg["render"] - gt).abs().mean() / B
+                        diff = pkg["render"] - gt
+                        loss = diff.abs().mean() / B
+                        sse_plain.append((diff.detach() ** 2).sum().reshape(1))
+                        self._sse_numel = diff.numel()
                         loss.backward()
                 finally:
                     _field.ACCUMULATE_INTO_GRAD = False
@@ -507,6 +539,8 @@ class ViewParallelTrainer:
         except BaseException:
             _field.drop_shared()               # never leave a half-used spatial product behind (a later render() would reuse it)
             raise
+        if sse_plain:
+            self._sse = torch.cat(sse_plain)
         self._mark("views_done")
         if self.sh_params:
             if not shs.is_cuda:                        # CPU plumbing tests: autograd accumulated into the leaf itself

@@ -15,8 +15,8 @@ from ._lib import check, current_stream
 _P = ctypes.c_void_p
 _lib.register("b200gs_activations_forward", ctypes.c_int, [ctypes.c_longlong, _P, _P, _P, _P, _P, _P, _P])
 _lib.register("b200gs_activations_backward", ctypes.c_int, [ctypes.c_longlong] + [_P] * 10)
-_lib.register("b200gs_l1_loss_fwd_bwd", ctypes.c_int, [ctypes.c_longlong, _P, _P, ctypes.c_float, _P, _P, _P])
-_lib.register("b200gs_l1_loss_fwd_bwd_u8", ctypes.c_int, [ctypes.c_int, ctypes.c_int, _P, _P, ctypes.c_float, _P, _P, _P])
+_lib.register("b200gs_l1_loss_fwd_bwd", ctypes.c_int, [ctypes.c_longlong, _P, _P, ctypes.c_float, _P, _P, _P, _P])
+_lib.register("b200gs_l1_loss_fwd_bwd_u8", ctypes.c_int, [ctypes.c_int, ctypes.c_int, _P, _P, ctypes.c_float, _P, _P, _P, _P])
 
 
 def _req(t, shape_tail):
@@ -60,9 +60,21 @@ def activations(scales, rotations, opacity):
     return _Activations.apply(scales, rotations, opacity)
 
 
-def l1_loss_and_grad(render, target, scale, loss_accum):
+def psnr_from_sse(sse, n):
+    """utils/image_utils.py:17-38 from the per-image sums of squared errors the L1 kernel leaves behind:
+    20 log10(1 / sqrt(mse)) per image (a device tensor; reading it is the caller's sync)."""
+    return 20.0 * torch.log10(1.0 / torch.sqrt(sse / float(n)))
+
+
+def l1_loss_and_grad(render, target, scale, loss_accum, sse_accum=None):
     """loss_accum[0] += scale * sum|render - target|; returns d(loss)/d(render) (= scale * sign).
+    sse_accum (optional, a 1-element float32 CUDA tensor the caller zeroes): += sum (render - target)^2, see psnr_from_sse.
     target: float32 [3,H,W], or the dataset's own uint8 [H,W,3] image (converted on the device as PILtoTorch does: u8 / 255)."""
+    sse = None
+    if sse_accum is not None:
+        if not (sse_accum.is_cuda and sse_accum.dtype == torch.float32 and sse_accum.numel() >= 1):
+            raise RuntimeError("l1_loss_and_grad: sse_accum must be a float32 CUDA tensor")
+        sse = sse_accum.data_ptr()
     if target.dtype == torch.uint8:
         if not (render.is_cuda and target.is_cuda and render.dtype == torch.float32 and render.dim() == 3 and render.shape[0] == 3
                 and tuple(target.shape) == (render.shape[1], render.shape[2], 3)):
@@ -70,7 +82,7 @@ def l1_loss_and_grad(render, target, scale, loss_accum):
         r, t = render.detach().contiguous(), target.contiguous()
         d = torch.empty_like(r)
         check(_lib.lib().b200gs_l1_loss_fwd_bwd_u8(int(r.shape[1]), int(r.shape[2]), r.data_ptr(), t.data_ptr(), float(scale),
-                                                   loss_accum.data_ptr(), d.data_ptr(), current_stream()), "l1_loss_u8")
+                                                   loss_accum.data_ptr(), sse, d.data_ptr(), current_stream()), "l1_loss_u8")
         return d
     if not (render.is_cuda and target.is_cuda and render.dtype == torch.float32 and target.dtype == torch.float32):
         raise RuntimeError("l1_loss_and_grad needs float32 CUDA tensors (there is no CPU path)")
@@ -78,6 +90,6 @@ def l1_loss_and_grad(render, target, scale, loss_accum):
         raise RuntimeError("render / target shape mismatch")
     r, t = render.detach().contiguous(), target.contiguous()
     d = torch.empty_like(r)
-    check(_lib.lib().b200gs_l1_loss_fwd_bwd(r.numel(), r.data_ptr(), t.data_ptr(), float(scale), loss_accum.data_ptr(), d.data_ptr(),
-                                            current_stream()), "l1_loss")
+    check(_lib.lib().b200gs_l1_loss_fwd_bwd(r.numel(), r.data_ptr(), t.data_ptr(), float(scale), loss_accum.data_ptr(), sse,
+                                            d.data_ptr(), current_stream()), "l1_loss")
     return d

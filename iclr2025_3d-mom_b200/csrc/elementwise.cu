@@ -58,66 +58,65 @@ __global__ void __launch_bounds__(256) activations_bwd_kernel(long long P, const
     }
 }
 
-// loss[0] += scale * sum |a - b| ; d[i] = scale * sign(a - b)   (sign(0) = 0 like torch.sign)
-__global__ void __launch_bounds__(256) l1_fwd_bwd_kernel(long long n, const float* __restrict__ a, const float* __restrict__ b,
-                                                         float scale, float* __restrict__ loss, float* __restrict__ d)
+// loss[0] += scale * sum |a - b| ; d[i] = scale * sign(a - b)   (sign(0) = 0 like torch.sign); sse[0] += sum (a - b)^2 when asked
+// for (the numerator of utils/image_utils.py:psnr, which train_4DGS.py:212 evaluates on the same two images every iteration).
+__device__ __forceinline__ void l1_block_finish(float acc, float sq, float scale, float* __restrict__ loss, float* __restrict__ sse)
 {
-    float acc = 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+    __shared__ float part[8], part_sq[8];
+    if ((threadIdx.x & 31) == 0) { part[threadIdx.x >> 5] = acc; part_sq[threadIdx.x >> 5] = sq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { s += part[w]; q += part_sq[w]; }
+        atomicAdd(loss, s * scale);
+        if (sse) atomicAdd(sse, q);
+    }
+}
+
+__global__ void __launch_bounds__(256) l1_fwd_bwd_kernel(long long n, const float* __restrict__ a, const float* __restrict__ b,
+                                                         float scale, float* __restrict__ loss, float* __restrict__ sse,
+                                                         float* __restrict__ d)
+{
+    float acc = 0.f, sq = 0.f;
     const long long n4 = n >> 2;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
         const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i), y = __ldg(reinterpret_cast<const float4*>(b) + i);
         const float e[4] = {x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w};
         float g[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { acc += fabsf(e[k]); g[k] = e[k] > 0.f ? scale : (e[k] < 0.f ? -scale : 0.f); }
+        for (int k = 0; k < 4; ++k) { acc += fabsf(e[k]); sq = fmaf(e[k], e[k], sq); g[k] = e[k] > 0.f ? scale : (e[k] < 0.f ? -scale : 0.f); }
         if (d) reinterpret_cast<float4*>(d)[i] = make_float4(g[0], g[1], g[2], g[3]);
     }
     for (long long i = (n4 << 2) + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
         const float e = __ldg(a + i) - __ldg(b + i);
-        acc += fabsf(e);
+        acc += fabsf(e); sq = fmaf(e, e, sq);
         if (d) d[i] = e > 0.f ? scale : (e < 0.f ? -scale : 0.f);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    __shared__ float part[8];
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) s += part[w];
-        atomicAdd(loss, s * scale);
-    }
+    l1_block_finish(acc, sq, scale, loss, sse);
 }
 
 // The same against the ground truth as the dataset holds it: uint8 HWC (a PIL image, scene/dataset_readers.py:1041), converted
 // on the device exactly like utils/general_utils.py:PILtoTorch does on the host (float(u8) / 255.0f, IEEE division): the view's
 // ground truth crosses PCIe as 3 B/pixel instead of 12.  render / d are CHW.
 __global__ void __launch_bounds__(256) l1_fwd_bwd_u8_kernel(int H, int W, const float* __restrict__ a, const unsigned char* __restrict__ gt,
-                                                            float scale, float* __restrict__ loss, float* __restrict__ d)
+                                                            float scale, float* __restrict__ loss, float* __restrict__ sse,
+                                                            float* __restrict__ d)
 {
-    float acc = 0.f;
+    float acc = 0.f, sq = 0.f;
     const long long n = (long long)H * W;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float t = __fdiv_rn((float)__ldg(gt + 3 * i + c), 255.0f);
             const float e = __ldg(a + c * n + i) - t;
-            acc += fabsf(e);
+            acc += fabsf(e); sq = fmaf(e, e, sq);
             if (d) d[c * n + i] = e > 0.f ? scale : (e < 0.f ? -scale : 0.f);
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    __shared__ float part[8];
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) s += part[w];
-        atomicAdd(loss, s * scale);
-    }
+    l1_block_finish(acc, sq, scale, loss, sse);
 }
 
 // Is every element of x bit-identical to x[0]?  out[0] = 1 / 0, out[1] = bits of x[0].  (gaussian_renderer/__init__.py:56 repeats
@@ -174,26 +173,26 @@ int b200gs_activations_backward(long long P, const float* scales_out, const floa
     return check_launch("activations_backward");
 }
 
-int b200gs_l1_loss_fwd_bwd(long long n, const float* render, const float* target, float scale, float* loss_accum, float* d_render,
-                           b200gs_stream_t stream)
+int b200gs_l1_loss_fwd_bwd(long long n, const float* render, const float* target, float scale, float* loss_accum, float* sse_accum,
+                           float* d_render, b200gs_stream_t stream)
 {
     if (n <= 0) return 0;
     if (!render || !target || !loss_accum) { set_error("l1_loss: null pointer"); return -1; }
     long long blocks = (n / 4 + 255) / 256;
     if (blocks > (long long)NUM_SMS * 8) blocks = (long long)NUM_SMS * 8;
     if (blocks < 1) blocks = 1;
-    l1_fwd_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, render, target, scale, loss_accum, d_render);
+    l1_fwd_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, render, target, scale, loss_accum, sse_accum, d_render);
     return check_launch("l1_loss");
 }
 
 int b200gs_l1_loss_fwd_bwd_u8(int H, int W, const float* render_chw, const unsigned char* target_hwc, float scale, float* loss_accum,
-                              float* d_render_chw, b200gs_stream_t stream)
+                              float* sse_accum, float* d_render_chw, b200gs_stream_t stream)
 {
     if (H <= 0 || W <= 0) return 0;
     if (!render_chw || !target_hwc || !loss_accum) { set_error("l1_loss_u8: null pointer"); return -1; }
     long long blocks = ((long long)H * W + 255) / 256;
     if (blocks > (long long)NUM_SMS * 8) blocks = (long long)NUM_SMS * 8;
-    l1_fwd_bwd_u8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(H, W, render_chw, target_hwc, scale, loss_accum, d_render_chw);
+    l1_fwd_bwd_u8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(H, W, render_chw, target_hwc, scale, loss_accum, sse_accum, d_render_chw);
     return check_launch("l1_loss_u8");
 }
 

@@ -336,14 +336,16 @@ int b200gs_activations_backward(long long P, const float* scales_out, const floa
                                 float* d_scales_raw, float* d_rot_raw, float* d_opacity_raw, b200gs_stream_t stream);
 /* L1 loss of utils/loss_utils.py:23-24 with its gradient in one pass: loss_accum[0] += scale * sum |render - target|,
  * d_render[i] = scale * sign(render[i] - target[i]) (d_render may be null). scale = 1 / (n * batch) gives the
- * per-view share of train_4DGS.py:205-210's batch-mean L1. loss_accum is a device float the caller zeroes. */
-int b200gs_l1_loss_fwd_bwd(long long n, const float* render, const float* target, float scale, float* loss_accum, float* d_render,
-                           b200gs_stream_t stream);
+ * per-view share of train_4DGS.py:205-210's batch-mean L1. loss_accum is a device float the caller zeroes.
+ * sse_accum (may be null): sse_accum[0] += sum (render - target)^2, the numerator of utils/image_utils.py:17-38 `psnr`, which
+ * train_4DGS.py:212 evaluates on the same two images every iteration: psnr = 20 log10(1 / sqrt(sse / n)). */
+int b200gs_l1_loss_fwd_bwd(long long n, const float* render, const float* target, float scale, float* loss_accum, float* sse_accum,
+                           float* d_render, b200gs_stream_t stream);
 /* The same against the ground truth as the dataset holds it -- uint8 [H,W,3] (scene/dataset_readers.py:1041), converted on the
  * device the way utils/general_utils.py:PILtoTorch does on the host (float(u8) / 255.0f): 3 B/pixel cross PCIe instead of 12.
  * render / d_render are [3,H,W]. */
 int b200gs_l1_loss_fwd_bwd_u8(int H, int W, const float* render_chw, const unsigned char* target_hwc, float scale, float* loss_accum,
-                              float* d_render_chw, b200gs_stream_t stream);
+                              float* sse_accum, float* d_render_chw, b200gs_stream_t stream);
 
 /* Is the [n] float tensor x one value repeated?  gaussian_renderer/__init__.py:56 hands the field the camera's single timestamp as
  * a materialised [P,1] tensor; when it is uniform the field takes its one-timestamp fast path (time planes from shared memory).

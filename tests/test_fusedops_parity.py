@@ -46,12 +46,19 @@ def test_l1_loss_and_grad(shape):
     with torch.no_grad():
         gt.view(-1)[:3] = img.view(-1)[:3]          # exact ties: sign(0) = 0
     B = 8
-    acc = torch.zeros(1, device="cuda")
-    d = fusedops.l1_loss_and_grad(img, gt, 1.0 / (img.numel() * B), acc)
+    acc, sse = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    d = fusedops.l1_loss_and_grad(img, gt, 1.0 / (img.numel() * B), acc, sse)
     ref = (img - gt).abs().mean() / B
     ref.backward()
     assert abs(acc.item() - ref.item()) < 1e-5 * ref.item()
     assert torch.equal(d, img.grad)
+    # utils/image_utils.py:17-38 (no mask): mse = ((a - b) ** 2).view(B, -1).mean(1); psnr = 20 log10(1 / sqrt(mse))
+    a, b = img.detach()[None], gt[None]
+    mse = ((a - b) ** 2).view(a.shape[0], -1).mean(1, keepdim=True)
+    want = 20 * torch.log10(1.0 / torch.sqrt(mse))
+    got = fusedops.psnr_from_sse(sse, img.numel())
+    assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want))
+    assert torch.equal(fusedops.l1_loss_and_grad(img, gt, 1.0 / (img.numel() * B), acc), d)      # sse stays optional
 
 
 def test_to8b_and_frame_ring():
@@ -84,9 +91,12 @@ def test_l1_against_uint8_target_equals_the_float_path():
     render = torch.rand(3, H, W, generator=g).cuda()
     render[0, :4, :4] = target[0, :4, :4]                     # exact hits: sign(0) = 0
     la, lb = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
-    da = fusedops.l1_loss_and_grad(render, target, 0.125 / render.numel(), la)
-    db = fusedops.l1_loss_and_grad(render, u8.cuda(), 0.125 / render.numel(), lb)
+    sa, sb = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    da = fusedops.l1_loss_and_grad(render, target, 0.125 / render.numel(), la, sa)
+    db = fusedops.l1_loss_and_grad(render, u8.cuda(), 0.125 / render.numel(), lb, sb)
     assert torch.equal(da, db)
+    assert abs(float(sa) - float(sb)) <= 1e-6 * float(sa)
+    assert abs(float(sb) - float(((render - target) ** 2).sum())) <= 1e-5 * float(sb)
     assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(la))
     ref = 0.125 * (render - target).abs().mean()
     assert abs(float(lb) - float(ref)) <= 2e-6 * float(ref)

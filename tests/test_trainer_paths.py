@@ -42,6 +42,9 @@ def test_fast_path_equals_plain_autograd_path(stage, views):
     for it in range(2):
         la = float(ta.step(cams, gts)); lb = float(tb.step(cams, gts))
         assert abs(la - lb) <= 2e-6 * max(1.0, abs(lb)), (it, la, lb)
+        # utils/image_utils.py:psnr as train_4DGS.py:212 logs it: the L1 kernel's side sum against the plain torch expression
+        pa, pb = float(ta.psnr()), float(tb.psnr())
+        assert abs(pa - pb) <= 1e-4 * abs(pb), (pa, pb)
         if it == 0:
             na = {n: p for n, p in ma.named_parameters()}
             for n, q in mb.named_parameters():

@@ -146,7 +146,7 @@ int main(int argc, char** argv)
         BK(b200gs_rast_buffer_sizes(P, (long long)cnt[0], W, H, sz));
         if (sz[1] > bin_cap) { if (bin) CK(cudaFree(bin)); bin_cap = sz[1] + sz[1] / 8; CK(cudaMalloc(&bin, bin_cap)); }
         tm.begin(); BK(b200gs_rast_forward_stage2(P, (long long)cnt[0], (long long)cnt[1], W, H, d_bg, geom, bin, bin_cap, img, sz[2], color, depth, st)); tm.end("rast_forward_stage2", count);
-        tm.begin(); BK(b200gs_l1_loss_fwd_bwd((long long)3 * H * W, color, gt, 1.f / (3.f * H * W * 8.f), loss, dimg, st)); tm.end("l1_loss_fwd_bwd", count);
+        tm.begin(); BK(b200gs_l1_loss_fwd_bwd((long long)3 * H * W, color, gt, 1.f / (3.f * H * W * 8.f), loss, nullptr, dimg, st)); tm.end("l1_loss_fwd_bwd", count);
         tm.begin();
         BK(b200gs_rast_backward_accumulate_sh(P, D, M, (long long)cnt[0], W, H, d_bg, pts_o, shs, nullptr, sc_a, 1.f, rt_a, nullptr, d_view, d_full, d_campos, (float)tanx, (float)tany,
                                               radii, geom, bin, img, dimg, nullptr, g_arena, g_m2d, g_col, g_op, g_m3d, g_cov, g_sh, g_sc, g_rot, st));
