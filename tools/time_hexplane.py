@@ -19,6 +19,8 @@ order = F._cell_order(xyz, grid.aabb)
 L = _lib.lib()
 class _N:
     def data_ptr(self): return None
+if os.environ.get("ORDER") == "identity":          # visit the (random) points in storage order: no cell coherence at all
+    order = torch.arange(P, device="cuda", dtype=order.dtype)
 if os.environ.get("SORTED"):
     xyz = xyz[order.long()].contiguous(); order = _N()
 feat = torch.empty(P, 64, device="cuda"); S = torch.rand(P, 64, device="cuda"); A = torch.zeros(P, 64, device="cuda")
