@@ -68,6 +68,39 @@ class FrameRing:
         return frame.copy() if copy else frame
 
 
+class FrameStore:
+    """All frames of a camera path in ONE pinned host array (render_4DGS.py:41-76 knows the frame count up front: it renders the
+    whole trajectory into a list and then calls `imageio.mimwrite`).  `put(i, image)` quantises on the current stream and starts
+    the async 3 B/pixel copy of frame i straight into its final place, so there is no host-side copy at all (FrameRing.pop()
+    costs one 6 MB memcpy per 1080p frame on the thread that also launches the kernels); `array()` waits for the copies and
+    returns the [n,H,W,3] uint8 numpy view (`list(store.array())` is the reference's `render_images`).  The pinned allocation
+    (cudaHostAlloc, ~0.2 s per GB) is made once in the constructor; a store can be refilled for the next path once the previous
+    one has been consumed."""
+
+    def __init__(self, n_frames, H, W, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.host = torch.empty((n_frames, H, W, 3), dtype=torch.uint8).pin_memory()
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.bytes_per_frame = H * W * 3
+        self.filled = 0
+
+    def put(self, index, image):
+        if not 0 <= index < self.host.shape[0]:
+            raise IndexError(f"FrameStore.put: frame {index} outside [0, {self.host.shape[0]})")
+        q = to8b(image)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(ready)
+            self.host[index].copy_(q, non_blocking=True)
+            q.record_stream(self.copy_stream)
+        self.filled += 1
+
+    def array(self):
+        self.copy_stream.synchronize()
+        return self.host.numpy()
+
+
 class FrameWriter:
     """PNG / MP4 encoding off the critical path.  render_4DGS.py:58-76 calls
     `torchvision.utils.save_image` per frame INSIDE its render loop and `imageio.mimwrite` after it, so its "FPS" is PNG-encode

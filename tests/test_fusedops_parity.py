@@ -78,6 +78,18 @@ def test_to8b_and_frame_ring():
     while ring.count:
         got.append(ring.pop().copy())
     assert len(got) == 6 and all(np.array_equal(a, to8b(f).transpose(1, 2, 0)) for a, f in zip(got, frames))
+    # the whole path in one pinned array, frames written out of order, refilled for a second path
+    store = output.FrameStore(6, 67, 129)
+    for i in (3, 0, 5, 1, 4, 2):
+        store.put(i, frames[i])
+    arr = store.array()
+    assert arr.shape == (6, 67, 129, 3) and all(np.array_equal(arr[i], to8b(f).transpose(1, 2, 0)) for i, f in enumerate(frames))
+    for i in range(6):
+        store.put(i, frames[5 - i])
+    arr = store.array()
+    assert all(np.array_equal(arr[i], to8b(frames[5 - i]).transpose(1, 2, 0)) for i in range(6))
+    with pytest.raises(IndexError):
+        store.put(6, frames[0])
 
 
 def test_l1_against_uint8_target_equals_the_float_path():
