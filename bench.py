@@ -1070,7 +1070,7 @@ def _main():
         try:
             from b200gs import _lib as _l
             res["config"]["kernel_options"] = {n: int(_l.lib().b200gs_get_option(n.encode()))
-                                               for n in ("mlp_fwd_elect", "mlp_bwd_v2", "hexplane_time_fwd", "hexplane_time_bwd", "lookback_parallel", "composite_pairs")}
+                                               for n in ("mlp_fwd_elect", "mlp_bwd_v2", "hexplane_time_fwd", "hexplane_time_bwd", "lookback_parallel", "composite_pairs", "sort_ballot_rank")}
             res["config"]["overlap_sh_reduce"] = bool(trainer.overlap_sh_reduce)
         except Exception as ex:              # informational only
             res["config"]["kernel_options"] = f"unavailable: {ex}"

@@ -45,7 +45,10 @@ int b200gs_version(void);
  *                    first is used, register budget for 3 / 2 resident CTAs per SM (hexplane.cu: hexplane_time_bwd2_kernel)
  *   "lookback_parallel" chained scans of the radix sort passes and of the instance emission (default 1):
  *                    predecessors' states are read 8 (per digit) / 32 (per warp) at a time instead of one dependent L2 round
- *                    trip each; identical results
+ *                    trip each (sort passes: only while all tiles are resident at once); identical results
+ *   "sort_ballot_rank" radix sort passes (default 1): the lanes of a warp that hold the same digit are found with one ballot per
+ *                    digit bit (4 or 8 VOTE + LOP3, independent across a thread's 16 keys) instead of MATCH.ANY, whose latency was
+ *                    the kernel's top stall: 103 -> 87 us per 1M-pair 32-bit sort, 96 -> 79 us per 2.4M-pair 12-bit sort; identical results
  *   "composite_pairs" compositing backward (default 1): a lane owns TWO pixels of an 8x8 warp patch and carries their state as
  *                    packed FP32 pairs (FFMA2 / FMUL2 / FADD2), the gradient butterfly is paid once per 64 pixels: 0.765 -> 0.608 ms
  *                    per 1M-Gaussian 1280x720 view; 0 = the one-pixel-per-lane kernel (rast_backward.cu)

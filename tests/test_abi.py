@@ -95,7 +95,7 @@ def test_kernel_variant_options_defaults_and_toggle():
     unknown names are an error."""
     from b200gs import _lib
     L = _lib.lib()
-    for name, dflt in ((b"mlp_bwd_v2", 87), (b"mlp_fwd_elect", 2), (b"hexplane_time_fwd", 2), (b"hexplane_time_bwd", 2), (b"lookback_parallel", 1), (b"composite_pairs", 1)):
+    for name, dflt in ((b"mlp_bwd_v2", 87), (b"mlp_fwd_elect", 2), (b"hexplane_time_fwd", 2), (b"hexplane_time_bwd", 2), (b"lookback_parallel", 1), (b"composite_pairs", 1), (b"sort_ballot_rank", 1)):
         env = os.environ.get("B200GS_" + name.decode().upper())
         want = int(env) if env is not None and env[:1].isdigit() else dflt
         assert L.b200gs_get_option(name) == want

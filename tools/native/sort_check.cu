@@ -31,8 +31,8 @@ int main(int argc, char** argv)
     cudaStream_t st; CK(cudaStreamCreate(&st));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     bool ok = true;
-    for (int variant = 0; variant < 2; ++variant) {          // lookback_parallel off / on
-        if (b200gs_set_option("lookback_parallel", variant)) { printf("%s\n", b200gs_last_error()); return 3; }
+    for (int variant = 0; variant < 4; ++variant) {          // lookback_parallel off / on  x  sort_ballot_rank off / on
+        if (b200gs_set_option("lookback_parallel", variant & 1) || b200gs_set_option("sort_ballot_rank", variant >> 1)) { printf("%s\n", b200gs_last_error()); return 3; }
         float total = 0; int side = 0;
         for (int rep = -1; rep < 10; ++rep) {
             CK(cudaMemcpyAsync(ka, k0, n * 4, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(va, v0, n * 4, cudaMemcpyDeviceToDevice, st));
@@ -46,8 +46,8 @@ int main(int argc, char** argv)
         CK(cudaMemcpy(ok_k.data(), side ? kb : ka, n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(ok_v.data(), side ? vb : va, n * 4, cudaMemcpyDeviceToHost));
         size_t bad = 0;
         for (size_t i = 0; i < n; ++i) bad += ok_v[i] != order[i] || ok_k[i] != keys[order[i]];
-        printf("lookback_parallel = %d: %.1f us per sort of %zu pairs on %d bits, %zu mismatches against std::stable_sort\n",
-               variant, 100.f * total, n, bits, bad);
+        printf("lookback_parallel = %d, sort_ballot_rank = %d: %.1f us per sort of %zu pairs on %d bits, %zu mismatches against std::stable_sort\n",
+               variant & 1, variant >> 1, 100.f * total, n, bits, bad);
         ok &= bad == 0;
     }
     printf("RESULT: %s\n", ok ? "PASS" : "FAIL");
