@@ -217,7 +217,8 @@ int radix_sort_pairs(u32* keys_a, u32* vals_a, u32* keys_b, u32* vals_b, size_t 
         // batched look-back pays while every tile is resident at once (3 CTAs per SM: 80 registers); beyond one wave the tiles of
         // the next wave find inclusive prefixes waiting and the plain walk is shorter (2.4M pairs / 12 bits: 79 vs 85 us)
         const bool hv = vals_a != nullptr, par = g_opt_lookback_parallel != 0 && tiles <= (size_t)3 * NUM_SMS;
-        // (32 states per round trip for single-wave inputs was measured too: 112 vs 103 us per 1M-pair sort, not kept)
+        // (32 states per round trip for single-wave inputs was measured too: 112 vs 103 us per 1M-pair sort, not kept;
+        //  so was __launch_bounds__(256, 4): 64 registers with 20-36 B of spills, 87 -> 95 us per 1M-pair sort, 79 -> 76 us at 2.4M)
 #define RS_PICK(BLV) do { constexpr int BL = BLV; \
         if (hv && par) RS_LAUNCH(true, RS_IPT, 8); \
         else if (hv) RS_LAUNCH(true, RS_IPT, 1); \
