@@ -753,6 +753,7 @@ def run_steps_e2e(trainer, cams, host_images, n_global, steps, device, barrier, 
     if impl == "b200":
         feeder = engine.HostImageFeeder(host_images, device)
         ring = engine.LossRing(depth=4)
+        lag = 1 if len(cams) > 1 else 2
         feeder.prefetch()
         for k in range(steps):
             g = feeder.take()
@@ -761,9 +762,13 @@ def run_steps_e2e(trainer, cams, host_images, n_global, steps, device, barrier, 
             loss = trainer.step(cams, g, global_batch=n_global)
             feeder.release()
             ring.push(loss)
-            v = ring.read(lag=1)                       # the previous step's loss: no pipeline drain
+            # every step's loss is read on the host, `lag` steps after it was queued: one step late while a step is long (N <= 4),
+            # two when a rank's step is a single ~5 ms view and the host needs that much queue depth to hide its own jitter
+            v = ring.read(lag=lag)
             last = v if v is not None else last
-        last = ring.read(lag=0)
+        for back in range(lag - 1, -1, -1):            # drain: the last `lag` losses
+            v = ring.read(lag=back)
+            last = v if v is not None else last
     else:
         for _ in range(steps):                         # what train_4DGS.py:194,236 does: blocking float upload, loss.item() per step
             g_step = [g.to(device, non_blocking=True) for g in host_images]
@@ -1032,7 +1037,7 @@ def _main():
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e * 1e3 / args.steps,
                 "last_loss": last,
                 "how": ("uint8 HWC ground truth (the dataset's own format) uploaded from pinned memory on a side stream one step ahead, converted "
-                        "inside the L1 kernel; loss copied to a pinned ring every step and read one step late") if impl == "b200" else
+                        "inside the L1 kernel; loss copied to a pinned ring every step and read one step late (two when a rank's step is a single view)") if impl == "b200" else
                        "float32 CHW ground truth uploaded per step, float(loss) per step (train_4DGS.py:194, :236)"},
         "clocks": clk.summary(),
         "gpu_launches": int(round(launches_per_step * args.steps)) if launches_per_step else 0,
