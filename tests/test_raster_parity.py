@@ -187,3 +187,21 @@ def test_edge_cases_empty_and_behind_camera():
         ras(means3D=act["means3D"], means2D=z(500, 3), opacities=act["opacities"], shs=act["shs"], scales=act["scales"])
     vis = ras.markVisible(act["means3D"])
     assert vis.dtype == torch.bool and int(vis.sum()) == 0
+
+
+def test_empty_model_renders_the_background_through_the_whole_path():
+    """Zero Gaussians (everything pruned) through engine.render: deformation field, activations, rasterizer, to8b."""
+    from b200gs import engine, output, synthetic as syn
+    dev = torch.device("cuda", 0)
+    raw = syn.make_gaussians(0, device=dev)
+    m = engine.GaussianState(raw).to(dev)
+    cam = syn.make_camera(64, 48, device=dev)
+    bg = torch.tensor([0.25, 0.5, 0.75], device=dev)
+    for stage in ("coarse", "fine"):
+        with torch.no_grad():
+            pkg = engine.render(cam, m, bg, stage=stage)
+        assert pkg["render"].shape == (3, 48, 64) and pkg["radii"].numel() == 0
+        assert torch.equal(pkg["render"], bg[:, None, None].expand(3, 48, 64))
+        assert float(pkg["depth"].abs().max()) == 0.0
+    q = output.to8b(pkg["render"])
+    assert q.shape == (48, 64, 3) and q[0, 0].tolist() == [63, 127, 191]
