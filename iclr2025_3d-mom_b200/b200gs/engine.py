@@ -355,6 +355,11 @@ class ViewParallelTrainer:
         self._sh_started = False
         self._sh_done = None
         self._sse, self._sse_numel = None, 0
+        # Forward of view i+1 on a second stream while view i's backward runs (B200GS_PIPELINE_VIEWS): the backwards stay
+        # strictly ordered (every accumulator they share -- SH buffer, d(S), arena, viewspace, radii -- is touched in order),
+        # only the latency-bound forward kernels (sorts, emission, read-back bubble) find idle SMs under the previous backward.
+        self.pipeline_views = (os.environ.get("B200GS_PIPELINE_VIEWS", "1") != "0") and self.shared_shs and dev.type == "cuda"
+        self.alt = torch.cuda.Stream(device=dev) if self.pipeline_views else None
         self.timeline = None                           # bench.py: dict of CUDA events around the phases of the last step
         self._build_arena()
 
@@ -486,56 +491,82 @@ class ViewParallelTrainer:
         if share_spatial:
             _field.begin_shared_step(m._deformation, m._xyz)
         first_sh = True
+        import contextlib
+        piped = self.pipeline_views and len(cams) > 1 and m._xyz.is_cuda
+        main = torch.cuda.current_stream() if piped else None
+        if piped:
+            self.alt.wait_stream(main)                 # shs, the spatial product and this step's images are ready
+        stream_of = (lambda vi: (main, self.alt)[vi & 1]) if piped else (lambda vi: None)
+        on = lambda st: torch.cuda.stream(st) if st is not None else contextlib.nullcontext()
+
+        def forward_view(vi):
+            with on(stream_of(vi)):
+                return self.render_fn(cams[vi], m, self.bg, self.stage, shs) if self.shared_shs else \
+                    self.render_fn(cams[vi], m, self.bg, self.stage)
+        prev_done = None
         try:
+            ahead = forward_view(0) if len(cams) else None
             for vi, (cam, gt) in enumerate(zip(cams, gts)):
-                pkg = self.render_fn(cam, m, self.bg, self.stage, shs) if self.shared_shs else \
-                    self.render_fn(cam, m, self.bg, self.stage)
-                # (before the backward: the SH tail, which reduces max_radii over the ranks, starts from inside the LAST one)
-                torch.maximum(self.max_radii, pkg["radii"], out=self.max_radii)
-                _field.ACCUMULATE_INTO_GRAD = self.shared_shs     # p.grad are arena views: let the field kernels add into them
-                on_gpu = shs is not None and shs.is_cuda
-                _rast.SH_GRAD_ACCUMULATOR = self.sh_grad if on_gpu else None
-                _rast.SH_GRAD_OVERWRITE = first_sh
-                if on_gpu and self.overlap_sh_reduce and vi == len(cams) - 1:
-                    # The SH tail starts from inside the LAST view's backward.  The SH gradient is complete as soon as the
-                    # rasterizer backward has been queued, but the deformation-MLP backward that follows is a persistent kernel
-                    # with one 230 KB CTA per SM and a static tile schedule: a collective that holds a few SMs while it runs
-                    # delays those CTAs by the collective's whole duration (measured at N = 8: 0.60 -> 1.22 ms).  So the tail
-                    # is started right AFTER the MLP backward has been queued and overlaps the time-plane / spatial HexPlane
-                    # backward, the arena all-reduce and the regulariser instead -- ordinary kernels that share SMs gracefully.
-                    if self.stage == "fine" and hasattr(_field, "AFTER_MLP_BACKWARD"):
-                        _field.AFTER_MLP_BACKWARD = self._sh_tail
-                    else:
-                        _rast.AFTER_SH_ACCUMULATE = self._sh_tail
-                try:
-                    if self.shared_shs and gt.is_cuda:
-                        # fused L1 (utils/loss_utils.py:23-24) + its gradient, then backward from the image
-                        if total is None:          # [loss | one squared-error sum per local view] zeroed by one fill
-                            acc_buf = torch.zeros(1 + len(cams), device=gt.device)
-                            total, self._sse = acc_buf[:1], acc_buf[1:]
-                        img = pkg["render"]
-                        self._sse_numel = img.numel()
-                        d_img = fusedops.l1_loss_and_grad(img, gt, 1.0 / (img.numel() * B), total, self._sse[vi:])
-                        img.backward(d_img)
-                        loss = None
-                    else:
-                        diff = pkg["render"] - gt
-                        loss = diff.abs().mean() / B
-                        sse_plain.append((diff.detach() ** 2).sum().reshape(1))
-                        self._sse_numel = diff.numel()
-                        loss.backward()
-                finally:
-                    _field.ACCUMULATE_INTO_GRAD = False
-                    _rast.SH_GRAD_ACCUMULATOR = None
-                    _rast.SH_GRAD_OVERWRITE = False
-                    _rast.AFTER_SH_ACCUMULATE = None
-                    _field.AFTER_MLP_BACKWARD = None
-                first_sh = False
-                vg = pkg["viewspace_points"].grad
-                if vg is not None:
-                    self.viewspace_grad += vg
-                if loss is not None:
-                    total = loss.detach() if total is None else total + loss.detach()
+                pkg = ahead
+                with on(stream_of(vi)):
+                    if prev_done is not None:
+                        torch.cuda.current_stream().wait_event(prev_done)
+                    # (before the backward: the SH tail, which reduces max_radii over the ranks, starts from inside the LAST one)
+                    torch.maximum(self.max_radii, pkg["radii"], out=self.max_radii)
+                    _field.ACCUMULATE_INTO_GRAD = self.shared_shs     # p.grad are arena views: let the field kernels add into them
+                    on_gpu = shs is not None and shs.is_cuda
+                    _rast.SH_GRAD_ACCUMULATOR = self.sh_grad if on_gpu else None
+                    _rast.SH_GRAD_OVERWRITE = first_sh
+                    if on_gpu and self.overlap_sh_reduce and vi == len(cams) - 1:
+                        # The SH tail starts from inside the LAST view's backward.  The SH gradient is complete as soon as the
+                        # rasterizer backward has been queued, but the deformation-MLP backward that follows is a persistent kernel
+                        # with one 230 KB CTA per SM and a static tile schedule: a collective that holds a few SMs while it runs
+                        # delays those CTAs by the collective's whole duration (measured at N = 8: 0.60 -> 1.22 ms).  So the tail
+                        # is started right AFTER the MLP backward has been queued and overlaps the time-plane / spatial HexPlane
+                        # backward, the arena all-reduce and the regulariser instead -- ordinary kernels that share SMs gracefully.
+                        if self.stage == "fine" and hasattr(_field, "AFTER_MLP_BACKWARD"):
+                            _field.AFTER_MLP_BACKWARD = self._sh_tail
+                        else:
+                            _rast.AFTER_SH_ACCUMULATE = self._sh_tail
+                    try:
+                        if self.shared_shs and gt.is_cuda:
+                            # fused L1 (utils/loss_utils.py:23-24) + its gradient, then backward from the image
+                            if total is None:          # [loss | one squared-error sum per local view] zeroed by one fill
+                                acc_buf = torch.zeros(1 + len(cams), device=gt.device)
+                                total, self._sse = acc_buf[:1], acc_buf[1:]
+                            img = pkg["render"]
+                            self._sse_numel = img.numel()
+                            d_img = fusedops.l1_loss_and_grad(img, gt, 1.0 / (img.numel() * B), total, self._sse[vi:])
+                            img.backward(d_img)
+                            loss = None
+                        else:
+                            diff = pkg["render"] - gt
+                            loss = diff.abs().mean() / B
+                            sse_plain.append((diff.detach() ** 2).sum().reshape(1))
+                            self._sse_numel = diff.numel()
+                            loss.backward()
+                    finally:
+                        _field.ACCUMULATE_INTO_GRAD = False
+                        _rast.SH_GRAD_ACCUMULATOR = None
+                        _rast.SH_GRAD_OVERWRITE = False
+                        _rast.AFTER_SH_ACCUMULATE = None
+                        _field.AFTER_MLP_BACKWARD = None
+                    first_sh = False
+                    vg = pkg["viewspace_points"].grad
+                    if vg is not None:
+                        self.viewspace_grad += vg
+                    if loss is not None:
+                        total = loss.detach() if total is None else total + loss.detach()
+                    if piped:
+                        prev_done = torch.cuda.Event()
+                        prev_done.record()
+                del pkg
+                if vi + 1 < len(cams):
+                    # piped: on the OTHER stream, so it runs under the backward queued just above (its stage-1 read-back is
+                    # the only host wait of a view, and that backward keeps the GPU busy meanwhile)
+                    ahead = forward_view(vi + 1)
+            if piped and prev_done is not None:
+                main.wait_event(prev_done)
         except BaseException:
             _field.drop_shared()               # never leave a half-used spatial product behind (a later render() would reuse it)
             raise
