@@ -326,13 +326,19 @@ def render_block(args, model, device, world, rank, impl, ref_render=None):
                 return _field.shared_spatial_product(model._deformation, model._xyz)
             return contextlib.nullcontext()
 
-        def run_all(consume=None):
+        def run_all(consume=None, streams=2):
             for sel in mine:
-                with shared():          # the spatial half of the HexPlane field once per path, time planes per frame
-                    for c in sel:
-                        r = fn(c)
+                if impl == "b200" and not args.no_shared_spatial:
+                    # the public sequence API: spatial half of the HexPlane field once per path, time planes per frame,
+                    # consecutive frames alternating between two streams
+                    for r in engine.render_frames(sel, model, bg, stage="fine", streams=streams):
                         if consume is not None:
                             consume(r["render"])
+                    continue
+                for c in sel:
+                    r = fn(c)
+                    if consume is not None:
+                        consume(r["render"])
         with torch.no_grad():
             with shared():
                 for c in mine[0][:3]:
@@ -342,6 +348,11 @@ def render_block(args, model, device, world, rank, impl, ref_render=None):
             e0.record(); run_all(); e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
+            ms_one_stream = None
+            if impl == "b200" and not args.no_shared_spatial:          # the same without the two-stream frame pipelining
+                e0.record(); run_all(streams=1); e1.record()
+                torch.cuda.synchronize()
+                ms_one_stream = e0.elapsed_time(e1)
             ms_plain = None
             if impl == "b200" and not args.no_shared_spatial:          # the same frames with the full six-plane pass per frame
                 e0.record()
@@ -396,17 +407,22 @@ def render_block(args, model, device, world, rank, impl, ref_render=None):
         if world > 1:
             import torch.distributed as dist
             t = torch.tensor([ms, wall * 1e3, ms_plain if ms_plain is not None else 0.0,
-                              wall_ring * 1e3 if wall_ring is not None else 0.0], device=device)
+                              wall_ring * 1e3 if wall_ring is not None else 0.0,
+                              ms_one_stream if ms_one_stream is not None else 0.0], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1]) / 1e3
             if ms_plain is not None:
                 ms_plain = float(t[2])
             if wall_ring is not None:
                 wall_ring = float(t[3]) / 1e3
+            if ms_one_stream is not None:
+                ms_one_stream = float(t[4])
         out[tag] = {"fps": n_total / (ms / 1e3), "e2e_fps": n_total / wall, "frames": n_total, "paths": list(paths.keys()),
                     "d2h_bytes_per_frame": 3 * W * H if impl == "b200" else 12 * W * H}
         if ms_plain is not None:
             out[tag]["fps_full_field_per_frame"] = n_total / (ms_plain / 1e3)
+        if ms_one_stream is not None:
+            out[tag]["fps_one_stream"] = n_total / (ms_one_stream / 1e3)
         if wall_ring is not None:
             out[tag]["e2e_fps_ring_copy"] = n_total / wall_ring
     return out

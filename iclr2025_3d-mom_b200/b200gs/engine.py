@@ -213,20 +213,57 @@ def render(cam, pc, bg_color, scaling_modifier=1.0, stage="fine", delta_scale=1,
             "depth": depth}
 
 
-def render_frames(cams, pc, bg_color, stage="fine", **kw):
+def render_frames(cams, pc, bg_color, stage="fine", streams=2, **kw):
     """render() for every camera of a sequence over ONE static model (render_4DGS.py:41-76), as a generator: in the fine
     stage the time-independent half of the HexPlane field is evaluated once for the whole sequence
-    (field.shared_spatial_product) instead of once per frame."""
+    (field.shared_spatial_product) instead of once per frame.
+    streams = 2 (GPU): consecutive frames alternate between two side streams, so that frame i+1's field + preprocess + depth
+    sort run under frame i's binning and compositing (all latency-bound: a frame alone leaves most SMs idle, and the host waits
+    once per frame for the instance count).  The caller's stream waits for a frame before it is yielded, so whatever the
+    consumer queues (output.FrameStore.put, a loss) is ordered after it without knowing about the streams."""
     import contextlib
     from . import field as _field
+    on_gpu = pc.get_xyz.is_cuda
     with contextlib.ExitStack() as stack:
-        if stage == "fine" and pc.get_xyz.is_cuda:
+        if stage == "fine" and on_gpu:
             with torch.no_grad():
                 stack.enter_context(_field.shared_spatial_product(pc._deformation, pc._xyz))
-        for cam in cams:
-            with torch.no_grad():              # per frame, not across the yield: the consumer keeps its own grad mode
-                out = render(cam, pc, bg_color, stage=stage, **kw)
+        pool = None
+        if on_gpu and streams and streams > 1:
+            cur = torch.cuda.current_stream()
+            pool = _frame_streams(pc.get_xyz.device, int(streams))
+            for st in pool:
+                st.wait_stream(cur)            # parameters and the spatial product are ready
+        for i, cam in enumerate(cams):
+            if pool is None:
+                with torch.no_grad():          # per frame, not across the yield: the consumer keeps its own grad mode
+                    out = render(cam, pc, bg_color, stage=stage, **kw)
+            else:
+                st = pool[i % len(pool)]
+                with torch.no_grad(), torch.cuda.stream(st):
+                    out = render(cam, pc, bg_color, stage=stage, **kw)
+                    done = torch.cuda.Event()
+                    done.record(st)
+                cur = torch.cuda.current_stream()
+                cur.wait_event(done)
+                for v in out.values():         # allocated on the side stream, consumed on the caller's
+                    if torch.is_tensor(v) and v.is_cuda:
+                        v.record_stream(cur)
             yield out
+        if pool is not None:                   # nothing of the sequence may outlive the shared product it reads
+            cur = torch.cuda.current_stream()
+            for st in pool:
+                cur.wait_stream(st)
+
+
+_FRAME_STREAMS = {}
+
+
+def _frame_streams(device, n):
+    key = (torch.device(device).index, n)
+    if key not in _FRAME_STREAMS:
+        _FRAME_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+    return _FRAME_STREAMS[key]
 
 
 class HostImageFeeder:
@@ -360,6 +397,10 @@ class ViewParallelTrainer:
         # only the latency-bound forward kernels (sorts, emission, read-back bubble) find idle SMs under the previous backward.
         self.pipeline_views = (os.environ.get("B200GS_PIPELINE_VIEWS", "1") != "0") and self.shared_shs and dev.type == "cuda"
         self.alt = torch.cuda.Stream(device=dev) if self.pipeline_views else None
+        if self.pipeline_views and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            # the leaves' AccumulateGrad nodes live on the stream of the first step's view 0; odd views produce their gradients
+            # on the second stream ON PURPOSE (the engine orders the accumulation; that is all this trainer needs)
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         self.timeline = None                           # bench.py: dict of CUDA events around the phases of the last step
         self._build_arena()
 

@@ -11,7 +11,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_render_frames_matches_frame_by_frame_rendering():
+@pytest.mark.parametrize("streams", [1, 2, 3])
+def test_render_frames_matches_frame_by_frame_rendering(streams):
     from b200gs import engine, synthetic as syn
     dev = torch.device("cuda", 0)
     P, W, H = 50000, 320, 200
@@ -22,12 +23,17 @@ def test_render_frames_matches_frame_by_frame_rendering():
         for p in model._deformation.deformation_net.grid.grids.parameters():
             p.add_(torch.randn_like(p) * 0.01)            # non-trivial time planes
     bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
-    cams = syn.orbit_cameras(4, W, H, device=dev)
+    cams = syn.orbit_cameras(7, W, H, device=dev)
     with torch.no_grad():
         ref = [engine.render(c, model, bg, stage="fine") for c in cams]
-    seq = list(engine.render_frames(cams, model, bg, stage="fine"))
+    # frames alternate over `streams` side streams; the consumer (here: a copy on the caller's stream) needs no stream handling
+    seq = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in f.items()}
+           for f in engine.render_frames(cams, model, bg, stage="fine", streams=streams)]
     from b200gs import field
     assert field._SHARED is None                           # the block cleaned up after itself
+    one = list(engine.render_frames(cams, model, bg, stage="fine", streams=1))
+    for a, b in zip(one, seq):                             # the stream layout changes nothing: bit-identical frames
+        assert torch.equal(a["render"], b["render"]) and torch.equal(a["radii"], b["radii"]) and torch.equal(a["depth"], b["depth"])
     for a, b in zip(ref, seq):
         diff = (a["render"] - b["render"]).abs().amax(dim=0)
         assert float((diff > 1e-4).float().mean()) < 1e-4, float(diff.max())
