@@ -178,18 +178,20 @@ class GaussianState(nn.Module):
 LAST_RASTER_STATE = None      # (R, geomBuffer, binningBuffer, imgBuffer) of the last no-grad render (bench.py counts pairs from it)
 
 
-def render(cam, pc, bg_color, scaling_modifier=1.0, stage="fine", delta_scale=1, debug=False, shs=None):
+def render(cam, pc, bg_color, scaling_modifier=1.0, stage="fine", delta_scale=1, debug=False, shs=None, leaves=None):
     """gaussian_renderer/__init__.py:22-178 for a b200gs.synthetic.SynthCamera-like `cam`.
     `shs`: optional pre-concatenated [P,16,3] SH tensor standing in for `pc.get_features` (the trainer
-    concatenates once per optimiser step instead of once per view; the values are identical)."""
-    means3D = pc.get_xyz
+    concatenates once per optimiser step instead of once per view; the values are identical).
+    `leaves`: optional (xyz, opacity, scaling, rotation) leaf tensors standing in for the model's parameters (same storage,
+    same .grad buffers: the trainer's per-stream aliases, see ViewParallelTrainer._alias_leaves)."""
+    means3D = pc.get_xyz if leaves is None else leaves[0]
     screenspace_points = torch.zeros_like(means3D, requires_grad=True)
     settings = GaussianRasterizationSettings(
         image_height=int(cam.image_height), image_width=int(cam.image_width), tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
         bg=bg_color, scale_modifier=scaling_modifier, viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix,
         sh_degree=pc.active_sh_degree, campos=cam.campos, prefiltered=False, debug=debug)
     rasterizer = GaussianRasterizer(raster_settings=settings)
-    opacity, scales, rotations = pc._opacity, pc._scaling, pc._rotation
+    opacity, scales, rotations = (pc._opacity, pc._scaling, pc._rotation) if leaves is None else leaves[1:]
     if shs is None:
         shs = pc.get_features
     if stage == "coarse":
@@ -381,7 +383,8 @@ class ViewParallelTrainer:
         self.rank = rank
         # our own render() takes the per-step SH tensor; an injected render_fn keeps the 4-argument form
         self.shared_shs = (render_fn is None) if shared_shs is None else bool(shared_shs)
-        self.render_fn = render_fn or (lambda cam, m, bg, st, shs=None: render(cam, m, bg, stage=st, shs=shs))
+        self.render_fn = render_fn or (lambda cam, m, bg, st, shs=None, leaves=None: render(cam, m, bg, stage=st, shs=shs, leaves=leaves))
+        self._own_render = render_fn is None
         dev = model.get_xyz.device
         # SH tail on a side stream, started from inside the last view's backward (B200GS_OVERLAP_SH_REDUCE=0: after the loop,
         # on the main stream -- same collectives, same order, nothing overlapped)
@@ -449,6 +452,22 @@ class ViewParallelTrainer:
         self.max_radii.zero_()
         for p, v in zip(self.arena_params, self.views):
             p.grad = v
+
+    def _alias_leaves(self):
+        """Second set of leaf tensors over the SAME storage and the SAME .grad buffers as the four per-Gaussian parameters the
+        views reach through autograd (xyz, opacity, scaling, rotation), for the views rendered on the second stream.  A leaf's
+        AccumulateGrad node runs on ONE stream -- the one its first forward use was recorded on -- so with a single set of
+        leaves every odd view's backward (second stream) would hand its gradients to the first stream for accumulation, and the
+        next view's forward, queued on that first stream, would wait for the end of that backward: no overlap for half of the
+        views.  With its own leaves each stream accumulates by itself; the order of the adds is still the view order (the
+        backwards are chained by events)."""
+        m = self.model
+        out = []
+        for p in (m._xyz, m._opacity, m._scaling, m._rotation):
+            a = p.detach().requires_grad_(p.requires_grad)
+            a.grad = p.grad
+            out.append(a)
+        return tuple(out)
 
     def local_views(self, n_global):
         """Indices of the global batch this rank renders: view b goes to rank b mod world_size."""
@@ -540,8 +559,12 @@ class ViewParallelTrainer:
         stream_of = (lambda vi: (main, self.alt)[vi & 1]) if piped else (lambda vi: None)
         on = lambda st: torch.cuda.stream(st) if st is not None else contextlib.nullcontext()
 
+        alias = self._alias_leaves() if piped and self._own_render else None
+
         def forward_view(vi):
             with on(stream_of(vi)):
+                if alias is not None and (vi & 1):
+                    return self.render_fn(cams[vi], m, self.bg, self.stage, shs, alias)
                 return self.render_fn(cams[vi], m, self.bg, self.stage, shs) if self.shared_shs else \
                     self.render_fn(cams[vi], m, self.bg, self.stage)
         prev_done = None
