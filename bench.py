@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--scale-mu", type=float, default=0.010, help="S-coarse 0.010 / S-fine 0.004 (SURVEY.md 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--render-frames", type=int, default=60, help="frames per camera path of the render block (0 = skip)")
+    ap.add_argument("--render-streams", type=int, default=2, help="streams engine.render_frames alternates the frames of a path over")
     ap.add_argument("--no-raster-only", action="store_true", help="skip the config-2 rasterizer-only block")
     ap.add_argument("--no-c5", action="store_true", help="skip the config-5 stress block (5M Gaussians at 3840x2160, N = 1 only)")
     ap.add_argument("--no-launcher-path", action="store_true", help="skip the block that runs the reference's unchanged train_4DGS.py through the launcher")
@@ -326,7 +327,7 @@ def render_block(args, model, device, world, rank, impl, ref_render=None):
                 return _field.shared_spatial_product(model._deformation, model._xyz)
             return contextlib.nullcontext()
 
-        def run_all(consume=None, streams=2):
+        def run_all(consume=None, streams=args.render_streams):
             for sel in mine:
                 if impl == "b200" and not args.no_shared_spatial:
                     # the public sequence API: spatial half of the HexPlane field once per path, time planes per frame,
@@ -343,6 +344,9 @@ def render_block(args, model, device, world, rank, impl, ref_render=None):
             with shared():
                 for c in mine[0][:3]:
                     fn(c)
+            if impl == "b200" and not args.no_shared_spatial:      # warm both streams' allocator pools as well
+                for _ in engine.render_frames(mine[0][:8], model, bg, stage="fine", streams=args.render_streams):
+                    pass
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); run_all(); e1.record()
