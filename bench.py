@@ -347,7 +347,11 @@ def render_block(args, model, device, world, rank, impl, ref_render=None):
             if impl == "b200" and not args.no_shared_spatial:      # warm both streams' allocator pools as well
                 for _ in engine.render_frames(mine[0][:8], model, bg, stage="fine", streams=args.render_streams):
                     pass
-            torch.cuda.synchronize()
+            run_all()                                  # one untimed pass over every frame: the instance counts (binning buffers) grow
+            torch.cuda.synchronize()                   # along a path, and the caching allocator should have seen the largest
+            if world > 1:
+                import torch.distributed as _dist
+                _dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); run_all(); e1.record()
             torch.cuda.synchronize()
