@@ -595,17 +595,24 @@ def launcher_path_block(args):
                    B200GS_LAUNCHER_LOG="1")
         for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
             env.pop(k, None)
-        t0 = time.perf_counter()
-        r = subprocess.run([sys.executable, "-m", "b200gs.launcher", "--reference", ref, "train_4DGS.py", "--input_dir", out, "--configs", cfg,
-                            "--expname", "synthetic", "--model_path", out, "--port", "6124", "--save_iterations", "120", "--test_iterations", "100000",
-                            "--video_iterations", "100000", "--quiet"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
-        wall = time.perf_counter() - t0
-        m = re.search(r"\[b200gs\] launcher summary: (.*)", r.stdout + r.stderr)
-        if r.returncode != 0 or not m:
-            return {"failed": (r.stdout + r.stderr)[-600:]}
-        summary = dict(kv.split("=") for kv in m.group(1).split())
-        return {"script": "train_4DGS.py (unchanged, baseline/_ref) via b200gs.launcher", "iters_per_s": float(summary["iters_per_s"]),
-                "view_iters_per_s": 2 * float(summary["iters_per_s"]), "iterations": int(summary["adam_steps"]), "batch_size": 2,
+        runs = []
+        for rep in range(3):          # a 159-iteration run lasts 1-2 s: one stray stall moves it by tens of percent (88-165 seen), so the median of 3
+            t0 = time.perf_counter()
+            r = subprocess.run([sys.executable, "-m", "b200gs.launcher", "--reference", ref, "train_4DGS.py", "--input_dir", out, "--configs", cfg,
+                                "--expname", "synthetic", "--model_path", out, "--port", str(6124 + rep), "--save_iterations", "120",
+                                "--test_iterations", "100000", "--video_iterations", "100000", "--quiet"],
+                               cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+            wall = time.perf_counter() - t0
+            m = re.search(r"\[b200gs\] launcher summary: (.*)", r.stdout + r.stderr)
+            if r.returncode != 0 or not m:
+                return {"failed": (r.stdout + r.stderr)[-600:]}
+            summary = dict(kv.split("=") for kv in m.group(1).split())
+            runs.append((float(summary["iters_per_s"]), wall, summary))
+        runs.sort(key=lambda t: t[0])
+        ips, wall, summary = runs[len(runs) // 2]
+        return {"script": "train_4DGS.py (unchanged, baseline/_ref) via b200gs.launcher", "iters_per_s": ips,
+                "iters_per_s_runs": [round(t[0], 1) for t in runs], "how": "median of 3 process runs",
+                "view_iters_per_s": 2 * ips, "iterations": int(summary["adam_steps"]), "batch_size": 2,
                 "points_initial": 210000, "image": "320x192", "process_wall_s": round(wall, 2),
                 "densify_cat_events": int(summary["densify_cat_events"]), "prune_events": int(summary["prune_events"]),
                 "time_row_forward_calls": int(summary["time_row_forward_calls"]),
@@ -796,7 +803,7 @@ def run_steps_e2e(trainer, cams, host_images, n_global, steps, device, barrier, 
     if impl == "b200":
         feeder = engine.HostImageFeeder(host_images, device)
         ring = engine.LossRing(depth=4)
-        lag = 1 if len(cams) > 1 else 2
+        lag = 1 if len(cams) > 2 else 2
         feeder.prefetch()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_wall = None
@@ -815,7 +822,7 @@ def run_steps_e2e(trainer, cams, host_images, n_global, steps, device, barrier, 
             feeder.release()
             ring.push(loss)
             # every step's loss is read on the host, `lag` steps after it was queued: one step late while a step is long (N <= 4),
-            # two when a rank's step is a single ~5 ms view and the host needs that much queue depth to hide its own jitter
+            # two when a rank's step is one or two views (5-7 ms) and the host needs that much queue depth to hide its own jitter
             v = ring.read(lag=lag)
             last = v if v is not None else last
             if k >= 0:
@@ -944,12 +951,16 @@ def _main():
         calls, phases = {}, {}
         if impl == "b200":
             from b200gs import _lib as _b200lib
+            # (with the views serialised on ONE stream: under view pipelining a kernel shares the SMs with the other stream's
+            #  forward and its event-to-event time is no longer its own; `ms_per_step_serial_instrumented` is this pass)
+            piped, trainer.pipeline_views = trainer.pipeline_views, False
             with _b200lib.CallTimer() as timer:
                 _b200lib.lib().b200gs_profile_enable(1)
                 ms_instr = run_steps(trainer, cams, gts_dev, n_global, args.steps, barrier, max_over_ranks)
                 calls = timer.summary()
                 phases = read_phases()
                 _b200lib.lib().b200gs_profile_enable(0)
+            trainer.pipeline_views = piped
             adam_t = calls.get("b200gs_adam_multi", {}).get("ms_avg", 0.0)
         else:
             ms_instr = ms
@@ -1102,7 +1113,7 @@ def _main():
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e * 1e3 / args.steps,
                 "warmup_steps": 2, "slowest_step_wall_ms": e2e_slowest, "last_loss": last,
                 "how": ("uint8 HWC ground truth (the dataset's own format) uploaded from pinned memory on a side stream one step ahead, converted "
-                        "inside the L1 kernel; loss copied to a pinned ring every step and read one step late (two when a rank's step is a single view)") if impl == "b200" else
+                        "inside the L1 kernel; loss copied to a pinned ring every step and read one step late (two when a rank's step is one or two views)") if impl == "b200" else
                        "float32 CHW ground truth uploaded per step, float(loss) per step (train_4DGS.py:194, :236)"},
         "clocks": clk.summary(),
         "gpu_launches": int(round(launches_per_step * args.steps)) if launches_per_step else 0,
@@ -1124,6 +1135,8 @@ def _main():
             res["roofline"]["compulsory_frac"] = round(compulsory / (dom["ms_avg"] * 1e-3) / 1e9 / hbm, 4)
         res["kernels"] = kernels
         res["kernels_pass_ms_per_step"] = ms_instr / args.steps
+        res["kernels_pass"] = ("the per-kernel pass brackets every entry point with CUDA events and runs the views of a step one after the other "
+                               "on one stream (the timed headline pipelines them over two), so each duration is the kernel's own")
         res["reference_sort_bytes_per_view"] = ref_sort_bytes
         if timeline:
             res["timeline"] = timeline
