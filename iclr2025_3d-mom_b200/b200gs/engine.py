@@ -400,6 +400,7 @@ class ViewParallelTrainer:
         # only the latency-bound forward kernels (sorts, emission, read-back bubble) find idle SMs under the previous backward.
         self.pipeline_views = (os.environ.get("B200GS_PIPELINE_VIEWS", "1") != "0") and self.shared_shs and dev.type == "cuda"
         self.alt = torch.cuda.Stream(device=dev) if self.pipeline_views else None
+        self.pipelined_mlp_sms = int(os.environ.get("B200GS_PIPELINED_MLP_SMS", "120"))      # 0: all SMs
         if self.pipeline_views and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
             # the leaves' AccumulateGrad nodes live on the stream of the first step's view 0; odd views produce their gradients
             # on the second stream ON PURPOSE (the engine orders the accumulation; that is all this trainer needs)
@@ -560,6 +561,13 @@ class ViewParallelTrainer:
         on = lambda st: torch.cuda.stream(st) if st is not None else contextlib.nullcontext()
 
         alias = self._alias_leaves() if piped and self._own_render else None
+        if piped and self.pipelined_mlp_sms:
+            # the deformation-MLP kernels are persistent, one CTA per SM with 157 / 230 KB of shared memory: while they own every SM
+            # nothing of the other stream's forward can be resident.  Leaving them 120 of the 148 SMs costs them little (they are
+            # latency-bound) and lets the sorts / emission / preprocess of the next view run next to them (377 -> 383 view-iters/s).
+            from . import _lib
+            for name in (b"mlp_bwd_sms", b"mlp_fwd_sms"):
+                _lib.lib().b200gs_set_option(name, int(self.pipelined_mlp_sms))
 
         def forward_view(vi):
             with on(stream_of(vi)):
@@ -634,6 +642,11 @@ class ViewParallelTrainer:
         except BaseException:
             _field.drop_shared()               # never leave a half-used spatial product behind (a later render() would reuse it)
             raise
+        finally:
+            if piped and self.pipelined_mlp_sms:
+                from . import _lib
+                for name in (b"mlp_bwd_sms", b"mlp_fwd_sms"):
+                    _lib.lib().b200gs_set_option(name, 0)
         if sse_plain:
             self._sse = torch.cat(sse_plain)
         self._mark("views_done")

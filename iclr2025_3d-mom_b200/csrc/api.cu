@@ -19,6 +19,8 @@ static int env_int(const char* name, int dflt) { const char* e = getenv(name); r
 int g_opt_mlp_bwd_v2 = env_int("B200GS_MLP_BWD_V2", 87);
 int g_opt_mlp_fwd_elect = env_int("B200GS_MLP_FWD_ELECT", 2);
 int g_opt_hexplane_time_bwd = env_int("B200GS_HEXPLANE_TIME_BWD", 2);    // 0.417 -> 0.354 ms (profiles/r2a_hexplane_time_check.txt)
+int g_opt_mlp_bwd_sms = env_int("B200GS_MLP_BWD_SMS", 0);
+int g_opt_mlp_fwd_sms = env_int("B200GS_MLP_FWD_SMS", 0);
 int g_opt_sort_ballot_rank = env_int("B200GS_SORT_BALLOT_RANK", 1);    // 103 -> 87 us per 1M-pair 32-bit sort, 96 -> 79 us per 2.4M-pair 12-bit sort (profiles/r3h_sort_check.txt)
 int g_opt_lookback_parallel = env_int("B200GS_LOOKBACK_PARALLEL", 1);    // 111 -> 103 us per 1M-pair sort (profiles/r2a_sort_check.txt)
 int g_opt_hexplane_time_fwd = env_int("B200GS_HEXPLANE_TIME_FWD", 2);    // 0.134 -> 0.112 ms, bit-identical
@@ -146,6 +148,8 @@ int b200gs_set_option(const char* name, int value)
     }
     if (name && !strcmp(name, "lookback_parallel")) { b200gs::g_opt_lookback_parallel = value; return 0; }
     if (name && !strcmp(name, "sort_ballot_rank")) { b200gs::g_opt_sort_ballot_rank = value; return 0; }
+    if (name && !strcmp(name, "mlp_bwd_sms")) { b200gs::g_opt_mlp_bwd_sms = value; return 0; }
+    if (name && !strcmp(name, "mlp_fwd_sms")) { b200gs::g_opt_mlp_fwd_sms = value; return 0; }
     if (name && !strcmp(name, "hexplane_time_fwd")) { b200gs::g_opt_hexplane_time_fwd = value; return 0; }
     if (name && !strcmp(name, "composite_pairs")) { b200gs::g_opt_composite_pairs = value; return 0; }
     set_error("b200gs_set_option: unknown option '%s'", name ? name : "(null)");
@@ -159,6 +163,8 @@ int b200gs_get_option(const char* name)
     if (name && !strcmp(name, "mlp_bwd_ablate")) return b200gs::g_opt_mlp_bwd_ablate;
     if (name && !strcmp(name, "lookback_parallel")) return b200gs::g_opt_lookback_parallel;
     if (name && !strcmp(name, "sort_ballot_rank")) return b200gs::g_opt_sort_ballot_rank;
+    if (name && !strcmp(name, "mlp_bwd_sms")) return b200gs::g_opt_mlp_bwd_sms;
+    if (name && !strcmp(name, "mlp_fwd_sms")) return b200gs::g_opt_mlp_fwd_sms;
     if (name && !strcmp(name, "hexplane_time_fwd")) return b200gs::g_opt_hexplane_time_fwd;
     if (name && !strcmp(name, "composite_pairs")) return b200gs::g_opt_composite_pairs;
     return -1;

@@ -595,7 +595,8 @@ int deform_mlp_backward_tc5(const b200gs_mlp_weights* w, const b200gs_mlp_grads*
     a.w = *w; a.gw = *gw; a.P = P; a.feat = feat; a.saved = saved; a.d_pts = d_pts; a.d_scales = d_scales; a.d_rot = d_rot;
     a.d_feat = d_feat; a.dy_sbo = 512u;
     const long long nblocks = (P + tc5::ROWS - 1) / tc5::ROWS;
-    const int grid = (int)(nblocks < NUM_SMS ? nblocks : NUM_SMS);
+    const int sms = g_opt_mlp_bwd_sms > 0 && g_opt_mlp_bwd_sms < NUM_SMS ? g_opt_mlp_bwd_sms : NUM_SMS;          // option: leave a few SMs to a concurrent stream
+    const int grid = (int)(nblocks < sms ? nblocks : sms);
     const size_t smem = tc5::bwd_smem();
     // experimental variant (see the kernel's header comment): opt-in until it has been measured on the GPU; needs 16-byte
     // aligned W1 / W2 gradient rows for its 128-bit REDs

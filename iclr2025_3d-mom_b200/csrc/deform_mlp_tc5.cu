@@ -512,7 +512,8 @@ int deform_mlp_forward_tc5(const b200gs_mlp_weights* w, long long P, const float
     a.frame_num = frame_num; a.frame_num_dev = frame_num_dev; a.delta_scale = delta_scale; a.pts_out = pts_out;
     a.scales_out = scales_out; a.rot_out = rot_out; a.saved = saved;
     const long long nblocks = (P + tc5::ROWS - 1) / tc5::ROWS;
-    const int grid = (int)(nblocks < NUM_SMS ? nblocks : NUM_SMS);
+    const int sms = g_opt_mlp_fwd_sms > 0 && g_opt_mlp_fwd_sms < NUM_SMS ? g_opt_mlp_fwd_sms : NUM_SMS;          // option: leave a few SMs to a concurrent stream
+    const int grid = (int)(nblocks < sms ? nblocks : sms);
     const size_t smem = tc5::fwd_smem(w->feat_dim);
     if (!saved && !(w->w2[0] && w->w2[1] && w->w2[2])) {
         set_error("deform_mlp_forward: saved == NULL (inference, nothing stashed) needs all three heads enabled");

@@ -49,6 +49,9 @@ int b200gs_version(void);
  *   "sort_ballot_rank" radix sort passes (default 1): the lanes of a warp that hold the same digit are found with one ballot per
  *                    digit bit (4 or 8 VOTE + LOP3, independent across a thread's 16 keys) instead of MATCH.ANY, whose latency was
  *                    the kernel's top stall: 103 -> 87 us per 1M-pair 32-bit sort, 96 -> 79 us per 2.4M-pair 12-bit sort; identical results
+ *   "mlp_fwd_sms" / "mlp_bwd_sms" (default 0 = all 148): CTAs of the persistent deformation-MLP kernels.  The view-pipelining trainer
+ *                    sets 120 around a step so that the other stream's sorts / emission / preprocess find free SMs next to them
+ *                    (377 -> 383 view-iterations/s; 96: slower again); same results up to the order of the weight-gradient flushes
  *   "composite_pairs" compositing backward (default 1): a lane owns TWO pixels of an 8x8 warp patch and carries their state as
  *                    packed FP32 pairs (FFMA2 / FMUL2 / FADD2), the gradient butterfly is paid once per 64 pixels: 0.765 -> 0.608 ms
  *                    per 1M-Gaussian 1280x720 view; 0 = the one-pixel-per-lane kernel (rast_backward.cu)
