@@ -401,10 +401,12 @@ class ViewParallelTrainer:
         self.pipeline_views = (os.environ.get("B200GS_PIPELINE_VIEWS", "1") != "0") and self.shared_shs and dev.type == "cuda"
         self.alt = torch.cuda.Stream(device=dev) if self.pipeline_views else None
         self.pipelined_mlp_sms = int(os.environ.get("B200GS_PIPELINED_MLP_SMS", "120"))      # 0: all SMs
-        if self.pipeline_views and hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
-            # the leaves' AccumulateGrad nodes live on the stream of the first step's view 0; odd views produce their gradients
-            # on the second stream ON PURPOSE (the engine orders the accumulation; that is all this trainer needs)
-            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        # SH tail from the rasterizer backward (instead of after the MLP backward) when the rank pipelines several views: the MLP
+        # backward is confined to `pipelined_mlp_sms` SMs then, so the collective's CTAs no longer displace its persistent ones
+        # (4 views per rank, N = 2: 661 -> 672 view-iters/s; 8 per rank, weak N = 4: 1,451 -> 1,496).  With one or two views per
+        # rank the late start stays better (N = 8: 1,607 vs 1,575; N = 4: 1,102 vs 1,085): the confined MLP backward and the
+        # collective's traffic slow the only views there are.  B200GS_SH_TAIL_EARLY=0/1 forces it.
+        self.sh_tail_early = os.environ.get("B200GS_SH_TAIL_EARLY", "auto")
         self.timeline = None                           # bench.py: dict of CUDA events around the phases of the last step
         self._build_arena()
 
@@ -561,7 +563,9 @@ class ViewParallelTrainer:
         on = lambda st: torch.cuda.stream(st) if st is not None else contextlib.nullcontext()
 
         alias = self._alias_leaves() if piped and self._own_render else None
-        if piped and self.pipelined_mlp_sms:
+        early = (piped and self.world_size > 1 and len(cams) >= 4) if self.sh_tail_early == "auto" else (self.sh_tail_early != "0" and self.world_size > 1)
+        confine = (piped or early) and self.pipelined_mlp_sms
+        if confine:
             # the deformation-MLP kernels are persistent, one CTA per SM with 157 / 230 KB of shared memory: while they own every SM
             # nothing of the other stream's forward can be resident.  Leaving them 120 of the 148 SMs costs them little (they are
             # latency-bound) and lets the sorts / emission / preprocess of the next view run next to them (377 -> 383 view-iters/s).
@@ -596,7 +600,7 @@ class ViewParallelTrainer:
                         # delays those CTAs by the collective's whole duration (measured at N = 8: 0.60 -> 1.22 ms).  So the tail
                         # is started right AFTER the MLP backward has been queued and overlaps the time-plane / spatial HexPlane
                         # backward, the arena all-reduce and the regulariser instead -- ordinary kernels that share SMs gracefully.
-                        if self.stage == "fine" and hasattr(_field, "AFTER_MLP_BACKWARD"):
+                        if self.stage == "fine" and hasattr(_field, "AFTER_MLP_BACKWARD") and not early:
                             _field.AFTER_MLP_BACKWARD = self._sh_tail
                         else:
                             _rast.AFTER_SH_ACCUMULATE = self._sh_tail
@@ -643,7 +647,7 @@ class ViewParallelTrainer:
             _field.drop_shared()               # never leave a half-used spatial product behind (a later render() would reuse it)
             raise
         finally:
-            if piped and self.pipelined_mlp_sms:
+            if confine:
                 from . import _lib
                 for name in (b"mlp_bwd_sms", b"mlp_fwd_sms"):
                     _lib.lib().b200gs_set_option(name, 0)
