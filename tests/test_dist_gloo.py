@@ -57,6 +57,9 @@ def _run(rank, world, port, ret):
     out = {k: v.detach().clone() for k, v in model.state_dict().items()}
     out["viewspace"] = tr.viewspace_grad.clone(); out["max_radii"] = tr.max_radii.clone()
     out["timenet_grad_is_none"] = model._deformation["timenet_w"].grad is None
+    # utils/image_utils.py:psnr of the LAST step's local views, as train_4DGS.py:212 logs it (evaluated before that step's update)
+    out["psnr_local"] = tr.psnr().detach().clone()
+    out["psnr_views"] = torch.tensor(mine)
     ret[rank if world > 1 else -1] = out
     if world > 1:
         dist.destroy_process_group()
@@ -70,8 +73,11 @@ def test_two_rank_step_equals_single_process():
     mp.spawn(_run, args=(2, port, ret), nprocs=2, join=True)
     single, r0, r1 = ret[-1], ret[0], ret[1]
     assert single["timenet_grad_is_none"] and r0["timenet_grad_is_none"]
+    # the per-rank PSNR means combine to the single-process mean over the batch (2 views each)
+    assert torch.allclose((r0["psnr_local"] + r1["psnr_local"]) / 2, single["psnr_local"], rtol=1e-5)
+    assert r0["psnr_views"].tolist() == [0, 2] and r1["psnr_views"].tolist() == [1, 3]
     for k in single:
-        if k == "timenet_grad_is_none":
+        if k in ("timenet_grad_is_none", "psnr_local", "psnr_views"):
             continue
         assert torch.equal(r0[k], r1[k]), f"ranks diverged on {k}"                  # replicas stay identical
         assert torch.allclose(single[k].float(), r0[k].float(), rtol=1e-5, atol=1e-7), k
