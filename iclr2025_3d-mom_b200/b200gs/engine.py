@@ -400,6 +400,10 @@ class ViewParallelTrainer:
         # only the latency-bound forward kernels (sorts, emission, read-back bubble) find idle SMs under the previous backward.
         self.pipeline_views = (os.environ.get("B200GS_PIPELINE_VIEWS", "1") != "0") and self.shared_shs and dev.type == "cuda"
         self.alt = torch.cuda.Stream(device=dev) if self.pipeline_views else None
+        # streams the views rotate over (2: forward of view i+1 under the backward of view i; 3: view i+2's forward is queued too --
+        # measured: 378 / 361-372 / 356 view-iters/s with 2 / 3 / 4 streams, so 2)
+        self.pipeline_streams = max(2, int(os.environ.get("B200GS_PIPELINE_STREAMS", "2")))
+        self.alts = ([self.alt] + [torch.cuda.Stream(device=dev) for _ in range(self.pipeline_streams - 2)]) if self.pipeline_views else []
         self.pipelined_mlp_sms = int(os.environ.get("B200GS_PIPELINED_MLP_SMS", "120"))      # 0: all SMs
         # SH tail from the rasterizer backward (instead of after the MLP backward) when the rank pipelines several views: the MLP
         # backward is confined to `pipelined_mlp_sms` SMs then, so the collective's CTAs no longer displace its persistent ones
@@ -558,11 +562,14 @@ class ViewParallelTrainer:
         piped = self.pipeline_views and len(cams) > 1 and m._xyz.is_cuda
         main = torch.cuda.current_stream() if piped else None
         if piped:
-            self.alt.wait_stream(main)                 # shs, the spatial product and this step's images are ready
-        stream_of = (lambda vi: (main, self.alt)[vi & 1]) if piped else (lambda vi: None)
+            for st in self.alts:
+                st.wait_stream(main)                   # shs, the spatial product and this step's images are ready
+        ring = ([main] + self.alts) if piped else [None]
+        stream_of = lambda vi: ring[vi % len(ring)]
         on = lambda st: torch.cuda.stream(st) if st is not None else contextlib.nullcontext()
 
-        alias = self._alias_leaves() if piped and self._own_render else None
+        alias = [None] + [self._alias_leaves() for _ in self.alts] if piped and self._own_render else None
+        depth = len(ring) - 1 if piped else 1          # forwards queued ahead of the backward in progress
         early = (piped and self.world_size > 1 and len(cams) >= 4) if self.sh_tail_early == "auto" else (self.sh_tail_early != "0" and self.world_size > 1)
         confine = (piped or early) and self.pipelined_mlp_sms
         if confine:
@@ -575,15 +582,15 @@ class ViewParallelTrainer:
 
         def forward_view(vi):
             with on(stream_of(vi)):
-                if alias is not None and (vi & 1):
-                    return self.render_fn(cams[vi], m, self.bg, self.stage, shs, alias)
+                if alias is not None and alias[vi % len(ring)] is not None:
+                    return self.render_fn(cams[vi], m, self.bg, self.stage, shs, alias[vi % len(ring)])
                 return self.render_fn(cams[vi], m, self.bg, self.stage, shs) if self.shared_shs else \
                     self.render_fn(cams[vi], m, self.bg, self.stage)
         prev_done = None
         try:
-            ahead = forward_view(0) if len(cams) else None
+            ahead = [forward_view(k) for k in range(min(depth, len(cams)))]
             for vi, (cam, gt) in enumerate(zip(cams, gts)):
-                pkg = ahead
+                pkg = ahead.pop(0)
                 with on(stream_of(vi)):
                     if prev_done is not None:
                         torch.cuda.current_stream().wait_event(prev_done)
@@ -637,10 +644,10 @@ class ViewParallelTrainer:
                         prev_done = torch.cuda.Event()
                         prev_done.record()
                 del pkg
-                if vi + 1 < len(cams):
-                    # piped: on the OTHER stream, so it runs under the backward queued just above (its stage-1 read-back is
+                if vi + depth < len(cams):
+                    # piped: on ANOTHER stream, so it runs under the backward queued just above (its stage-1 read-back is
                     # the only host wait of a view, and that backward keeps the GPU busy meanwhile)
-                    ahead = forward_view(vi + 1)
+                    ahead.append(forward_view(vi + depth))
             if piped and prev_done is not None:
                 main.wait_event(prev_done)
         except BaseException:
