@@ -53,3 +53,32 @@ def test_scaling_lines_are_weak_scaling_of_the_same_workload():
     assert all(l["scaling"] == "weak" and l["config"]["views_per_gpu"] == lines[0]["config"]["views_per_gpu"] for l in lines)
     by_n = {l["n_gpus"]: l["value"] for l in lines}
     assert all(by_n[n] > 0.85 * n * by_n[1] for n in by_n)
+
+
+def test_round2_lines_schema_and_strong_scaling_of_the_named_batch():
+    """The final round-2 lines: BASELINE.json config 3 as written (global batch 8 sharded over N GPUs, strong scaling) with the
+    weak block next to it, the reference arm of the same visit, and the extra blocks DESIGN.md §6 quotes."""
+    d, path = _latest("r4q_bench_b200_n1.json")
+    r, _ = _latest("r4q_bench_reference.json")
+    for k in BASE + ["cpu_baseline", "kernels", "timeline", "render", "raster_only", "stress_c5", "launcher_path"]:
+        assert k in d, (k, path)
+    for k in BASE:
+        assert k in r, k
+    assert d["scaling"] == "strong" and d["config"]["global_batch"] == 8 and r["impl"] == "reference"
+    assert d["config"]["kernel_options"]["sort_ballot_rank"] == 1 and d["config"]["kernel_options"]["mlp_bwd_v2"] == 87
+    assert d["metric"] == r["metric"] and d["unit"] == r["unit"] and d["config"]["workload"] == r["config"]["workload"]
+    assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 8 * 3 * 720 * 1280
+    assert d["roofline"]["traffic"] and "ncu --set full" in d["roofline"]["traffic_source"]
+    assert d["value"] > 10 * r["value"] and d["e2e"]["value"] > 10 * r["e2e"]["value"]
+    assert d["cpu_baseline"]["c1"]["config"].startswith("C1")
+    for tag in ("1920x1080", "1280x720"):
+        assert d["render"][tag]["e2e_fps"] > 5 * r["render"][tag]["e2e_fps"]
+    lines = {}
+    for pat in ("r4o_bench_b200_n2.json", "r4n_bench_b200_n4_early_sh_tail.json", "r4r_bench_b200_n8.json"):
+        l, _ = _latest(pat)
+        lines[l["n_gpus"]] = l
+    for n, l in lines.items():
+        assert l["scaling"] == "strong" and l["config"]["global_batch"] == 8 and l["config"]["views_per_gpu"] == 8 // n
+        assert l["weak"]["scaling"] == "weak" and l["weak"]["views_per_gpu"] == 8 and l["weak"]["global_batch"] == 8 * n
+        assert l["value"] > d["value"] and l["weak"]["value"] > 0.9 * n * d["value"]
+        assert not set(l["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
